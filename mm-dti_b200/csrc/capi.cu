@@ -1,0 +1,17 @@
+// Library-wide C ABI plumbing: version and thread-local error text.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+
+static thread_local char g_err[512] = "";
+
+void mmdti_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int mmdti_version(void) { return 100; }
+extern "C" const char* mmdti_last_error(void) { return g_err; }

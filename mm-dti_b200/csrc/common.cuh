@@ -1,0 +1,171 @@
+// Shared device/host helpers for the mmdti_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <type_traits>
+
+#include "../../include/mmdti_b200.h"
+
+// ---------------------------------------------------------------- error plumbing
+void mmdti_set_error(const char* fmt, ...);
+#define MMDTI_REQUIRE(cond, ...)              \
+    do {                                      \
+        if (!(cond)) {                        \
+            mmdti_set_error(__VA_ARGS__);     \
+            return MMDTI_ERR_ARG;             \
+        }                                     \
+    } while (0)
+#define MMDTI_CUDA_OK(call)                                                          \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            mmdti_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                     \
+            return MMDTI_ERR_CUDA;                                                   \
+        }                                                                            \
+    } while (0)
+#define MMDTI_LAUNCH_OK()                                                              \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) {                                                      \
+            mmdti_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                       \
+            return MMDTI_ERR_CUDA;                                                     \
+        }                                                                              \
+    } while (0)
+
+static inline bool mmdti_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---------------------------------------------------------------- type helpers
+typedef __nv_bfloat16 bf16;
+
+template <typename T> struct TypeOf;
+template <> struct TypeOf<float> { static constexpr int id = MMDTI_F32; };
+template <> struct TypeOf<bf16> { static constexpr int id = MMDTI_BF16; };
+template <> struct TypeOf<__half> { static constexpr int id = MMDTI_F16; };
+
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+    return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+}
+// pack / unpack two 16-bit pair-tensor elements of type TP
+template <typename TP> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<bf16>(float lo, float hi) { return pack_bf16(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) { return pack_f16(lo, hi); }
+template <typename TP> __device__ __forceinline__ float2 unpack2(uint32_t u);
+template <> __device__ __forceinline__ float2 unpack2<bf16>(uint32_t u) { return unpack_bf16(u); }
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return unpack_f16(u); }
+
+// ---------------------------------------------------------------- warp helpers
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    return v;
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------- tensor-core wrappers
+// D(16x8,f32) += A(16x8,bf16,row) * B(8x8,bf16,col)
+__device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(b0));
+}
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                               uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                                  const void* smem_row_ptr) {
+    uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* smem_row_ptr) {
+    uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n"
+                 : "=r"(r0), "=r"(r1)
+                 : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                            const void* smem_row_ptr) {
+    uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(a));
+}
+
+// ---------------------------------------------------------------- counter-based dropout RNG
+// lowbias32 avalanche hash; the keep decision of element (stream, row, col) depends only on
+// (seed, stream, row, col), so forward, backward and the debug dump agree under any tiling.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t rng_stream_key(unsigned long long seed, uint32_t stream) {
+    uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+    return mix32(lo ^ mix32(stream * 0x9E3779B1U + hi + 0x85EBCA6BU));
+}
+// 32 random bits shared by the column pair (col & ~1, col | 1) of `row`; low 16 bits belong to
+// the even column, high 16 bits to the odd one.  rows < 2^21, cols < 2^11.
+__device__ __forceinline__ uint32_t rng_pair_bits(uint32_t key, uint32_t row, uint32_t col) {
+    return mix32(key ^ ((row << 10) | (col >> 1)));
+}
+__device__ __forceinline__ bool rng_keep(uint32_t bits, uint32_t col, uint32_t thresh16) {
+    uint32_t r = (col & 1u) ? (bits >> 16) : (bits & 0xffffu);
+    return r >= thresh16;
+}
+
+// exact unsigned division by a small runtime constant: q = n / d for n*d < 2^32
+struct FastDiv {
+    uint32_t d, m;
+    __host__ __device__ explicit FastDiv(uint32_t d_) : d(d_), m(d_ > 1 ? (0xFFFFFFFFu / d_ + 1u) : 0u) {}
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
+};

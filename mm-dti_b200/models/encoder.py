@@ -1,0 +1,219 @@
+"""Drop-in for the reference's models/encoder.py (same classes as models/mm_model.py:86-128,
+211-269): gaussian, GaussianLayer, NonLinearHead, UnimolEncoder, ChembertaEncoder.
+
+Fusion behind unchanged call sites.  The reference computes
+    bias = gbf_proj(gbf(dist, et)).permute(0,3,1,2).contiguous().view(-1,L,L)
+(models/mm_model.py:553-556, models/encoder.py:484-491).  Here ``GaussianLayer.forward``
+returns a ``DeferredBasis`` (nothing computed yet); ``NonLinearHead.forward`` recognises it,
+runs the fused K1 kernel straight into the (B,H,L,L) layout and returns the (B,L,L,H)
+*view* of it, so the caller's permute+contiguous+view are no-ops.  Any other use of the
+deferred basis materialises the (B,L,L,K) tensor through the stand-alone kernel."""
+import argparse
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import config, ops
+from .transformers import TransformerEncoderWithPair
+from .unicore_compat import Dictionary, get_activation_fn, init_bert_params
+
+BACKBONE = {"transformer": TransformerEncoderWithPair}
+
+
+def gaussian(x, mean, std):
+    """models/mm_model.py:211-224 (pi truncated to 3.14159 like the reference)."""
+    pi = 3.14159
+    a = (2 * pi) ** 0.5
+    return torch.exp(-0.5 * (((x - mean) / std) ** 2)) / (a * std)
+
+
+class DeferredBasis:
+    """The not-yet-computed output of GaussianLayer.forward."""
+
+    def __init__(self, layer, x, edge_type):
+        self.layer, self.x, self.edge_type = layer, x, edge_type
+        self._value = None
+
+    def materialize(self):
+        if self._value is None:
+            l = self.layer
+            self._value = ops.GaussBasisFn.apply(self.x, self.edge_type, l.means.weight, l.stds.weight,
+                                                 l.mul.weight, l.bias.weight).type_as(l.means.weight)
+        return self._value
+
+    def __getattr__(self, name):            # behave like the tensor when used as one
+        return getattr(self.materialize(), name)
+
+
+class GaussianLayer(nn.Module):
+    def __init__(self, K=128, edge_types=1024):
+        super().__init__()
+        self.K = K
+        self.means = nn.Embedding(1, K)
+        self.stds = nn.Embedding(1, K)
+        self.mul = nn.Embedding(edge_types, 1)
+        self.bias = nn.Embedding(edge_types, 1)
+        nn.init.uniform_(self.means.weight, 0, 3)
+        nn.init.uniform_(self.stds.weight, 0, 3)
+        nn.init.constant_(self.bias.weight, 0)
+        nn.init.constant_(self.mul.weight, 1)
+
+    def forward(self, x, edge_type):
+        return DeferredBasis(self, x, edge_type)
+
+
+class NonLinearHead(nn.Module):
+    def __init__(self, input_dim, out_dim, activation_fn, hidden=None):
+        super().__init__()
+        hidden = input_dim if not hidden else hidden
+        self.linear1 = nn.Linear(input_dim, hidden)
+        self.linear2 = nn.Linear(hidden, out_dim)
+        self.activation_name = activation_fn
+        self.activation_fn = get_activation_fn(activation_fn)
+
+    def fusable(self, basis):
+        return (self.activation_name == "gelu" and basis.layer.K == 128 and self.linear1.in_features == 128
+                and self.linear1.out_features == 128 and self.linear2.out_features == 64)
+
+    def forward(self, x, key_pad=None):
+        if isinstance(x, DeferredBasis):
+            if self.fusable(x):
+                g = x.layer
+                out = ops.pair_bias(x.x, x.edge_type, g.means.weight, g.stds.weight, g.mul.weight, g.bias.weight,
+                                    self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                                    key_pad=key_pad)                      # (B,H,L,L)
+                return out.permute(0, 2, 3, 1)                             # (B,L,L,H) view
+            x = x.materialize()
+        x = self.linear1(x)
+        x = self.activation_fn(x)
+        x = self.linear2(x)
+        return x
+
+
+def molecule_architecture():
+    """models/encoder.py / models/mm_model.py:325-343."""
+    args = argparse.Namespace()
+    args.encoder_layers = 15
+    args.encoder_embed_dim = 512
+    args.encoder_ffn_embed_dim = 2048
+    args.encoder_attention_heads = 64
+    args.dropout = 0.1
+    args.emb_dropout = 0.1
+    args.attention_dropout = 0.1
+    args.activation_dropout = 0.0
+    args.pooler_dropout = 0.2
+    args.max_seq_len = 512
+    args.activation_fn = "gelu"
+    args.pooler_activation_fn = "tanh"
+    args.post_ln = False
+    args.backbone = "transformer"
+    args.kernel = "gaussian"
+    args.delta_pair_repr_norm_loss = -1.0
+    return args
+
+
+class UnimolEncoder(nn.Module):
+    """Conformer encoder alone (reference: models/encoder.py:375-502; identical sub-module and
+    state_dict names: embed_tokens, gbf, gbf_proj, encoder.*).
+
+    params: ``dict_path`` (mol.dict.txt; default = the built-in Uni-Mol symbol list),
+    ``pretrain_path`` (Uni-Mol checkpoint, loaded strict=False like the reference),
+    plus any override of the molecule_architecture() fields (e.g. encoder_layers=2)."""
+
+    def __init__(self, output_dim=2, **params):
+        super().__init__()
+        self.args = molecule_architecture()
+        for k, v in params.items():
+            if hasattr(self.args, k):
+                setattr(self.args, k, v)
+        self.output_dim = output_dim
+        self.data_type = "molecule"
+        self.remove_hs = params.get("remove_hs", False)
+        self.use_fds = params.get("fds", False)
+        dict_path = params.get("dict_path")
+        self.dictionary = Dictionary.load(dict_path) if dict_path else Dictionary.unimol_default()
+        self.mask_idx = self.dictionary.add_symbol("[MASK]", is_special=True)
+        self.padding_idx = self.dictionary.pad()
+        self.embed_tokens = nn.Embedding(len(self.dictionary), self.args.encoder_embed_dim, self.padding_idx)
+        self.encoder = BACKBONE[self.args.backbone](
+            encoder_layers=self.args.encoder_layers,
+            embed_dim=self.args.encoder_embed_dim,
+            ffn_embed_dim=self.args.encoder_ffn_embed_dim,
+            attention_heads=self.args.encoder_attention_heads,
+            emb_dropout=self.args.emb_dropout,
+            dropout=self.args.dropout,
+            attention_dropout=self.args.attention_dropout,
+            activation_dropout=self.args.activation_dropout,
+            max_seq_len=self.args.max_seq_len,
+            activation_fn=self.args.activation_fn,
+            no_final_head_layer_norm=self.args.delta_pair_repr_norm_loss < 0,
+        )
+        self.encoder.pair_outputs = False           # forward() only uses output[0]
+        K = 128
+        n_edge_type = len(self.dictionary) * len(self.dictionary)
+        self.gbf_proj = NonLinearHead(K, self.args.encoder_attention_heads, self.args.activation_fn)
+        self.gbf = GaussianLayer(K, n_edge_type)
+        self.apply(init_bert_params)
+        self.pretrain_path = params.get("pretrain_path")
+        self.load_pretrained_weights(self.pretrain_path)
+
+    def load_pretrained_weights(self, path):
+        if path is not None and os.path.exists(path):
+            state_dict = torch.load(path, map_location=lambda storage, loc: storage)
+            self.load_state_dict(state_dict["model"], strict=False)
+
+    @classmethod
+    def build_model(cls, args):
+        return cls(args)
+
+    def forward(self, src_tokens, src_distance, src_edge_type):
+        """-> all_repr (B,L,512).  The key-padding mask is always handed to the kernels (no
+        host sync on ``padding_mask.any()``); with no padding it is all-false and the result is
+        identical to the reference's padding_mask=None branch (Q15)."""
+        padding_mask = src_tokens.eq(self.padding_idx)
+        x = self.embed_tokens(src_tokens)
+        bias = self.gbf_proj(self.gbf(src_distance, src_edge_type), key_pad=padding_mask)
+        bias = bias.permute(0, 3, 1, 2).contiguous()
+        bias = bias.view(-1, bias.size(-2), bias.size(-1))
+        encoder_rep = self.encoder(x, padding_mask=padding_mask, attn_mask=bias, _mask_merged=True)[0]
+        return encoder_rep
+
+    def batch_collate_fn(self, samples):
+        """models/encoder.py:504-544 — pads a list of (features, label) samples."""
+        from ..data import pad_1d_tokens, pad_2d
+        batch = {}
+        for k in samples[0][0].keys():
+            if k == "src_edge_type":
+                v = pad_2d([torch.as_tensor(s[0][k]).long() for s in samples], pad_idx=self.padding_idx)
+            elif k == "src_distance":
+                v = pad_2d([torch.as_tensor(s[0][k]).float() for s in samples], pad_idx=0.0)
+            elif k == "src_tokens":
+                v = pad_1d_tokens([torch.as_tensor(s[0][k]).long() for s in samples], pad_idx=self.padding_idx)
+            elif k == "weights":
+                v = torch.tensor([s[0][k] for s in samples])
+            else:
+                continue
+            batch[k] = v
+        try:
+            label = torch.tensor([s[1] for s in samples])
+        except Exception:
+            label = None
+        return batch, label
+
+
+class ChembertaEncoder(nn.Module):
+    """models/encoder.py:548-572: the HF SMILES encoder; stock PyTorch (out of the hot path).
+    ``model_name_or_path`` may also be a transformers config object (random init, offline)."""
+
+    def __init__(self, model_name_or_path, **params):
+        super().__init__()
+        from transformers import AutoModel, PretrainedConfig
+        if isinstance(model_name_or_path, PretrainedConfig):
+            self.bert = AutoModel.from_config(model_name_or_path)
+        else:
+            self.bert = AutoModel.from_pretrained(model_name_or_path)
+
+    def forward(self, input_ids, attention_mask):
+        return self.bert(input_ids, attention_mask, return_dict=True)[0]

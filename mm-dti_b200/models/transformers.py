@@ -1,0 +1,98 @@
+"""TransformerEncoderWithPair — drop-in for the reference's models/transformers.py:14-183
+(same constructor, forward signature, return tuple and state_dict names), running on the
+mmdti_b200 kernels.  The pair tensor is carried as (B,H,L,L) in config.pair_dtype()."""
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import config, ops
+from .unicore_compat import LayerNorm, TransformerEncoderLayer
+
+
+class TransformerEncoderWithPair(nn.Module):
+    def __init__(
+        self,
+        encoder_layers: int = 6,
+        embed_dim: int = 768,
+        ffn_embed_dim: int = 3072,
+        attention_heads: int = 8,
+        emb_dropout: float = 0.1,
+        dropout: float = 0.1,
+        attention_dropout: float = 0.1,
+        activation_dropout: float = 0.0,
+        max_seq_len: int = 256,
+        activation_fn: str = "gelu",
+        post_ln: bool = False,
+        no_final_head_layer_norm: bool = False,
+    ) -> None:
+        super().__init__()
+        self.emb_dropout = emb_dropout
+        self.max_seq_len = max_seq_len
+        self.embed_dim = embed_dim
+        self.attention_heads = attention_heads
+        self.emb_layer_norm = LayerNorm(self.embed_dim)
+        self.final_layer_norm = LayerNorm(self.embed_dim) if not post_ln else None
+        self.final_head_layer_norm = LayerNorm(attention_heads) if not no_final_head_layer_norm else None
+        self.layers = nn.ModuleList([
+            TransformerEncoderLayer(embed_dim=self.embed_dim, ffn_embed_dim=ffn_embed_dim,
+                                    attention_heads=attention_heads, dropout=dropout,
+                                    attention_dropout=attention_dropout, activation_dropout=activation_dropout,
+                                    activation_fn=activation_fn, post_ln=post_ln)
+            for _ in range(encoder_layers)
+        ])
+        # MM-DTI discards outputs 1..4 (models/mm_model.py:559); set False to skip producing them
+        self.pair_outputs = True
+
+    def forward(self, emb: torch.Tensor, attn_mask: Optional[torch.Tensor] = None,
+                padding_mask: Optional[torch.Tensor] = None, _mask_merged: bool = False):
+        """emb (B,L,D); attn_mask (B*H,L,L) pair bias — MUTATED IN PLACE with -inf at padded key
+        columns exactly like models/transformers.py:122-132; padding_mask (B,L) bool or None.
+        Returns (x, pair (B,L,L,H), delta_pair (B,L,L,H), x_norm, delta_pair_norm)."""
+        bsz, seq_len = emb.size(0), emb.size(1)
+        H = self.attention_heads
+        x = self.emb_layer_norm(emb)
+        x = F.dropout(x, p=self.emb_dropout, training=self.training)
+        if padding_mask is not None:
+            x = x * (1 - padding_mask.unsqueeze(-1).type_as(x))
+        assert attn_mask is not None
+        if padding_mask is not None and not _mask_merged:
+            if not attn_mask.is_contiguous():
+                raise ValueError("attn_mask must be contiguous (B*H, L, L)")
+            ops.pair_mask_fill_(attn_mask, padding_mask)          # the caller's tensor, in place
+        pdt = config.pair_dtype()
+        pair = attn_mask if attn_mask.dtype == pdt else attn_mask.to(pdt)
+        pair = pair.view(bsz * H, seq_len, seq_len)
+        pair_first = pair
+        for layer in self.layers:
+            x, pair, _ = layer(x, padding_mask=None, attn_bias=pair, return_attn=True)
+
+        if not self.pair_outputs:
+            if self.final_layer_norm is not None:
+                x = self.final_layer_norm(x)
+            return x, None, None, None, None
+
+        def norm_loss(t, eps=1e-10, tolerance=1.0):
+            t = t.float()
+            max_norm = t.shape[-1] ** 0.5
+            norm = torch.sqrt(torch.sum(t ** 2, dim=-1) + eps)
+            return F.relu((norm - max_norm).abs() - tolerance)
+
+        def masked_mean(mask, value, dim=-1, eps=1e-10):
+            return (torch.sum(mask * value, dim=dim) / (eps + torch.sum(mask, dim=dim))).mean()
+
+        x_norm = norm_loss(x)
+        if padding_mask is not None:
+            token_mask = 1.0 - padding_mask.float()
+        else:
+            token_mask = torch.ones_like(x_norm)
+        x_norm = masked_mean(token_mask, x_norm)
+        if self.final_layer_norm is not None:
+            x = self.final_layer_norm(x)
+        pair_out, delta = ops.PairOutputsFn.apply(pair_first.contiguous(), pair.contiguous(), bsz, H, seq_len)
+        pair_mask = token_mask[..., None] * token_mask[..., None, :]
+        delta_norm = masked_mean(pair_mask, norm_loss(delta), dim=(-1, -2))
+        if self.final_head_layer_norm is not None:
+            delta = self.final_head_layer_norm(delta)
+        return x, pair_out, delta, x_norm, delta_norm

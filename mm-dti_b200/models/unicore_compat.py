@@ -1,0 +1,183 @@
+"""The slice of Uni-Core's API the reference imports (models/transformers.py:11,
+models/mm_model.py:13-16), re-implemented on the mmdti_b200 kernels so the drop-in
+does not depend on Uni-Core: LayerNorm, init_bert_params, get_activation_fn, Dictionary,
+SelfMultiheadAttention, TransformerEncoderLayer (same constructor arguments, parameter
+names and return conventions)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import config, ops
+from .._lib import MMDTIError
+
+UNIMOL_DICT = ["[PAD]", "[CLS]", "[SEP]", "[UNK]", "C", "N", "O", "S", "H", "Cl", "F", "Br", "I", "Si",
+               "P", "B", "Na", "K", "Al", "Ca", "Sn", "As", "Hg", "Fe", "Zn", "Cr", "Se", "Gd", "Au", "Li"]
+
+
+def get_activation_fn(activation):
+    if activation == "relu":
+        return F.relu
+    if activation == "gelu":
+        return F.gelu
+    if activation == "tanh":
+        return torch.tanh
+    if activation == "linear":
+        return lambda x: x
+    raise RuntimeError("--activation-fn {} not supported".format(activation))
+
+
+class LayerNorm(nn.LayerNorm):
+    def __init__(self, normalized_shape, eps=1e-5, elementwise_affine=True):
+        super().__init__(normalized_shape, eps=eps, elementwise_affine=elementwise_affine)
+
+    def forward(self, x):
+        return F.layer_norm(x.float(), self.normalized_shape, self.weight, self.bias, self.eps)
+
+
+def init_bert_params(module):
+    if isinstance(module, nn.Linear):
+        module.weight.data.normal_(mean=0.0, std=0.02)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    if isinstance(module, nn.Embedding):
+        module.weight.data.normal_(mean=0.0, std=0.02)
+        if module.padding_idx is not None:
+            module.weight.data[module.padding_idx].zero_()
+
+
+class Dictionary:
+    """Symbol table in file order (one symbol per line)."""
+
+    def __init__(self, *, bos="[CLS]", pad="[PAD]", eos="[SEP]", unk="[UNK]"):
+        self.bos_word, self.pad_word, self.eos_word, self.unk_word = bos, pad, eos, unk
+        self.symbols, self.indices = [], {}
+
+    def __len__(self):
+        return len(self.symbols)
+
+    def index(self, sym):
+        return self.indices.get(sym, self.indices.get(self.unk_word))
+
+    def add_symbol(self, word, is_special=False):
+        if word not in self.indices:
+            self.indices[word] = len(self.symbols)
+            self.symbols.append(word)
+        return self.indices[word]
+
+    def bos(self):
+        return self.index(self.bos_word)
+
+    def pad(self):
+        return self.index(self.pad_word)
+
+    def eos(self):
+        return self.index(self.eos_word)
+
+    def unk(self):
+        return self.index(self.unk_word)
+
+    @classmethod
+    def load(cls, path):
+        d = cls()
+        with open(path, "r", encoding="utf-8") as fh:
+            for line in fh:
+                tok = line.strip().split()
+                if tok:
+                    d.add_symbol(tok[0])
+        return d
+
+    @classmethod
+    def unimol_default(cls):
+        d = cls()
+        for s in UNIMOL_DICT:
+            d.add_symbol(s)
+        return d
+
+
+def _lin(x, layer, dt):
+    return F.linear(x.to(dt), layer.weight.to(dt), None if layer.bias is None else layer.bias.to(dt))
+
+
+class SelfMultiheadAttention(nn.Module):
+    """in_proj / out_proj around the pair-biased attention kernel (head_dim must be 8)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0.1, bias=True, scaling_factor=1):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.dropout = embed_dim, num_heads, dropout
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        self.scaling = (self.head_dim * scaling_factor) ** -0.5
+        self.in_proj = nn.Linear(embed_dim, embed_dim * 3, bias=bias)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=bias)
+
+    def forward(self, query, key_padding_mask=None, attn_bias=None, return_attn=False, inplace_pair=False):
+        if self.head_dim != 8:
+            raise MMDTIError("mmdti_b200 pair attention is built for head_dim 8 (Uni-Mol: 512/64); got %d" % self.head_dim)
+        B, L, D = query.shape
+        H = self.num_heads
+        dt = config.act_dtype()
+        pdt = config.pair_dtype()
+        if attn_bias is None:
+            attn_bias = torch.zeros((B * H, L, L), device=query.device, dtype=pdt)
+        if attn_bias.dtype != pdt:
+            attn_bias = attn_bias.to(pdt)
+        attn_bias = attn_bias.contiguous()
+        if key_padding_mask is not None:
+            attn_bias = attn_bias.clone()
+            ops.pair_mask_fill_(attn_bias, key_padding_mask)
+        qkv = _lin(query, self.in_proj, dt).reshape(B * L, 3 * D)
+        p = self.dropout if self.training else 0.0
+        o, scores = ops.pair_attention(qkv, attn_bias, B, H, L, self.scaling, p, ops.next_seed() if p > 0 else 0,
+                                       inplace_pair)
+        o = _lin(o, self.out_proj, dt).view(B, L, D)
+        if not return_attn:
+            return o
+        # Uni-Core also returns the (B*H,L,L) probabilities; they are never materialised here
+        return o, scores.view(B * H, L, L), None
+
+
+class TransformerEncoderLayer(nn.Module):
+    """Pre-LN (or post-LN) encoder layer; with return_attn=True also returns the pre-softmax
+    scores (QK^T*scale + bias), which TransformerEncoderWithPair feeds to the next layer."""
+
+    def __init__(self, embed_dim=768, ffn_embed_dim=3072, attention_heads=8, dropout=0.1, attention_dropout=0.1,
+                 activation_dropout=0.0, activation_fn="gelu", post_ln=False):
+        super().__init__()
+        self.embed_dim, self.attention_heads = embed_dim, attention_heads
+        self.attention_dropout = attention_dropout
+        self.dropout, self.activation_dropout = dropout, activation_dropout
+        self.activation_fn = get_activation_fn(activation_fn)
+        self.self_attn = SelfMultiheadAttention(embed_dim, attention_heads, dropout=attention_dropout)
+        self.self_attn_layer_norm = LayerNorm(embed_dim)
+        self.fc1 = nn.Linear(embed_dim, ffn_embed_dim)
+        self.fc2 = nn.Linear(ffn_embed_dim, embed_dim)
+        self.final_layer_norm = LayerNorm(embed_dim)
+        self.post_ln = post_ln
+
+    def forward(self, x, attn_bias=None, padding_mask=None, return_attn=False, inplace_pair=False):
+        dt = config.act_dtype()
+        residual = x
+        if not self.post_ln:
+            x = self.self_attn_layer_norm(x)
+        x = self.self_attn(query=x, key_padding_mask=padding_mask, attn_bias=attn_bias, return_attn=return_attn,
+                           inplace_pair=inplace_pair)
+        if return_attn:
+            x, attn_weights, attn_probs = x
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        x = residual + x
+        if self.post_ln:
+            x = self.self_attn_layer_norm(x)
+        residual = x
+        if not self.post_ln:
+            x = self.final_layer_norm(x)
+        x = _lin(x, self.fc1, dt)
+        x = self.activation_fn(x)
+        x = F.dropout(x, p=self.activation_dropout, training=self.training)
+        x = _lin(x, self.fc2, dt)
+        x = F.dropout(x, p=self.dropout, training=self.training)
+        x = residual + x
+        if self.post_ln:
+            x = self.final_layer_norm(x)
+        if not return_attn:
+            return x
+        return x, attn_weights, attn_probs

@@ -1,0 +1,238 @@
+"""torch.autograd.Function wrappers around the C ABI (include/mmdti_b200.h).
+
+Every op requires CUDA tensors and the compiled library; there is no fallback."""
+import threading
+
+import torch
+
+from . import _lib, config
+from ._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
+
+_seed_lock = threading.Lock()
+_seed_counter = 0
+
+
+def next_seed():
+    """Deterministic per-call dropout seed derived from torch's seed and a call counter."""
+    global _seed_counter
+    with _seed_lock:
+        _seed_counter += 1
+        c = _seed_counter
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+
+
+def reset_seed_counter():
+    global _seed_counter
+    _seed_counter = 0
+
+
+# =========================================================================== K1
+class PairBiasFn(torch.autograd.Function):
+    """dist (B,L,L) f32, edge_type (B,L,L) int64 -> pair bias (B,H,L,L).
+    Reference: models/mm_model.py:553-556 (gbf -> gbf_proj -> permute -> contiguous)."""
+
+    @staticmethod
+    def forward(ctx, dist, edge_type, means, stds, mul, bias, w1, b1, w2, b2, key_pad, out_dtype, fp32_math):
+        _lib.require_cuda(dist, edge_type, means, w1)
+        B, L = dist.shape[0], dist.shape[1]
+        K, H, E = means.numel(), w2.shape[0], mul.numel()
+        dist = dist.contiguous().float()
+        edge_type = edge_type.contiguous().long()
+        ps = [t.detach().contiguous().float() for t in (means, stds, mul, bias, w1, b1, w2, b2)]
+        kp = key_pad.contiguous().to(torch.uint8) if key_pad is not None else None
+        out = torch.empty((B, H, L, L), device=dist.device, dtype=out_dtype)
+        call("mmdti_pair_bias_fwd", dist, edge_type, *ps, kp, out, i32(B), i32(L), i32(K), i32(H), i32(E),
+             i32(DTYPE_CODE[out_dtype]), i32(1 if fp32_math else 0), stream_ptr())
+        ctx.save_for_backward(dist, edge_type, *ps)
+        ctx.fp32_math = fp32_math
+        ctx.dims = (B, L, K, H, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        dist, edge_type, means, stds, mul, bias, w1, b1, w2, b2 = ctx.saved_tensors
+        B, L, K, H, E = ctx.dims
+        cdt = torch.float32 if ctx.fp32_math else torch.bfloat16
+        dev = dist.device
+        d_means = torch.zeros(K, device=dev)
+        d_stds = torch.zeros(K, device=dev)
+        d_mul = torch.zeros(E, device=dev)
+        d_bias = torch.zeros(E, device=dev)
+        d_w1 = torch.zeros(K, K, device=dev)
+        d_b1 = torch.zeros(K, device=dev)
+        d_w2 = torch.zeros(H, K, device=dev)
+        d_b2 = torch.zeros(H, device=dev)
+        d_out = d_out.contiguous()
+        if d_out.dtype not in (torch.float32, torch.bfloat16):
+            d_out = d_out.float()
+        w1c, w2c, b1c = w1.to(cdt), w2.to(cdt), b1.to(cdt)
+        # molecules per chunk: bound the (pairs,128) temporaries to ~256 MB
+        per_mol = L * L * K * (4 if ctx.fp32_math else 2) * 6
+        chunk = max(1, min(B, (256 << 20) // max(per_mol, 1)))
+        for b0 in range(0, B, chunk):
+            b1_ = min(B, b0 + chunk)
+            nb = b1_ - b0
+            npairs = nb * L * L
+            dist_c, et_c = dist[b0:b1_], edge_type[b0:b1_]
+            G = torch.empty((npairs, K), device=dev, dtype=cdt)
+            call("mmdti_gauss_basis", dist_c, et_c, means, stds, mul, bias, G, i64(npairs), i32(K), i32(E),
+                 i32(DTYPE_CODE[cdt]), stream_ptr())
+            dO = torch.empty((npairs, H), device=dev, dtype=cdt)
+            call("mmdti_pair_to_rows", d_out[b0:b1_], dO, i32(nb), i32(H), i32(L), i32(DTYPE_CODE[d_out.dtype]),
+                 i32(DTYPE_CODE[cdt]), stream_ptr())
+            Z = torch.addmm(b1c, G, w1c.t())
+            Hm = torch.nn.functional.gelu(Z)
+            d_w2 += (dO.t() @ Hm).float()
+            d_b2 += dO.float().sum(0)
+            dH = dO @ w2c
+            dZ = torch.ops.aten.gelu_backward(dH, Z)
+            d_w1 += (dZ.t() @ G).float()
+            d_b1 += dZ.float().sum(0)
+            dG = (dZ @ w1c).contiguous()
+            call("mmdti_gauss_param_grad", dG, dist_c, et_c, means, stds, mul, bias, d_means, d_stds, d_mul,
+                 d_bias, i64(npairs), i32(K), i32(E), i32(DTYPE_CODE[cdt]), stream_ptr())
+        return (None, None, d_means.view(1, K), d_stds.view(1, K), d_mul.view(E, 1), d_bias.view(E, 1),
+                d_w1, d_b1, d_w2, d_b2, None, None, None)
+
+
+def pair_bias(dist, edge_type, means, stds, mul, bias, w1, b1, w2, b2, key_pad=None):
+    return PairBiasFn.apply(dist, edge_type, means, stds, mul, bias, w1, b1, w2, b2, key_pad,
+                            config.pair_dtype(), config.fp32_mode())
+
+
+class GaussBasisFn(torch.autograd.Function):
+    """Stand-alone GaussianLayer.forward (models/mm_model.py:254-269) -> (B,L,L,K) f32."""
+
+    @staticmethod
+    def forward(ctx, dist, edge_type, means, stds, mul, bias):
+        _lib.require_cuda(dist, edge_type, means)
+        K, E = means.numel(), mul.numel()
+        dist = dist.contiguous().float()
+        edge_type = edge_type.contiguous().long()
+        ps = [t.detach().contiguous().float() for t in (means, stds, mul, bias)]
+        out = torch.empty(tuple(dist.shape) + (K,), device=dist.device, dtype=torch.float32)
+        call("mmdti_gauss_basis", dist, edge_type, *ps, out, i64(dist.numel()), i32(K), i32(E), i32(_lib.F32),
+             stream_ptr())
+        ctx.save_for_backward(dist, edge_type, *ps)
+        return out
+
+    @staticmethod
+    def backward(ctx, dG):
+        dist, edge_type, means, stds, mul, bias = ctx.saved_tensors
+        K, E = means.numel(), mul.numel()
+        dev = dist.device
+        d_means, d_stds = torch.zeros(K, device=dev), torch.zeros(K, device=dev)
+        d_mul, d_bias = torch.zeros(E, device=dev), torch.zeros(E, device=dev)
+        dG = dG.contiguous().float()
+        call("mmdti_gauss_param_grad", dG, dist, edge_type, means, stds, mul, bias, d_means, d_stds, d_mul, d_bias,
+             i64(dist.numel()), i32(K), i32(E), i32(_lib.F32), stream_ptr())
+        return None, None, d_means.view(1, K), d_stds.view(1, K), d_mul.view(E, 1), d_bias.view(E, 1)
+
+
+def pair_mask_fill_(pair, key_pad, fill=float("-inf")):
+    """In place: pair[b,h,:,j] = fill where key_pad[b,j] (models/transformers.py:122-132)."""
+    _lib.require_cuda(pair, key_pad)
+    B, L = key_pad.shape
+    if not pair.is_contiguous():
+        raise _lib.MMDTIError("pair_mask_fill_: the pair tensor must be contiguous (B*H,L,L)")
+    H = pair.numel() // (B * L * L)
+    kp = key_pad.contiguous().to(torch.uint8)
+    call("mmdti_pair_mask_fill", pair, kp, i32(B), i32(H), i32(L), i32(DTYPE_CODE[pair.dtype]), f32(fill), stream_ptr())
+    return pair
+
+
+# =========================================================================== K2
+class PairAttnFn(torch.autograd.Function):
+    """qkv (B*L, 3*H*8) [q|k|v], pair_in (B,H,L,L) -> o (B*L, H*8), pair_out (B,H,L,L).
+    Reference: Uni-Core SelfMultiheadAttention(return_attn=True) core via
+    models/transformers.py:136-139."""
+
+    @staticmethod
+    def forward(ctx, qkv, pair_in, B, H, L, scale, dropout_p, seed, inplace_pair):
+        _lib.require_cuda(qkv, pair_in)
+        D = H * 8
+        if qkv.shape != (B * L, 3 * D) or not qkv.is_contiguous():
+            raise _lib.MMDTIError("pair_attn: qkv must be a contiguous (B*L, 3*H*8) tensor")
+        if pair_in.numel() != B * H * L * L or not pair_in.is_contiguous():
+            raise _lib.MMDTIError("pair_attn: pair must be a contiguous (B,H,L,L) tensor")
+        o = torch.empty((B * L, D), device=qkv.device, dtype=qkv.dtype)
+        pair_out = pair_in if inplace_pair else torch.empty_like(pair_in)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        call("mmdti_pair_attn_fwd", q, k, v, i64(3 * D), pair_in, pair_out, o, i64(D), i32(B), i32(H), i32(L),
+             f32(scale), f32(dropout_p), u64(seed), i32(DTYPE_CODE[qkv.dtype]), i32(DTYPE_CODE[pair_in.dtype]),
+             stream_ptr())
+        if inplace_pair:
+            ctx.mark_dirty(pair_in)
+        ctx.save_for_backward(qkv, pair_out, o)
+        ctx.cfg = (B, H, L, scale, dropout_p, seed)
+        ctx.set_materialize_grads(False)
+        return o, pair_out
+
+    @staticmethod
+    def backward(ctx, d_o, d_pair_out):
+        qkv, s, o = ctx.saved_tensors
+        B, H, L, scale, dropout_p, seed = ctx.cfg
+        D = H * 8
+        gdt = s.dtype          # the pair gradient is carried in the pair tensor's own dtype
+        if d_o is None:
+            d_o = torch.zeros_like(o)
+        d_o = d_o.contiguous()
+        if d_o.dtype != o.dtype:
+            d_o = d_o.to(o.dtype)
+        if d_pair_out is not None:
+            d_pair_out = d_pair_out.contiguous()
+            if d_pair_out.dtype != gdt:
+                d_pair_out = d_pair_out.to(gdt)
+        d_pair_in = torch.empty(s.shape, device=s.device, dtype=gdt)
+        dqkv = torch.empty_like(qkv)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
+        call("mmdti_pair_attn_bwd", q, k, v, i64(3 * D), s, o, d_o, i64(D), d_pair_out, d_pair_in, dq, dk, dv,
+             i64(3 * D), i32(B), i32(H), i32(L), f32(scale), f32(dropout_p), u64(seed), i32(DTYPE_CODE[qkv.dtype]),
+             i32(DTYPE_CODE[s.dtype]), i32(DTYPE_CODE[gdt]), stream_ptr())
+        return dqkv, d_pair_in, None, None, None, None, None, None, None
+
+
+def pair_attention(qkv, pair_in, B, H, L, scale, dropout_p=0.0, seed=0, inplace_pair=False):
+    return PairAttnFn.apply(qkv, pair_in, B, H, L, scale, dropout_p, seed, inplace_pair)
+
+
+def attn_dropout_mask(B, H, L, dropout_p, seed, device="cuda"):
+    """Debug/test export of the keep mask used by pair_attention for `seed`."""
+    keep = torch.empty((B, H, L, L), device=device, dtype=torch.uint8)
+    call("mmdti_pair_attn_dropout_mask", keep, i32(B), i32(H), i32(L), f32(dropout_p), u64(seed), stream_ptr())
+    return keep.bool()
+
+
+class PairOutputsFn(torch.autograd.Function):
+    """(pair_first, pair_last) (B,H,L,L) -> pair (B,L,L,H) f32, delta (B,L,L,H) f32
+    (models/transformers.py:163-172)."""
+
+    @staticmethod
+    def forward(ctx, pair_first, pair_last, B, H, L):
+        pair = torch.empty((B, L, L, H), device=pair_last.device, dtype=torch.float32)
+        delta = torch.empty_like(pair)
+        call("mmdti_pair_outputs", pair_first, pair_last, pair, delta, i32(B), i32(H), i32(L),
+             i32(DTYPE_CODE[pair_last.dtype]), stream_ptr())
+        ctx.save_for_backward(pair_last)
+        ctx.dims = (B, H, L, pair_first.dtype)
+        ctx.set_materialize_grads(False)
+        return pair, delta
+
+    @staticmethod
+    def backward(ctx, d_pair, d_delta):
+        (pair_last,) = ctx.saved_tensors
+        B, H, L, first_dtype = ctx.dims
+        g_last = None
+        if d_pair is not None:
+            g_last = d_pair
+        if d_delta is not None:
+            g_last = d_delta if g_last is None else g_last + d_delta
+        if g_last is None:
+            return None, None, None, None, None
+        valid = torch.isfinite(pair_last).view(B, H, L, L)
+        g_last = g_last.permute(0, 3, 1, 2) * valid
+        g_first = None
+        if d_delta is not None:
+            g_first = (-(d_delta.permute(0, 3, 1, 2) * valid)).to(first_dtype).contiguous().view(-1, L, L)
+        return g_first, g_last.to(pair_last.dtype).contiguous().view(pair_last.shape), None, None, None

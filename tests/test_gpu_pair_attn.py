@@ -1,0 +1,139 @@
+"""GPU parity of K2 (pair-biased attention fwd/bwd, C ABI mmdti_pair_attn_*) vs the oracle."""
+import pytest
+import torch
+
+from conftest import norm_err, rel_err
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+MODES = [("fp32", "fp32"), ("bf16", "bf16"), ("bf16", "fp16"), ("bf16", "fp32")]
+TORCH = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+# tolerances (max-abs error / max-abs reference): fp32 validation mode 1e-5 class; the
+# bf16 modes are bounded by bf16 operand rounding (2^-9) of the tensor-core inputs.
+TOL = {"fp32": dict(o=2e-5, s=2e-5, g=5e-5), "bf16": dict(o=2e-2, s=1.2e-2, g=3e-2)}
+
+
+def _problem(B, H, L, act, pair, seed, n_pad):
+    g = torch.Generator().manual_seed(seed)
+    D = H * 8
+    qkv = torch.randn(B * L, 3 * D, generator=g) * 0.7
+    bias = torch.randn(B, H, L, L, generator=g)
+    pad = torch.zeros(B, L, dtype=torch.bool)
+    for b in range(B):
+        k = min(n_pad * b, L - 1)
+        if k:
+            pad[b, L - k:] = True
+    bias.masked_fill_(pad[:, None, None, :], float("-inf"))
+    d_o = torch.randn(B * L, D, generator=g)
+    d_s = torch.randn(B, H, L, L, generator=g) * 0.3
+    adt, pdt = TORCH[act], TORCH[pair]
+    # round inputs to the storage types so the oracle sees exactly what the kernel sees
+    return (qkv.to(adt), bias.to(pdt), d_o.to(adt), d_s.to(pdt), pad)
+
+
+def _oracle(qkv, bias, d_o, d_s, B, H, L, p, keep):
+    D = H * 8
+    qkv = qkv.double().cpu().requires_grad_(True)
+    bias = bias.double().cpu().requires_grad_(True)
+    q, k, v = qkv.view(B, L, 3 * D).chunk(3, dim=-1)
+    sp = lambda t: t.reshape(B, L, H, 8).transpose(1, 2)
+    o, s = restate.pair_attention(sp(q), sp(k), sp(v), bias, 8 ** -0.5, p, keep)
+    o2 = o.transpose(1, 2).reshape(B * L, D)
+    fin = torch.isfinite(s)
+    loss = (o2 * d_o.double().cpu()).sum() + (torch.where(fin, s, torch.zeros_like(s)) * d_s.double().cpu()).sum()
+    loss.backward()
+    return o2.detach(), s.detach(), qkv.grad, bias.grad
+
+
+@pytest.mark.parametrize("act,pair", MODES)
+@pytest.mark.parametrize("L", [5, 16, 33, 66, 67, 130, 258])
+def test_pair_attn_parity(act, pair, L, report):
+    from mmdti_b200 import ops
+    B, H = (2, 3) if L > 100 else (3, 4)
+    qkv, bias, d_o, d_s, pad = _problem(B, H, L, act, pair, seed=L, n_pad=3)
+    dev = "cuda"
+    qkv_g = qkv.to(dev).requires_grad_(True)
+    bias_g = bias.to(dev).requires_grad_(True)
+    o, s = ops.pair_attention(qkv_g, bias_g, B, H, L, 8 ** -0.5, 0.0, 0)
+    d_s_g = d_s.to(dev).clone()
+    d_s_g.masked_fill_(pad.to(dev)[:, None, None, :], 0)
+    torch.autograd.backward([o, s], [d_o.to(dev), d_s_g])
+    torch.cuda.synchronize()
+    ro, rs, rdqkv, rdb = _oracle(qkv.float(), bias.float(), d_o.float(), d_s.float(), B, H, L, 0.0, None)
+    tol = TOL[act]
+    errs = dict(o=rel_err(o.float(), ro), s=rel_err(s.float(), rs), dqkv=rel_err(qkv_g.grad.float(), rdqkv),
+                dbias=rel_err(bias_g.grad.float(), rdb), n_dqkv=norm_err(qkv_g.grad.float(), rdqkv),
+                n_dbias=norm_err(bias_g.grad.float(), rdb), n_o=norm_err(o.float(), ro))
+    report("pair_attn", act, pair, "L=%d" % L, {k: "%.2e" % v for k, v in errs.items()})
+    # the stored scores are rounded to the pair dtype
+    s_tol = {"fp32": tol["s"], "bf16": 1.2e-2, "fp16": 2e-3}[pair] if act != "fp32" else tol["s"]
+    assert errs["o"] < tol["o"], errs
+    assert errs["s"] < max(s_tol, tol["s"]), errs
+    assert errs["dqkv"] < tol["g"], errs
+    assert errs["dbias"] < tol["g"], errs
+    # -inf (padded key) pattern is exact and carries no gradient
+    assert torch.equal(torch.isinf(s.float().cpu()), pad[:, None, None, :].expand(B, H, L, L))
+    assert (bias_g.grad.float().cpu()[pad[:, None, None, :].expand(B, H, L, L)] == 0).all()
+
+
+@pytest.mark.parametrize("act,pair", [("fp32", "fp32"), ("bf16", "bf16")])
+def test_pair_attn_dropout_replay(act, pair, report):
+    """Training-mode parity: export the kernel's keep mask and replay it in the oracle."""
+    from mmdti_b200 import ops
+    B, H, L, p, seed = 2, 4, 66, 0.1, 12345
+    qkv, bias, d_o, d_s, pad = _problem(B, H, L, act, pair, seed=7, n_pad=5)
+    dev = "cuda"
+    qkv_g = qkv.to(dev).requires_grad_(True)
+    bias_g = bias.to(dev).requires_grad_(True)
+    o, s = ops.pair_attention(qkv_g, bias_g, B, H, L, 8 ** -0.5, p, seed)
+    d_s_g = d_s.to(dev).clone()
+    d_s_g.masked_fill_(pad.to(dev)[:, None, None, :], 0)
+    torch.autograd.backward([o, s], [d_o.to(dev), d_s_g])
+    keep = ops.attn_dropout_mask(B, H, L, p, seed).cpu()
+    rate = keep.float().mean().item()
+    thr = round(p * 65536)
+    assert abs(rate - (1 - thr / 65536)) < 5e-3, rate
+    # the kernel rescales by the exact keep probability 1 - thr/65536
+    ro, rs, rdqkv, rdb = _oracle(qkv.float(), bias.float(), d_o.float(), d_s.float(), B, H, L, thr / 65536, keep)
+    tol = TOL[act]
+    errs = dict(o=rel_err(o.float(), ro), dqkv=rel_err(qkv_g.grad.float(), rdqkv), dbias=rel_err(bias_g.grad.float(), rdb))
+    report("pair_attn_dropout", act, pair, {k: "%.2e" % v for k, v in errs.items()}, "keep_rate=%.4f" % rate)
+    assert errs["o"] < tol["o"] and errs["dqkv"] < tol["g"] and errs["dbias"] < tol["g"], errs
+    # determinism: same seed -> same output; different seed -> different mask
+    o2, _ = ops.pair_attention(qkv_g.detach(), bias_g.detach(), B, H, L, 8 ** -0.5, p, seed)
+    assert torch.equal(o2, o.detach())
+    keep2 = ops.attn_dropout_mask(B, H, L, p, seed + 1).cpu()
+    assert (keep2 != keep).float().mean().item() > 0.05
+
+
+def test_pair_attn_inplace_and_no_dpair(report):
+    """pair_out may alias pair_in; d_pair_out may be absent (last layer of MM-DTI)."""
+    from mmdti_b200 import ops
+    B, H, L = 2, 4, 66
+    qkv, bias, d_o, d_s, pad = _problem(B, H, L, "bf16", "bf16", seed=3, n_pad=4)
+    dev = "cuda"
+    qkv_g = qkv.to(dev).requires_grad_(True)
+    bias_g = bias.to(dev).requires_grad_(True)
+    o, s = ops.pair_attention(qkv_g, bias_g, B, H, L, 8 ** -0.5, 0.0, 0)
+    o.backward(d_o.to(dev))
+    g1, gb1 = qkv_g.grad.clone(), bias_g.grad.clone()
+    ro, rs, rdqkv, rdb = _oracle(qkv.float(), bias.float(), d_o.float(), d_s.float() * 0, B, H, L, 0.0, None)
+    assert rel_err(g1.float(), rdqkv) < 3e-2 and rel_err(gb1.float(), rdb) < 3e-2
+    with torch.no_grad():
+        b2 = bias.to(dev).clone()
+        o2, s2 = ops.pair_attention(qkv.to(dev), b2, B, H, L, 8 ** -0.5, 0.0, 0, True)
+        assert s2.data_ptr() == b2.data_ptr()
+        assert torch.equal(o2, o.detach()) and torch.equal(s2, s.detach())
+
+
+def test_pair_attn_argument_errors():
+    from mmdti_b200 import ops
+    from mmdti_b200._lib import MMDTIError
+    with pytest.raises(MMDTIError):
+        ops.pair_attention(torch.zeros(10, 96), torch.zeros(1, 4, 10, 10), 1, 4, 10, 1.0)      # CPU tensors
+    with pytest.raises(MMDTIError):
+        ops.pair_attention(torch.zeros(10, 90, device="cuda"), torch.zeros(1, 4, 10, 10, device="cuda"), 1, 4, 10, 1.0)
+    with pytest.raises(MMDTIError):     # L beyond the supported maximum
+        ops.pair_attention(torch.zeros(300, 24, device="cuda", dtype=torch.bfloat16),
+                           torch.zeros(1, 1, 300, 300, device="cuda", dtype=torch.bfloat16), 1, 1, 300, 1.0)

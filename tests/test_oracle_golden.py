@@ -1,0 +1,125 @@
+"""CPU: the oracle restatement reproduces every golden fixture generated from the
+reference's own files (oracle/make_golden.py)."""
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import restate
+from oracle.detw import det_state_dict
+
+
+def _params(g):
+    return {k[2:]: v.clone().requires_grad_(True) for k, v in g.items() if k.startswith("w.")}
+
+
+def test_pair_bias_golden():
+    for tag in ("init", "pre"):
+        g = load_golden("pair_bias_" + tag)
+        p = _params(g)
+        out = restate.pair_bias(g["in.dist"], g["in.edge_type"], p).view(g["out.bias"].shape)
+        assert rel_err(out, g["out.bias"]) < 5e-6
+        (out * g["in.upstream"]).sum().backward()
+        for k, v in g.items():
+            if k.startswith("grad."):
+                assert rel_err(p[k[5:]].grad, v) < 5e-5, k
+
+
+def test_encoder_golden():
+    for tag in ("small", "nopad"):
+        g = load_golden("encoder_" + tag)
+        H, D, Fd, nl = [int(v) for v in g["cfg"]]
+        p = _params(g)
+        pm = g["in.tokens"].eq(0)
+        pm = pm if pm.any() else None
+        emb = g["in.emb"].clone().requires_grad_(True)
+        b0 = g["in.bias"].clone().requires_grad_(True)
+        bw = b0 * 1.0
+        x, pair, delta, xn, dn = restate.encoder_with_pair(emb, bw, pm, p, H, nl)
+        assert rel_err(x, g["out.x"]) < 5e-6
+        assert rel_err(pair, g["out.pair"]) < 5e-6
+        assert rel_err(delta, g["out.delta"]) < 5e-6
+        assert torch.equal(torch.isinf(bw), torch.isinf(g["out.bias_after"]))      # Q1, bit-exact
+        (x * g["in.up_x"]).sum().add((delta * g["in.up_delta"]).sum()).add(xn).add(dn).backward()
+        assert rel_err(emb.grad, g["grad.emb"]) < 5e-5
+        assert rel_err(b0.grad, g["grad.bias"]) < 5e-5
+
+
+def test_encoder_slice_golden():
+    g = load_golden("encoder_slice")
+    H, D, Fd, nl, seed = [int(v) for v in g["cfg"]]
+    from tests_util import slice_shapes
+    p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(H, D, Fd, nl), seed=seed).items()}
+    rep = restate.unimol_encoder(g["in.tokens"], g["in.dist"], g["in.edge_type"], p, heads=H, n_layers=nl)
+    assert rel_err(rep, g["out.rep"]) < 5e-6
+    (rep * g["in.up"]).sum().backward()
+    for k, v in g.items():
+        if k.startswith("grad."):
+            assert rel_err(p[k[5:]].grad, v) < 5e-5, k
+
+
+def test_infonce_golden():
+    for tag in ("n16", "n37", "n64d512"):
+        g = load_golden("infonce_" + tag)
+        q, k = g["in.q"].clone().requires_grad_(True), g["in.k"].clone().requires_grad_(True)
+        loss = restate.info_nce(q, k, 0.1)
+        loss.backward()
+        assert rel_err(loss, g["out.loss"]) < 1e-6
+        assert rel_err(q.grad, g["grad.q"]) < 1e-5 and rel_err(k.grad, g["grad.k"]) < 1e-5
+
+
+def test_ct_golden():
+    for n in (16, 45):
+        g = load_golden("ct_n%d" % n)
+        f = g["in.feature"]
+        cases = {
+            "regress_w": lambda x: restate.ct_regress(x, g["in.y"], g["in.yhat"], weights=g["in.weights"], w=0.2),
+            "regress_now": lambda x: restate.ct_regress(x, g["in.y"], g["in.yhat"], w=0.2),
+            "single": lambda x: restate.ct_single(x, g["in.cls"]),
+            "multi": lambda x: restate.ct_multi(x, g["in.multi"]),
+        }
+        for name, fn in cases.items():
+            x = f.clone().requires_grad_(True)
+            loss = fn(x)
+            loss.backward()
+            assert rel_err(loss, g["out." + name]) < 1e-6, name
+            assert rel_err(x.grad, g["grad." + name]) < 1e-5, name
+        for mode, lab in (("regress", "in.y"), ("single", "in.cls"), ("multi", "in.multi")):
+            pos, neg, _ = restate.ct_masks(mode, g[lab], g["in.yhat"], 0.2)
+            assert torch.equal(pos, g["out.%s_pos" % mode].bool())          # bit-exact
+            assert torch.equal(neg, g["out.%s_neg" % mode].bool())
+
+
+def test_fds_golden():
+    g = load_golden("fds")
+    cfg = dict(min_value=float(g["cfg.min_value"]), bin_width=float(g["cfg.bin_width"]), bucket_num=12,
+               bucket_start=0, start_update=0, start_smooth=1, momentum=0.9)
+    win = restate.fds_kernel_window("gaussian", 5, 1)
+    assert rel_err(win, g["cfg.window"]) < 1e-6
+    assert torch.equal(restate.fds_label_bins(g["in.labels"], cfg["min_value"], cfg["bin_width"]), g["out.bins"].long())
+    nb, D = 12, 16
+    st = {"epoch": torch.zeros(1), "running_mean": torch.zeros(nb, D), "running_var": torch.ones(nb, D),
+          "running_mean_last_epoch": torch.zeros(nb, D), "running_var_last_epoch": torch.ones(nb, D),
+          "smoothed_mean_last_epoch": torch.zeros(nb, D), "smoothed_var_last_epoch": torch.ones(nb, D),
+          "num_samples_tracked": torch.zeros(nb)}
+    restate.fds_update_running_stats(g["in.feats_e0"], g["in.labels"], 0, st, cfg)
+    restate.fds_update_last_epoch_stats(1, st, win)
+    for k in ("running_mean", "running_var", "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked"):
+        assert rel_err(st[k], g["out.e1." + k]) < 1e-5, k
+    x = g["in.smooth_x"].clone().requires_grad_(True)
+    xs = restate.fds_smooth(x * 1.0, g["in.labels"], 1, st, cfg)
+    (xs * g["in.smooth_up"]).sum().backward()
+    assert rel_err(xs, g["out.smooth"]) < 1e-5
+    assert rel_err(x.grad, g["grad.smooth_x"]) < 1e-5
+    sub = g["in.sub"].bool()
+    xs2 = restate.fds_smooth(g["in.smooth_x"][sub].clone(), g["in.labels"][sub], 1, st, cfg)
+    assert rel_err(xs2, g["out.smooth_noedge"]) < 1e-5
+    restate.fds_update_running_stats(g["in.feats_e1"], g["in.labels"], 1, st, cfg)
+    restate.fds_update_last_epoch_stats(2, st, win)
+    for k in ("running_mean", "running_var", "smoothed_mean_last_epoch", "smoothed_var_last_epoch", "num_samples_tracked"):
+        assert rel_err(st[k], g["out.e2." + k]) < 1e-5, k
+    m = g["in.cal_mat"]
+    v1z = g["in.cal_v1"].clone()
+    v1z[[2, 7]] = 0
+    args = (g["in.cal_m1"], g["in.cal_v1"], g["in.cal_m2"], g["in.cal_v2"])
+    assert rel_err(restate.calibrate_mean_var(m.clone(), *args), g["out.cal_full"]) < 1e-6
+    assert rel_err(restate.calibrate_mean_var(m.clone(), args[0], v1z, args[2], args[3]), g["out.cal_zero_cols"]) < 1e-6
+    assert rel_err(restate.calibrate_mean_var(m.clone(), args[0], args[1] * 0, args[2], args[3]), g["out.cal_tiny"]) < 1e-6
