@@ -15,6 +15,12 @@
  *     "pair" = the (B,H,L,L) pair tensor, "gpair" = its gradient.
  *   - all tensors are dense row-major; `ld*` arguments are row strides in ELEMENTS.
  *   - head_dim is fixed at 8 (Uni-Mol: 512-d / 64 heads, models/mm_model.py:325-343).
+ *   - PAIR LAYOUT: inside the library the pair tensor is (B, H, L, Lp) with row stride
+ *     Lp = mmdti_pair_ld(L) >= L (a multiple of 8 that is 8 mod 16): rows are 16-byte aligned and
+ *     one (molecule, head) tile is one contiguous range, which is what lets a tile move with a
+ *     single TMA bulk copy and sit bank-conflict-free in shared memory.  Padding columns
+ *     [L, Lp) hold -inf (0 in gradients).  mmdti_pair_pad / mmdti_pair_unpad convert from / to
+ *     the reference's dense (B*H, L, L) tensors.
  */
 #ifndef MMDTI_B200_H
 #define MMDTI_B200_H
@@ -39,13 +45,22 @@ extern "C" {
 int mmdti_version(void);
 const char* mmdti_last_error(void);
 
+/* row stride Lp of the padded pair layout for sequence length L (-1 if L > 264) */
+int mmdti_pair_ld(int L);
+/* dense (BH, L, L) in_dtype -> padded (BH, L, Lp) pair_dtype (padding columns = -inf), and back */
+int mmdti_pair_pad(const void* dense, void* padded, int BH, int L, int in_dtype, int pair_dtype,
+                   void* stream);
+int mmdti_pair_unpad(const void* padded, void* dense, int BH, int L, int pair_dtype, int out_dtype,
+                     void* stream);
+
 /* ---------------------------------------------------------------- K1: pair bias
  * Replaces GaussianLayer.forward + gaussian() + NonLinearHead.forward + permute/contiguous
  * (models/mm_model.py:211-224, 254-269, 117-128, 553-556; duplicates models/encoder.py:207-265,
  * 484-491):   u = mul[et]*dist + bias[et];  g_k = N(u; mean_k, |std_k|+1e-5) (pi=3.14159);
  *             out[b,h,i,j] = W2 gelu(W1 g + b1) + b2.
  * dist (B,L,L) f32, edge_type (B,L,L) int64, means/stds (K) f32, mul/bias (E) f32,
- * w1 (K,K) b1 (K) w2 (H,K) b2 (H) f32 (row-major, torch Linear layout), out (B,H,L,L) pair_dtype.
+ * w1 (K,K) b1 (K) w2 (H,K) b2 (H) f32 (row-major, torch Linear layout), out (B,H,L,Lp) pair_dtype
+ * (padded pair layout, padding columns written as -inf).
  * key_pad (B,L) uint8 or NULL: when given, padded KEY columns are written as -inf, i.e. the
  * merge of models/transformers.py:122-132 is fused into the producer.
  * K must be 128 and H must be 64. */
@@ -59,7 +74,7 @@ int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, const float
  * GEMMs on the host side, see mm-dti_b200/ops.py:PairBiasFn.backward):
  *  - mmdti_gauss_basis: the (npairs,128) basis g (out_dtype f32|bf16), i.e. GaussianLayer.forward
  *    alone (models/mm_model.py:254-269);
- *  - mmdti_pair_to_rows: (B,H,L,L) -> (B*L*L, H) transpose of the incoming gradient (non-finite
+ *  - mmdti_pair_to_rows: padded (B,H,L,Lp) -> (B*L*L, H) transpose of the incoming gradient (non-finite
  *    entries are written as 0);
  *  - mmdti_gauss_param_grad: from dG (npairs,128) accumulate (+=) d_means,d_stds (K) and the
  *    961-bin scatter d_mul,d_bias (E). */
@@ -73,10 +88,11 @@ int mmdti_gauss_param_grad(const void* dG, const float* dist, const int64_t* edg
                            const float* bias, float* d_means, float* d_stds, float* d_mul,
                            float* d_bias, int64_t npairs, int K, int E, int dg_dtype, void* stream);
 
-/* In-place merge of the key-padding mask into the pair bias: pair[b,h,i,j] = -inf where
- * key_pad[b,j] != 0.  Replaces fill_attn_mask, models/transformers.py:122-132 (bit-exact). */
-int mmdti_pair_mask_fill(void* pair, const uint8_t* key_pad, int B, int H, int L, int pair_dtype,
-                         float fill, void* stream);
+/* In-place merge of the key-padding mask into the pair bias: pair[b,h,i,j] = fill where
+ * key_pad[b,j] != 0.  Replaces fill_attn_mask, models/transformers.py:122-132 (bit-exact).
+ * ld = row stride of `pair`: L for the reference's dense tensor, Lp for the padded layout. */
+int mmdti_pair_mask_fill(void* pair, const uint8_t* key_pad, int B, int H, int L, int ld,
+                         int pair_dtype, float fill, void* stream);
 
 /* ---------------------------------------------------------------- K2: pair-biased attention
  * Replaces the attention core of Uni-Core's SelfMultiheadAttention(return_attn=True) as driven
@@ -85,7 +101,8 @@ int mmdti_pair_mask_fill(void* pair, const uint8_t* key_pad, int B, int H, int L
  *     A = dropout(softmax_rows(S));  O = A V
  * q,k,v: (B*L, *) act_dtype with row stride ldqkv; head h of token t lives at
  * columns [h*8, h*8+8) of row t (so q/k/v may point INTO the in_proj output: no transposes).
- * o: (B*L, H*8) with row stride ldo.  pair_in/pair_out (B,H,L,L) pair_dtype; may alias.
+ * o: (B*L, H*8) with row stride ldo.  pair_in/pair_out (B,H,L,Lp) pair_dtype (padded layout,
+ * -inf in the padding columns); may alias.
  * Dropout: element (b,h,i,j) is kept iff its counter-based random number (a function of
  * seed,b,h,i,j only) is >= round(p*65536); kept values are scaled by 65536/(65536-thresh). */
 int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, int64_t ldqkv,
@@ -95,7 +112,8 @@ int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, int64_t ldq
 
 /* Backward.  s = pair_out and o = the output of the forward call (same seed/dropout_p; o and d_o
  * share the row stride lddo; rowsum(dA o A) is taken as d_o . o).  d_pair_out may be NULL
- * (treated as 0).  Writes d_pair_in (gpair_dtype; may alias d_pair_out) and dq,dk,dv
+ * (treated as 0) and must be 0 wherever s is -inf.  Pair tensors are in the padded layout.
+ * Writes d_pair_in (gpair_dtype == pair_dtype; may alias d_pair_out) and dq,dk,dv
  * (act_dtype, row stride lddqkv, same head-column convention as q,k,v):
  *     dS = A o (dA - rowsum(dA o A)) + d_pair_out;  d_pair_in = dS;
  *     dQ = scale dS K;  dK = scale dS^T Q;  dV = A'^T dO. */
@@ -109,7 +127,7 @@ int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq
 int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, float dropout_p, uint64_t seed,
                                  void* stream);
 
-/* (B,H,L,L) pair_dtype -> (B,L,L,H) f32 "pair" and "delta pair" outputs of
+/* padded (B,H,L,Lp) pair_dtype -> dense (B,L,L,H) f32 "pair" and "delta pair" outputs of
  * TransformerEncoderWithPair.forward (models/transformers.py:163-172): pair_last permuted, and
  * delta = pair_last - pair_first with padded key columns (where pair_last is -inf) set to 0. */
 int mmdti_pair_outputs(const void* pair_first, const void* pair_last, float* pair_out,

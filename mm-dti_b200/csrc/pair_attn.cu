@@ -1,30 +1,39 @@
 // K2 — pair-biased multi-head self-attention (head_dim 8), forward and backward.
 //
-// One CTA per (molecule b, head h).  The (L,L) pair tile of that head is one contiguous
-// L*L-element range of the (B,H,L,L) tensor, so it is staged through shared memory with
-// fully coalesced flat copies (global -> smem rows padded to a bank-conflict-free stride),
-// consumed / produced in the register layout of mma.sync m16n8k8 / m16n8k16 (head_dim 8 is
-// exactly the K of m16n8k8 for Q K^T and the N of m16n8k16 for A V), and written back
-// with the same flat coalesced copy.  The kernel is bound by the pair-tensor HBM traffic
-// (read P + write P' forward; read S, read dP', write dP backward): 32 flop per 4..8 bytes.
+// Data layout.  The pair tensor is carried as (B, H, L, Lp) with Lp = 8*NKB, NKB odd, so every
+// row is 16-byte aligned, the (L x Lp) tile of one (molecule, head) is ONE contiguous 16-byte
+// aligned range, and Lp == 8 (mod 16) makes the same image bank-conflict-free in shared
+// memory.  Padding columns [L, Lp) hold -inf (an invariant every producer keeps), so they
+// vanish in the softmax without any column predicate.
+//
+// Execution.  Persistent CTAs walk a contiguous range of (tile, row-chunk) work items through a
+// 2-stage shared-memory ring: the pair slab of item w+1 arrives by ONE TMA bulk copy
+// (cp.async.bulk + mbarrier complete_tx) and the q/k/v head rows by 16-byte cp.async while item
+// w is computed; the updated slab leaves by one TMA bulk store.  Inside a CTA each warp owns
+// 16 query rows x all keys in the register layout of mma.sync m16n8k8 (Q K^T: K = head_dim = 8)
+// and m16n8k16 (A V: N = head_dim = 8).  32 flop per 4..8 bytes of pair traffic: the kernel
+// is bound by HBM / instruction issue, not by the tensor pipe.
 //
 // Reference semantics: Uni-Core SelfMultiheadAttention(return_attn=True) as driven by
 // models/transformers.py:136-139 (see include/mmdti_b200.h).
 #include "common.cuh"
 
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
 constexpr int HD = MMDTI_HEAD_DIM;  // 8
+constexpr int NSTAGE = 2;
+constexpr float LOG2E = 1.4426950408889634f;
 
-// row stride (elements) of the smem pair slabs: multiple of 8, and == 8 (mod 16) so that
-// (a) 32-bit fragment accesses of 8 rows x 4 column pairs hit 32 distinct banks and
-// (b) ldmatrix rows (16 B) of 8 consecutive slab rows hit 8 distinct 16-byte bank groups.
 template <int NKB> struct Geo {
-    static constexpr int KP = NKB * 8;                                // padded key count
-    static constexpr int STRIDE = (KP % 16 == 8) ? KP : KP + 8;
+    static_assert(NKB % 2 == 1, "NKB must be odd so that the row stride is 8 mod 16");
+    static constexpr int KP = NKB * 8;        // padded key count == pair row stride (elements)
+    static constexpr int STRIDE = KP;
     static constexpr int NKB16 = (NKB + 1) / 2;
+    static constexpr int KROWS = KP + 8;      // K/V smem rows (last 16-key block reads 8 rows past KP)
+    static constexpr int MAXKB16 = NKB <= 9 ? 1 : (NKB <= 17 ? 3 : 6);   // 16-key blocks per warp (bwd phase 2)
 };
 
 struct FwdParams {
@@ -37,7 +46,7 @@ struct FwdParams {
     float scale, keep_scale;
     uint32_t thresh16;
     unsigned long long seed;
-    int crb;   // 16-row blocks staged per chunk (<= warps per CTA)
+    int crb, nchunks;     // 16-row blocks per chunk, chunks per tile
 };
 
 struct BwdParams {
@@ -48,57 +57,8 @@ struct BwdParams {
     float scale, keep_scale;
     uint32_t thresh16;
     unsigned long long seed;
-    int crb;
+    int crb, nchunks;
 };
-
-// ------------------------------------------------------------------ slab copies
-// global (flat, contiguous nrows*L elements) <-> smem [nrows][STRIDE]
-template <typename TP, int STRIDE>
-__device__ __forceinline__ void slab_load(TP* __restrict__ slab, const TP* __restrict__ g, int nrows, int L,
-                                          int tid, int nthr) {
-    if (sizeof(TP) == 2 && (L & 1) == 0) {
-        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(g);
-        uint32_t* s32 = reinterpret_cast<uint32_t*>(slab);
-        const int Lh = L >> 1, n = nrows * Lh;
-        const FastDiv fd(Lh);
-#pragma unroll 4
-        for (int e = tid; e < n; e += nthr) {
-            const int r = fd.div(e), c = e - r * Lh;
-            s32[r * (STRIDE / 2) + c] = __ldg(g32 + e);
-        }
-    } else {
-        const int n = nrows * L;
-        const FastDiv fd(L);
-#pragma unroll 4
-        for (int e = tid; e < n; e += nthr) {
-            const int r = fd.div(e), c = e - r * L;
-            slab[r * STRIDE + c] = g[e];
-        }
-    }
-}
-template <typename TP, int STRIDE>
-__device__ __forceinline__ void slab_store(TP* __restrict__ g, const TP* __restrict__ slab, int nrows, int L,
-                                           int tid, int nthr) {
-    if (sizeof(TP) == 2 && (L & 1) == 0) {
-        uint32_t* g32 = reinterpret_cast<uint32_t*>(g);
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(slab);
-        const int Lh = L >> 1, n = nrows * Lh;
-        const FastDiv fd(Lh);
-#pragma unroll 4
-        for (int e = tid; e < n; e += nthr) {
-            const int r = fd.div(e), c = e - r * Lh;
-            g32[e] = s32[r * (STRIDE / 2) + c];
-        }
-    } else {
-        const int n = nrows * L;
-        const FastDiv fd(L);
-#pragma unroll 4
-        for (int e = tid; e < n; e += nthr) {
-            const int r = fd.div(e), c = e - r * L;
-            g[e] = slab[r * STRIDE + c];
-        }
-    }
-}
 
 // two adjacent pair elements (col even) of a slab row -> floats
 template <typename TP> __device__ __forceinline__ float2 slab_get2(const TP* row, int col) {
@@ -120,111 +80,131 @@ template <typename TP> __device__ __forceinline__ float2 slab_put2(TP* row, int 
     }
 }
 
-template <typename T> __device__ __forceinline__ void load_head_row(float (&dst)[HD], const T* p) {
-    if constexpr (std::is_same<T, float>::value) {
-        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
-        dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
-    } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(p);
-        float2 f;
-        f = unpack_bf16(u.x); dst[0] = f.x; dst[1] = f.y;
-        f = unpack_bf16(u.y); dst[2] = f.x; dst[3] = f.y;
-        f = unpack_bf16(u.z); dst[4] = f.x; dst[5] = f.y;
-        f = unpack_bf16(u.w); dst[6] = f.x; dst[7] = f.y;
-    }
+// cp.async one head row (8 elements of T) global -> shared
+template <typename T> __device__ __forceinline__ void cp_head_row(T* dst, const T* src) {
+    cp_async_16(dst, src);
+    if constexpr (sizeof(T) == 4) cp_async_16(dst + 4, src + 4);
+}
+
+template <typename T> __device__ __forceinline__ void zero_fill(T* p, int n, int tid, int nthr) {
+    for (int i = tid; i < n; i += nthr) p[i] = from_f<T>(0.f);
 }
 
 // ===================================================================== forward
-// smem layout (T = bf16):  Ks [KP][8] bf16 | Vt [8][STRIDE] bf16 | slab [NW*16][STRIDE] TP
-//             (T = float): Ks [KP][8] f32  | Vs [KP][8] f32      | slab
+template <typename T, typename TP, int NKB>
+struct FwdStage {
+    using G = Geo<NKB>;
+    T* K;      // [KROWS][8]
+    T* V;      // [KROWS][8]
+    T* Q;      // [NR][8]
+    TP* slab;  // [NR][STRIDE]
+    static __host__ __device__ size_t bytes(int NR) {
+        return (size_t)(2 * G::KROWS + NR) * HD * sizeof(T) + (size_t)NR * G::STRIDE * sizeof(TP);
+    }
+    __device__ void carve(unsigned char* base, int NR) {
+        K = reinterpret_cast<T*>(base);
+        V = K + G::KROWS * HD;
+        Q = V + G::KROWS * HD;
+        slab = reinterpret_cast<TP*>(Q + NR * HD);
+    }
+};
+
 template <typename T, typename TP, int NKB>
 __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
     using G = Geo<NKB>;
     constexpr bool F32 = std::is_same<T, float>::value;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* Ks = reinterpret_cast<T*>(smem_raw);
-    T* Vx = Ks + G::KP * HD;                                            // Vt (bf16) or Vs (f32)
-    constexpr int VX_ELEMS = F32 ? G::KP * HD : HD * G::STRIDE;
-    TP* slab = reinterpret_cast<TP*>(Vx + VX_ELEMS);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
 
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
-    const int nwarps = nthr >> 5;
     const int g = lane >> 2, q4 = lane & 3;
-    const int bh = blockIdx.x, b = bh / p.H, h = bh - b * p.H;
-    const int L = p.L;
-    const T* qg = static_cast<const T*>(p.q) + (size_t)b * L * p.ldqkv + h * HD;
-    const T* kg = static_cast<const T*>(p.k) + (size_t)b * L * p.ldqkv + h * HD;
-    const T* vg = static_cast<const T*>(p.v) + (size_t)b * L * p.ldqkv + h * HD;
-    T* og = static_cast<T*>(p.o) + (size_t)b * L * p.ldo + h * HD;
-    const TP* pin = static_cast<const TP*>(p.pin) + (size_t)bh * L * L;
-    TP* pout = static_cast<TP*>(p.pout) + (size_t)bh * L * L;
+    const int L = p.L, NR = p.crb * 16;
 
-    // ---- stage K (row-major) and V (transposed for the bf16 path) of this head
-    for (int key = tid; key < G::KP; key += nthr) {
-        float kr[HD], vr[HD];
-        if (key < L) {
-            load_head_row(kr, kg + (size_t)key * p.ldqkv);
-            load_head_row(vr, vg + (size_t)key * p.ldqkv);
-        } else {
+    FwdStage<T, TP, NKB> st[NSTAGE];
+    const size_t stage_bytes = (FwdStage<T, TP, NKB>::bytes(NR) + 127) & ~size_t(127);
 #pragma unroll
-            for (int d = 0; d < HD; ++d) kr[d] = vr[d] = 0.f;
-        }
-#pragma unroll
-        for (int d = 0; d < HD; ++d) {
-            Ks[key * HD + d] = from_f<T>(kr[d]);
-            if constexpr (F32) Vx[key * HD + d] = vr[d];
-            else Vx[d * G::STRIDE + key] = from_f<T>(vr[d]);
-        }
-    }
-    if constexpr (!F32 && (G::STRIDE > G::KP)) {   // zero the stride padding of Vt (never read; kept clean)
-        constexpr int PADC = G::STRIDE - G::KP;
-        for (int i = tid; i < HD * PADC; i += nthr) {
-            const int d = i / PADC, c = i - d * PADC;
-            Vx[d * G::STRIDE + G::KP + c] = from_f<T>(0.f);
-        }
-    }
+    for (int s = 0; s < NSTAGE; ++s) st[s].carve(smem_raw + s * stage_bytes, NR);
 
-    const uint32_t rkey = rng_stream_key(p.seed, (uint32_t)bh);
+    // one-time init: zero K/V/Q (rows beyond L stay zero for ever), barriers
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) zero_fill(st[s].K, (2 * G::KROWS + NR) * HD, tid, nthr);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long ntiles = (long long)p.B * p.H;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const long long w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
+    const size_t tile_elems = (size_t)L * G::STRIDE;
+
+    auto prefetch = [&](long long w, int s) {
+        const long long tile = w / p.nchunks;
+        const int chunk = (int)(w - tile * p.nchunks);
+        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+        const int row0 = chunk * NR, nrows = min(L - row0, NR);
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP));
+            mbar_arrive_expect_tx(&full_bar[s], bytes);
+            bulk_g2s(st[s].slab, static_cast<const TP*>(p.pin) + tile * tile_elems + (size_t)row0 * G::STRIDE, bytes,
+                     &full_bar[s]);
+        }
+        const T* qg = static_cast<const T*>(p.q) + (size_t)b * L * p.ldqkv + h * HD;
+        const T* kg = static_cast<const T*>(p.k) + (size_t)b * L * p.ldqkv + h * HD;
+        const T* vg = static_cast<const T*>(p.v) + (size_t)b * L * p.ldqkv + h * HD;
+        for (int i = tid; i < 2 * L + nrows; i += nthr) {
+            if (i < L) cp_head_row(st[s].K + i * HD, kg + (size_t)i * p.ldqkv);
+            else if (i < 2 * L) cp_head_row(st[s].V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
+            else cp_head_row(st[s].Q + (i - 2 * L) * HD, qg + (size_t)(row0 + i - 2 * L) * p.ldqkv);
+        }
+        cp_async_commit();
+    };
+
     const bool do_drop = p.thresh16 != 0;
-    const int nrb = (L + 15) >> 4;
+    if (w0 < w1) prefetch(w0, 0);
 
-    for (int rb0 = 0; rb0 < nrb; rb0 += p.crb) {
-        const int row0 = rb0 * 16;
-        const int nrows = min(L - row0, p.crb * 16);
-        __syncthreads();
-        slab_load<TP, G::STRIDE>(slab, pin + (size_t)row0 * L, nrows, L, tid, nthr);
-        __syncthreads();
+    int it = 0;
+    for (long long w = w0; w < w1; ++w, ++it) {
+        const int s = it & 1;
+        const long long tile = w / p.nchunks;
+        const int chunk = (int)(w - tile * p.nchunks);
+        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+        const int row0 = chunk * NR, nrows = min(L - row0, NR);
 
-        const int rb = rb0 + warp;
-        if (warp < p.crb && rb < nrb) {
-            const int ra = rb * 16 + g, rbb = ra + 8;            // global query rows of this thread
-            TP* srow_a = slab + (ra - row0) * G::STRIDE;
-            TP* srow_b = srow_a + 8 * G::STRIDE;
-            float s[NKB][4];
+        cp_async_wait<0>();
+        mbar_wait(&full_bar[s], (it >> 1) & 1);
+        __syncthreads();                    // item w is resident; everyone is done with item w-1
+        if (w + 1 < w1) {
+            if (tid == 0) bulk_wait_read<0>();       // the store that last read stage s^1 has drained it
+            prefetch(w + 1, s ^ 1);
+        }
+
+        if (warp < p.crb && row0 + warp * 16 < L) {
+            const T* Ks = st[s].K;
+            const T* Vs = st[s].V;
+            const T* Qs = st[s].Q;
+            const int la = warp * 16 + g, lb = la + 8;               // local rows
+            const int ra = row0 + la, rbb = row0 + lb;                // global rows
+            TP* srow_a = st[s].slab + la * G::STRIDE;
+            TP* srow_b = st[s].slab + lb * G::STRIDE;
+            float sc[NKB][4];
 
             // ---- S = Q K^T
             if constexpr (!F32) {
-                const uint32_t qa0 = ra < L ? *reinterpret_cast<const uint32_t*>(qg + (size_t)ra * p.ldqkv + 2 * q4) : 0u;
-                const uint32_t qa1 = rbb < L ? *reinterpret_cast<const uint32_t*>(qg + (size_t)rbb * p.ldqkv + 2 * q4) : 0u;
-                const uint32_t* Ks32 = reinterpret_cast<const uint32_t*>(Ks);
+                const uint32_t* Q32 = reinterpret_cast<const uint32_t*>(Qs);
+                const uint32_t* K32 = reinterpret_cast<const uint32_t*>(Ks);
+                const uint32_t qa0 = Q32[la * 4 + q4], qa1 = Q32[lb * 4 + q4];
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
-                    s[kb][0] = s[kb][1] = s[kb][2] = s[kb][3] = 0.f;
-                    mma_bf16_1688(s[kb], qa0, qa1, Ks32[(kb * 8 + g) * 4 + q4]);
+                    sc[kb][0] = sc[kb][1] = sc[kb][2] = sc[kb][3] = 0.f;
+                    mma_bf16_1688(sc[kb], qa0, qa1, K32[(kb * 8 + g) * 4 + q4]);
                 }
             } else {
                 float qa[HD], qb[HD];
-                if (ra < L) load_head_row(qa, qg + (size_t)ra * p.ldqkv);
-                else {
 #pragma unroll
-                    for (int d = 0; d < HD; ++d) qa[d] = 0.f;
-                }
-                if (rbb < L) load_head_row(qb, qg + (size_t)rbb * p.ldqkv);
-                else {
-#pragma unroll
-                    for (int d = 0; d < HD; ++d) qb[d] = 0.f;
-                }
+                for (int d = 0; d < HD; ++d) { qa[d] = Qs[la * HD + d]; qb[d] = Qs[lb * HD + d]; }
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
@@ -236,23 +216,21 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
                             da = fmaf(qa[d], kr[d], da);
                             db = fmaf(qb[d], kr[d], db);
                         }
-                        s[kb][e] = da;
-                        s[kb][2 + e] = db;
+                        sc[kb][e] = da;
+                        sc[kb][2 + e] = db;
                     }
                 }
             }
 
-            // ---- S = scale*S + P ; P' := S (stored, rounded to TP) ; running row max
+            // ---- S = scale*S + P ; P' := S (stored, rounded to TP) ; row max
             float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 const int col = kb * 8 + 2 * q4;
                 const float2 pa = slab_get2<TP>(srow_a, col), pb = slab_get2<TP>(srow_b, col);
-                float2 va = slab_put2<TP>(srow_a, col, fmaf(s[kb][0], p.scale, pa.x), fmaf(s[kb][1], p.scale, pa.y));
-                float2 vb = slab_put2<TP>(srow_b, col, fmaf(s[kb][2], p.scale, pb.x), fmaf(s[kb][3], p.scale, pb.y));
-                if (col >= L) { va.x = -INFINITY; vb.x = -INFINITY; }
-                if (col + 1 >= L) { va.y = -INFINITY; vb.y = -INFINITY; }
-                s[kb][0] = va.x; s[kb][1] = va.y; s[kb][2] = vb.x; s[kb][3] = vb.y;
+                const float2 va = slab_put2<TP>(srow_a, col, fmaf(sc[kb][0], p.scale, pa.x), fmaf(sc[kb][1], p.scale, pa.y));
+                const float2 vb = slab_put2<TP>(srow_b, col, fmaf(sc[kb][2], p.scale, pb.x), fmaf(sc[kb][3], p.scale, pb.y));
+                sc[kb][0] = va.x; sc[kb][1] = va.y; sc[kb][2] = vb.x; sc[kb][3] = vb.y;
                 ma = fmaxf(ma, fmaxf(va.x, va.y));
                 mb = fmaxf(mb, fmaxf(vb.x, vb.y));
             }
@@ -261,47 +239,66 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
 
             // ---- softmax numerators, row sums, dropout
             float suma = 0.f, sumb = 0.f;
+            if constexpr (F32) {
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                    sc[kb][0] = expf(sc[kb][0] - ma); sc[kb][1] = expf(sc[kb][1] - ma);
+                    sc[kb][2] = expf(sc[kb][2] - mb); sc[kb][3] = expf(sc[kb][3] - mb);
+                }
+            } else {
+                const float ka = ma * LOG2E, kbm = mb * LOG2E;
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                    sc[kb][0] = exp2f(fmaf(sc[kb][0], LOG2E, -ka));
+                    sc[kb][1] = exp2f(fmaf(sc[kb][1], LOG2E, -ka));
+                    sc[kb][2] = exp2f(fmaf(sc[kb][2], LOG2E, -kbm));
+                    sc[kb][3] = exp2f(fmaf(sc[kb][3], LOG2E, -kbm));
+                }
+            }
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
-                if constexpr (F32) {
-                    s[kb][0] = expf(s[kb][0] - ma); s[kb][1] = expf(s[kb][1] - ma);
-                    s[kb][2] = expf(s[kb][2] - mb); s[kb][3] = expf(s[kb][3] - mb);
-                } else {
-                    s[kb][0] = __expf(s[kb][0] - ma); s[kb][1] = __expf(s[kb][1] - ma);
-                    s[kb][2] = __expf(s[kb][2] - mb); s[kb][3] = __expf(s[kb][3] - mb);
-                }
-                suma += s[kb][0] + s[kb][1];
-                sumb += s[kb][2] + s[kb][3];
-                if (do_drop) {
+                suma += sc[kb][0] + sc[kb][1];
+                sumb += sc[kb][2] + sc[kb][3];
+            }
+            if (do_drop) {
+                const uint32_t rkey = rng_stream_key(p.seed, (uint32_t)tile);
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
                     const int col = kb * 8 + 2 * q4;
                     const uint32_t ba = rng_pair_bits(rkey, ra, col), bb = rng_pair_bits(rkey, rbb, col);
-                    if (!rng_keep(ba, 0, p.thresh16)) s[kb][0] = 0.f;
-                    if (!rng_keep(ba, 1, p.thresh16)) s[kb][1] = 0.f;
-                    if (!rng_keep(bb, 0, p.thresh16)) s[kb][2] = 0.f;
-                    if (!rng_keep(bb, 1, p.thresh16)) s[kb][3] = 0.f;
+                    if (!rng_keep(ba, 0, p.thresh16)) sc[kb][0] = 0.f;
+                    if (!rng_keep(ba, 1, p.thresh16)) sc[kb][1] = 0.f;
+                    if (!rng_keep(bb, 0, p.thresh16)) sc[kb][2] = 0.f;
+                    if (!rng_keep(bb, 1, p.thresh16)) sc[kb][3] = 0.f;
                 }
             }
             suma = quad_sum(suma);
             sumb = quad_sum(sumb);
             const float inva = p.keep_scale / suma, invb = p.keep_scale / sumb;
+            T* og = static_cast<T*>(p.o) + (size_t)b * L * p.ldo + h * HD;
 
             // ---- O = A' V
             if constexpr (!F32) {
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t* Vt32 = reinterpret_cast<const uint32_t*>(Vx);
 #pragma unroll
-                for (int j = 0; j < G::NKB16; ++j) {
-                    const int kb0 = 2 * j, kb1 = 2 * j + 1;
-                    const uint32_t a0 = pack_bf16(s[kb0][0], s[kb0][1]);
-                    const uint32_t a1 = pack_bf16(s[kb0][2], s[kb0][3]);
-                    uint32_t a2 = 0u, a3 = 0u, b1 = 0u;
-                    const uint32_t b0 = Vt32[(g * G::STRIDE + kb0 * 8 + 2 * q4) >> 1];
-                    if (kb1 < NKB) {
-                        a2 = pack_bf16(s[kb1][0], s[kb1][1]);
-                        a3 = pack_bf16(s[kb1][2], s[kb1][3]);
-                        b1 = Vt32[(g * G::STRIDE + kb1 * 8 + 2 * q4) >> 1];
+                for (int j = 0; j < G::NKB16; j += 2) {
+                    uint32_t b0, b1, b2 = 0u, b3 = 0u;
+                    if (j + 1 < G::NKB16) ldmatrix_x4_trans(b0, b1, b2, b3, Vs + (j * 16 + lane) * HD);
+                    else ldmatrix_x2_trans(b0, b1, Vs + (j * 16 + (lane & 15)) * HD);
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        if (j + jj < G::NKB16) {
+                            const int kb0 = 2 * (j + jj), kb1 = kb0 + 1;
+                            const uint32_t a0 = pack_bf16(sc[kb0][0], sc[kb0][1]);
+                            const uint32_t a1 = pack_bf16(sc[kb0][2], sc[kb0][3]);
+                            uint32_t a2 = 0u, a3 = 0u;
+                            if (kb1 < NKB) {
+                                a2 = pack_bf16(sc[kb1][0], sc[kb1][1]);
+                                a3 = pack_bf16(sc[kb1][2], sc[kb1][3]);
+                            }
+                            mma_bf16_16816(o, a0, a1, a2, a3, jj ? b2 : b0, jj ? b3 : b1);
+                        }
                     }
-                    mma_bf16_16816(o, a0, a1, a2, a3, b0, b1);
                 }
                 if (ra < L)
                     *reinterpret_cast<uint32_t*>(og + (size_t)ra * p.ldo + 2 * q4) = pack_bf16(o[0] * inva, o[1] * inva);
@@ -315,11 +312,11 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
                 for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float* vr = Vx + (kb * 8 + 2 * q4 + e) * HD;
+                        const float* vr = Vs + (kb * 8 + 2 * q4 + e) * HD;
 #pragma unroll
                         for (int d = 0; d < HD; ++d) {
-                            oa[d] = fmaf(s[kb][e], vr[d], oa[d]);
-                            ob[d] = fmaf(s[kb][2 + e], vr[d], ob[d]);
+                            oa[d] = fmaf(sc[kb][e], vr[d], oa[d]);
+                            ob[d] = fmaf(sc[kb][2 + e], vr[d], ob[d]);
                         }
                     }
                 }
@@ -342,186 +339,240 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
                 }
             }
         }
+        fence_proxy_async();
         __syncthreads();
-        slab_store<TP, G::STRIDE>(pout + (size_t)row0 * L, slab, nrows, L, tid, nthr);
+        if (tid == 0) {
+            bulk_s2g(static_cast<TP*>(p.pout) + tile * tile_elems + (size_t)row0 * G::STRIDE, st[s].slab,
+                     (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP)));
+            bulk_commit();
+        }
     }
+    if (tid == 0) bulk_wait_all<0>();
 }
 
 // ===================================================================== backward
-// smem layout, T = bf16 (NR = crb*16 rows per chunk, LR = 16*ceil(L/16) rows):
-//   Kt [8][STRIDE] bf16 | Vs [KP][8] bf16 | Qs [LR][8] bf16 | dOs [LR][8] bf16 |
-//   sS [NR][STRIDE] TP | sG [NR][STRIDE] TG | dSt [NR][STRIDE] bf16 | Apt [NR][STRIDE] bf16
-// T = float: Ks,Vs,Qs,dOs f32 [..][8]; dSt/Apt f32; dKacc,dVacc [KP][8] f32 at the end.
-// delta_i = rowsum(dA o A) is taken as dO_i . O_i (O from the forward), so a row's dA never
-// has to be resident all at once.
+// delta_i = rowsum(dA o A) is taken as dO_i . O_i (O from the forward).
+// Contract: the incoming d_pair_out is 0 wherever S = -inf (masked keys / padding columns);
+// A is exactly 0 there, so dS = A o (dA - delta) + d_pair_out is 0 there too, unpredicated.
+template <typename T, typename TP, typename TG, int NKB>
+struct BwdStage {
+    using G = Geo<NKB>;
+    T *K, *V;            // [KROWS][8]
+    T *Q, *dO, *O;       // [NR][8]
+    TP* sS;              // [NR][STRIDE]
+    TG* sG;              // [NR][STRIDE]
+    static __host__ __device__ size_t bytes(int NR) {
+        return (size_t)(2 * G::KROWS + 3 * NR) * HD * sizeof(T) + (size_t)NR * G::STRIDE * (sizeof(TP) + sizeof(TG));
+    }
+    __device__ void carve(unsigned char* base, int NR) {
+        K = reinterpret_cast<T*>(base);
+        V = K + G::KROWS * HD;
+        Q = V + G::KROWS * HD;
+        dO = Q + NR * HD;
+        O = dO + NR * HD;
+        sS = reinterpret_cast<TP*>(O + NR * HD);
+        sG = reinterpret_cast<TG*>(sS + NR * G::STRIDE);
+    }
+};
+
 template <typename T, typename TP, typename TG, int NKB>
 __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
     using G = Geo<NKB>;
     constexpr bool F32 = std::is_same<T, float>::value;
-    constexpr int MAXKB16 = 3;   // 16-key blocks per warp in phase 2 (host: ceil(nrb/nwarps) <= 3)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // dS in the mma operand type: aliases the dP slab when that already has this type
+    constexpr bool ALIAS_DS = std::is_same<T, TG>::value;
+    constexpr int MAXKB16 = G::MAXKB16;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
 
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int nwarps = nthr >> 5;
     const int g = lane >> 2, q4 = lane & 3;
-    const int bh = blockIdx.x, b = bh / p.H, h = bh - b * p.H;
-    const int L = p.L;
-    const int nrb = (L + 15) >> 4, LR = nrb * 16, NR = p.crb * 16;
+    const int L = p.L, NR = p.crb * 16;
+    const int nkb16 = (L + 15) >> 4;
 
-    T* Kx = reinterpret_cast<T*>(smem_raw);                      // Kt (bf16) / Ks (f32)
-    constexpr int KX_ELEMS = F32 ? G::KP * HD : HD * G::STRIDE;
-    T* Vs = Kx + KX_ELEMS;
-    T* Qs = Vs + G::KP * HD;
-    T* dOs = Qs + LR * HD;
-    TP* sS = reinterpret_cast<TP*>(dOs + LR * HD);
-    TG* sG = reinterpret_cast<TG*>(sS + NR * G::STRIDE);
-    T* dSt = reinterpret_cast<T*>(sG + NR * G::STRIDE);
-    T* Apt = dSt + NR * G::STRIDE;
-    float* dKacc = reinterpret_cast<float*>(Apt + NR * G::STRIDE);   // f32 path only
+    BwdStage<T, TP, TG, NKB> st[NSTAGE];
+    const size_t stage_bytes = (BwdStage<T, TP, TG, NKB>::bytes(NR) + 127) & ~size_t(127);
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) st[s].carve(smem_raw + s * stage_bytes, NR);
+    unsigned char* extra = smem_raw + NSTAGE * stage_bytes;
+    T* Apt = reinterpret_cast<T*>(extra);                            // [NR][STRIDE] dropped probabilities
+    T* dSt_own = Apt + NR * G::STRIDE;                               // [NR][STRIDE] (only when !ALIAS_DS)
+    float* dKacc = reinterpret_cast<float*>(ALIAS_DS ? dSt_own : dSt_own + NR * G::STRIDE);   // f32 path only
     float* dVacc = dKacc + G::KP * HD;
 
-    const T* qg = static_cast<const T*>(p.q) + (size_t)b * L * p.ldqkv + h * HD;
-    const T* kg = static_cast<const T*>(p.k) + (size_t)b * L * p.ldqkv + h * HD;
-    const T* vg = static_cast<const T*>(p.v) + (size_t)b * L * p.ldqkv + h * HD;
-    const T* og = static_cast<const T*>(p.o) + (size_t)b * L * p.lddo + h * HD;
-    const T* dog = static_cast<const T*>(p.d_o) + (size_t)b * L * p.lddo + h * HD;
-    T* dqg = static_cast<T*>(p.dq) + (size_t)b * L * p.lddqkv + h * HD;
-    T* dkg = static_cast<T*>(p.dk) + (size_t)b * L * p.lddqkv + h * HD;
-    T* dvg = static_cast<T*>(p.dv) + (size_t)b * L * p.lddqkv + h * HD;
-    const TP* sg = static_cast<const TP*>(p.s) + (size_t)bh * L * L;
-    const TG* dpo = p.dpout ? static_cast<const TG*>(p.dpout) + (size_t)bh * L * L : nullptr;
-    TG* dpi = static_cast<TG*>(p.dpin) + (size_t)bh * L * L;
-
-    // ---- stage K, V, Q, dO of this head (zero rows beyond L)
-    for (int r = tid; r < max(G::KP, LR); r += nthr) {
-        float kr[HD], vr[HD], qr[HD], gr[HD];
-        if (r < L) {
-            load_head_row(kr, kg + (size_t)r * p.ldqkv);
-            load_head_row(vr, vg + (size_t)r * p.ldqkv);
-            load_head_row(qr, qg + (size_t)r * p.ldqkv);
-            load_head_row(gr, dog + (size_t)r * p.lddo);
-        } else {
 #pragma unroll
-            for (int d = 0; d < HD; ++d) kr[d] = vr[d] = qr[d] = gr[d] = 0.f;
-        }
+    for (int s = 0; s < NSTAGE; ++s) {
+        zero_fill(st[s].K, (2 * G::KROWS + 3 * NR) * HD, tid, nthr);
+        zero_fill(st[s].sG, NR * G::STRIDE, tid, nthr);
+    }
+    if (tid == 0) {
 #pragma unroll
-        for (int d = 0; d < HD; ++d) {
-            if (r < G::KP) {
-                if constexpr (F32) Kx[r * HD + d] = kr[d];
-                else Kx[d * G::STRIDE + r] = from_f<T>(kr[d]);
-                Vs[r * HD + d] = from_f<T>(vr[d]);
-            }
-            if (r < LR) {
-                Qs[r * HD + d] = from_f<T>(qr[d]);
-                dOs[r * HD + d] = from_f<T>(gr[d]);
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long ntiles = (long long)p.B * p.H;
+    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
+    const long long w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
+    const size_t tile_elems = (size_t)L * G::STRIDE;
+    const bool has_dpo = p.dpout != nullptr;
+
+    auto prefetch = [&](long long w, int s) {
+        const long long tile = w / p.nchunks;
+        const int chunk = (int)(w - tile * p.nchunks);
+        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+        const int row0 = chunk * NR, nrows = min(L - row0, NR);
+        if (tid == 0) {
+            const uint32_t bs = (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP));
+            const uint32_t bg = has_dpo ? (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TG)) : 0u;
+            mbar_arrive_expect_tx(&full_bar[s], bs + bg);
+            bulk_g2s(st[s].sS, static_cast<const TP*>(p.s) + tile * tile_elems + (size_t)row0 * G::STRIDE, bs, &full_bar[s]);
+            if (has_dpo)
+                bulk_g2s(st[s].sG, static_cast<const TG*>(p.dpout) + tile * tile_elems + (size_t)row0 * G::STRIDE, bg,
+                         &full_bar[s]);
+        }
+        const size_t tok = (size_t)b * L;
+        const T* qg = static_cast<const T*>(p.q) + tok * p.ldqkv + h * HD;
+        const T* kg = static_cast<const T*>(p.k) + tok * p.ldqkv + h * HD;
+        const T* vg = static_cast<const T*>(p.v) + tok * p.ldqkv + h * HD;
+        const T* og = static_cast<const T*>(p.o) + tok * p.lddo + h * HD;
+        const T* dog = static_cast<const T*>(p.d_o) + tok * p.lddo + h * HD;
+        for (int i = tid; i < 2 * L + 3 * nrows; i += nthr) {
+            if (i < L) cp_head_row(st[s].K + i * HD, kg + (size_t)i * p.ldqkv);
+            else if (i < 2 * L) cp_head_row(st[s].V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
+            else {
+                const int j = i - 2 * L, which = j / nrows, r = j - which * nrows;
+                if (which == 0) cp_head_row(st[s].Q + r * HD, qg + (size_t)(row0 + r) * p.ldqkv);
+                else if (which == 1) cp_head_row(st[s].dO + r * HD, dog + (size_t)(row0 + r) * p.lddo);
+                else cp_head_row(st[s].O + r * HD, og + (size_t)(row0 + r) * p.lddo);
             }
         }
-    }
-    if constexpr (F32) {
-        for (int i = tid; i < G::KP * HD; i += nthr) dKacc[i] = dVacc[i] = 0.f;
-    }
+        cp_async_commit();
+    };
 
-    const uint32_t rkey = rng_stream_key(p.seed, (uint32_t)bh);
     const bool do_drop = p.thresh16 != 0;
-
     float dk_acc[MAXKB16][4], dv_acc[MAXKB16][4];
-#pragma unroll
-    for (int i = 0; i < MAXKB16; ++i)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dk_acc[i][c] = dv_acc[i][c] = 0.f;
 
-    for (int rb0 = 0; rb0 < nrb; rb0 += p.crb) {
-        const int row0 = rb0 * 16;
-        const int nrows = min(L - row0, NR);
-        const int nrb_chunk = min(nrb - rb0, p.crb);
-        __syncthreads();
-        slab_load<TP, G::STRIDE>(sS, sg + (size_t)row0 * L, nrows, L, tid, nthr);
-        if (dpo) slab_load<TG, G::STRIDE>(sG, dpo + (size_t)row0 * L, nrows, L, tid, nthr);
-        __syncthreads();
+    if (w0 < w1) prefetch(w0, 0);
+    int it = 0;
+    for (long long w = w0; w < w1; ++w, ++it) {
+        const int s = it & 1;
+        const long long tile = w / p.nchunks;
+        const int chunk = (int)(w - tile * p.nchunks);
+        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+        const int row0 = chunk * NR, nrows = min(L - row0, NR);
+        const int nrb_chunk = (nrows + 15) >> 4;
+
+        cp_async_wait<0>();
+        mbar_wait(&full_bar[s], (it >> 1) & 1);
+        __syncthreads();        // item w resident; item w-1 (incl. its phase 2 readers) finished everywhere
+        if (w + 1 < w1) {
+            if (tid == 0) bulk_wait_read<0>();
+            prefetch(w + 1, s ^ 1);
+        }
+
+        if (chunk == 0) {
+#pragma unroll
+            for (int i = 0; i < MAXKB16; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dk_acc[i][c] = dv_acc[i][c] = 0.f;
+            if constexpr (F32) {
+                for (int i = tid; i < G::KP * HD; i += nthr) dKacc[i] = dVacc[i] = 0.f;
+            }
+        }
+
+        const T* Ks = st[s].K;
+        const T* Vs = st[s].V;
+        const T* Qs = st[s].Q;
+        const T* dOs = st[s].dO;
+        const T* Os = st[s].O;
+        T* dSt = ALIAS_DS ? reinterpret_cast<T*>(st[s].sG) : dSt_own;
 
         // ================= phase 1: per 16-row block: A, dA, dS, dQ
-        const int rb = rb0 + warp;
-        if (warp < p.crb && rb < nrb) {
-            const int ra = rb * 16 + g, rbb = ra + 8;
-            const int la = ra - row0, lb = la + 8;
-            const TP* srow_a = sS + la * G::STRIDE;
-            const TP* srow_b = sS + lb * G::STRIDE;
-            TG* grow_a = sG + la * G::STRIDE;
-            TG* grow_b = sG + lb * G::STRIDE;
+        if (warp < nrb_chunk) {
+            const int la = warp * 16 + g, lb = la + 8;
+            const int ra = row0 + la, rbb = row0 + lb;
+            const TP* srow_a = st[s].sS + la * G::STRIDE;
+            const TP* srow_b = st[s].sS + lb * G::STRIDE;
+            TG* grow_a = st[s].sG + la * G::STRIDE;
+            TG* grow_b = st[s].sG + lb * G::STRIDE;
             T* ap_a = Apt + la * G::STRIDE;
             T* ap_b = Apt + lb * G::STRIDE;
             T* ds_a = dSt + la * G::STRIDE;
             T* ds_b = dSt + lb * G::STRIDE;
             const bool va_ok = ra < L, vb_ok = rbb < L;
 
-            // ---- softmax recompute: s[][] := A (normalised probabilities)
-            float s[NKB][4];
+            // ---- softmax recompute: sc[][] := exp(S - max)
+            float sc[NKB][4];
             float ma = -INFINITY, mb = -INFINITY;
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 const int col = kb * 8 + 2 * q4;
-                float2 xa = slab_get2<TP>(srow_a, col), xb = slab_get2<TP>(srow_b, col);
-                if (col >= L || !va_ok) xa.x = -INFINITY;
-                if (col + 1 >= L || !va_ok) xa.y = -INFINITY;
-                if (col >= L || !vb_ok) xb.x = -INFINITY;
-                if (col + 1 >= L || !vb_ok) xb.y = -INFINITY;
-                s[kb][0] = xa.x; s[kb][1] = xa.y; s[kb][2] = xb.x; s[kb][3] = xb.y;
+                const float2 xa = slab_get2<TP>(srow_a, col), xb = slab_get2<TP>(srow_b, col);
+                sc[kb][0] = xa.x; sc[kb][1] = xa.y; sc[kb][2] = xb.x; sc[kb][3] = xb.y;
                 ma = fmaxf(ma, fmaxf(xa.x, xa.y));
                 mb = fmaxf(mb, fmaxf(xb.x, xb.y));
             }
             ma = quad_max(ma);
             mb = quad_max(mb);
-            if (ma == -INFINITY) ma = 0.f;      // rows beyond L: keep everything finite (A = 0)
-            if (mb == -INFINITY) mb = 0.f;
+            if (!(ma > -INFINITY)) ma = 0.f;      // stale / fully masked rows: keep everything finite
+            if (!(mb > -INFINITY)) mb = 0.f;
             float suma = 0.f, sumb = 0.f;
+            if constexpr (F32) {
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                    sc[kb][0] = expf(sc[kb][0] - ma); sc[kb][1] = expf(sc[kb][1] - ma);
+                    sc[kb][2] = expf(sc[kb][2] - mb); sc[kb][3] = expf(sc[kb][3] - mb);
+                }
+            } else {
+                const float ka = ma * LOG2E, kbm = mb * LOG2E;
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) {
+                    sc[kb][0] = exp2f(fmaf(sc[kb][0], LOG2E, -ka));
+                    sc[kb][1] = exp2f(fmaf(sc[kb][1], LOG2E, -ka));
+                    sc[kb][2] = exp2f(fmaf(sc[kb][2], LOG2E, -kbm));
+                    sc[kb][3] = exp2f(fmaf(sc[kb][3], LOG2E, -kbm));
+                }
+            }
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
-                if constexpr (F32) {
-                    s[kb][0] = expf(s[kb][0] - ma); s[kb][1] = expf(s[kb][1] - ma);
-                    s[kb][2] = expf(s[kb][2] - mb); s[kb][3] = expf(s[kb][3] - mb);
-                } else {
-                    s[kb][0] = __expf(s[kb][0] - ma); s[kb][1] = __expf(s[kb][1] - ma);
-                    s[kb][2] = __expf(s[kb][2] - mb); s[kb][3] = __expf(s[kb][3] - mb);
-                }
-                suma += s[kb][0] + s[kb][1];
-                sumb += s[kb][2] + s[kb][3];
+                suma += sc[kb][0] + sc[kb][1];
+                sumb += sc[kb][2] + sc[kb][3];
             }
             suma = quad_sum(suma);
             sumb = quad_sum(sumb);
-            const float inva = suma > 0.f ? 1.f / suma : 0.f, invb = sumb > 0.f ? 1.f / sumb : 0.f;
+            // rows beyond L (stale slab rows) get A = 0
+            const float inva = (va_ok && suma > 0.f) ? 1.f / suma : 0.f;
+            const float invb = (vb_ok && sumb > 0.f) ? 1.f / sumb : 0.f;
 
             // ---- delta = dO . O per row; dO fragments
-            float dela = 0.f, delb = 0.f;
-            uint32_t ga0 = 0u, ga1 = 0u;          // bf16 A-operand fragments of dO rows ra / rbb
-            float gfa[HD], gfb[HD];               // f32 path
+            float dela, delb;
+            uint32_t ga0 = 0u, ga1 = 0u;
+            float gfa[HD], gfb[HD];
             if constexpr (!F32) {
                 const uint32_t* dO32 = reinterpret_cast<const uint32_t*>(dOs);
-                ga0 = dO32[ra * 4 + q4];
-                ga1 = dO32[rbb * 4 + q4];
-                if (va_ok) {
-                    const float2 x = unpack_bf16(ga0);
-                    const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(og + (size_t)ra * p.lddo + 2 * q4));
-                    dela = x.x * y.x + x.y * y.y;
-                }
-                if (vb_ok) {
-                    const float2 x = unpack_bf16(ga1);
-                    const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(og + (size_t)rbb * p.lddo + 2 * q4));
-                    delb = x.x * y.x + x.y * y.y;
-                }
+                const uint32_t* O32 = reinterpret_cast<const uint32_t*>(Os);
+                ga0 = dO32[la * 4 + q4];
+                ga1 = dO32[lb * 4 + q4];
+                const float2 x = unpack_bf16(ga0), y = unpack_bf16(O32[la * 4 + q4]);
+                const float2 x2 = unpack_bf16(ga1), y2 = unpack_bf16(O32[lb * 4 + q4]);
+                dela = x.x * y.x + x.y * y.y;
+                delb = x2.x * y2.x + x2.y * y2.y;
             } else {
+                const float* dOf = reinterpret_cast<const float*>(dOs);
+                const float* Of = reinterpret_cast<const float*>(Os);
 #pragma unroll
-                for (int d = 0; d < HD; ++d) { gfa[d] = dOs[ra * HD + d]; gfb[d] = dOs[rbb * HD + d]; }
-                if (va_ok) {
-                    dela = gfa[2 * q4] * og[(size_t)ra * p.lddo + 2 * q4] + gfa[2 * q4 + 1] * og[(size_t)ra * p.lddo + 2 * q4 + 1];
-                }
-                if (vb_ok) {
-                    delb = gfb[2 * q4] * og[(size_t)rbb * p.lddo + 2 * q4] + gfb[2 * q4 + 1] * og[(size_t)rbb * p.lddo + 2 * q4 + 1];
-                }
+                for (int d = 0; d < HD; ++d) { gfa[d] = dOf[la * HD + d]; gfb[d] = dOf[lb * HD + d]; }
+                dela = dOf[la * HD + 2 * q4] * Of[la * HD + 2 * q4] + dOf[la * HD + 2 * q4 + 1] * Of[la * HD + 2 * q4 + 1];
+                delb = dOf[lb * HD + 2 * q4] * Of[lb * HD + 2 * q4] + dOf[lb * HD + 2 * q4 + 1] * Of[lb * HD + 2 * q4 + 1];
             }
             dela = quad_sum(dela);
             delb = quad_sum(delb);
 
-            // ---- per key block: dA' = dO V^T, A', dS; dS kept in s[][] for dQ
+            // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
+            const uint32_t rkey = rng_stream_key(p.seed, (uint32_t)tile);
             const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
@@ -549,8 +600,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                     k2 = rng_keep(bb, 0, p.thresh16) ? p.keep_scale : 0.f;
                     k3 = rng_keep(bb, 1, p.thresh16) ? p.keep_scale : 0.f;
                 }
-                const float A0 = s[kb][0] * inva, A1 = s[kb][1] * inva, A2 = s[kb][2] * invb, A3 = s[kb][3] * invb;
-                // A' (dropped probabilities) for dV
+                const float A0 = sc[kb][0] * inva, A1 = sc[kb][1] * inva, A2 = sc[kb][2] * invb, A3 = sc[kb][3] * invb;
                 if constexpr (F32) {
                     *reinterpret_cast<float2*>(ap_a + col) = make_float2(A0 * k0, A1 * k1);
                     *reinterpret_cast<float2*>(ap_b + col) = make_float2(A2 * k2, A3 * k3);
@@ -558,49 +608,50 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                     *reinterpret_cast<uint32_t*>(ap_a + col) = pack_bf16(A0 * k0, A1 * k1);
                     *reinterpret_cast<uint32_t*>(ap_b + col) = pack_bf16(A2 * k2, A3 * k3);
                 }
-                // dS = A o (dA - delta) + dP'
                 float2 ua = make_float2(0.f, 0.f), ub = make_float2(0.f, 0.f);
-                if (dpo) { ua = slab_get2<TG>(grow_a, col); ub = slab_get2<TG>(grow_b, col); }
-                float d0 = A0 * (da[0] * k0 - dela) + ua.x;
-                float d1 = A1 * (da[1] * k1 - dela) + ua.y;
-                float d2 = A2 * (da[2] * k2 - delb) + ub.x;
-                float d3 = A3 * (da[3] * k3 - delb) + ub.y;
-                // masked (S = -inf), padded columns and padded rows carry no gradient
-                const float2 xa = slab_get2<TP>(srow_a, col), xb = slab_get2<TP>(srow_b, col);
-                if (col >= L || !va_ok || xa.x == -INFINITY) d0 = 0.f;
-                if (col + 1 >= L || !va_ok || xa.y == -INFINITY) d1 = 0.f;
-                if (col >= L || !vb_ok || xb.x == -INFINITY) d2 = 0.f;
-                if (col + 1 >= L || !vb_ok || xb.y == -INFINITY) d3 = 0.f;
+                if (has_dpo) {
+                    ua = slab_get2<TG>(grow_a, col);
+                    ub = slab_get2<TG>(grow_b, col);
+                }
+                float d0 = fmaf(A0, fmaf(da[0], k0, -dela), ua.x);
+                float d1 = fmaf(A1, fmaf(da[1], k1, -dela), ua.y);
+                float d2 = fmaf(A2, fmaf(da[2], k2, -delb), ub.x);
+                float d3 = fmaf(A3, fmaf(da[3], k3, -delb), ub.y);
+                if (!va_ok) { d0 = 0.f; d1 = 0.f; }      // rows beyond L: stale slab rows
+                if (!vb_ok) { d2 = 0.f; d3 = 0.f; }
                 // stored (rounded) values are what the previous layer sees; use them for dQ/dK too
                 const float2 sa = slab_put2<TG>(grow_a, col, d0, d1);
                 const float2 sb = slab_put2<TG>(grow_b, col, d2, d3);
-                s[kb][0] = sa.x; s[kb][1] = sa.y; s[kb][2] = sb.x; s[kb][3] = sb.y;
-                if constexpr (F32) {
-                    *reinterpret_cast<float2*>(ds_a + col) = sa;
-                    *reinterpret_cast<float2*>(ds_b + col) = sb;
-                } else {
+                sc[kb][0] = sa.x; sc[kb][1] = sa.y; sc[kb][2] = sb.x; sc[kb][3] = sb.y;
+                if constexpr (!ALIAS_DS) {
                     *reinterpret_cast<uint32_t*>(ds_a + col) = pack_bf16(sa.x, sa.y);
                     *reinterpret_cast<uint32_t*>(ds_b + col) = pack_bf16(sb.x, sb.y);
                 }
             }
 
             // ---- dQ = scale * dS K
+            T* dqg = static_cast<T*>(p.dq) + (size_t)b * L * p.lddqkv + h * HD;
             if constexpr (!F32) {
                 float o[4] = {0.f, 0.f, 0.f, 0.f};
-                const uint32_t* Kt32 = reinterpret_cast<const uint32_t*>(Kx);
 #pragma unroll
-                for (int j = 0; j < G::NKB16; ++j) {
-                    const int kb0 = 2 * j, kb1 = 2 * j + 1;
-                    const uint32_t a0 = pack_bf16(s[kb0][0], s[kb0][1]);
-                    const uint32_t a1 = pack_bf16(s[kb0][2], s[kb0][3]);
-                    uint32_t a2 = 0u, a3 = 0u, b1 = 0u;
-                    const uint32_t b0 = Kt32[(g * G::STRIDE + kb0 * 8 + 2 * q4) >> 1];
-                    if (kb1 < NKB) {
-                        a2 = pack_bf16(s[kb1][0], s[kb1][1]);
-                        a3 = pack_bf16(s[kb1][2], s[kb1][3]);
-                        b1 = Kt32[(g * G::STRIDE + kb1 * 8 + 2 * q4) >> 1];
+                for (int j = 0; j < G::NKB16; j += 2) {
+                    uint32_t b0, b1, b2 = 0u, b3 = 0u;
+                    if (j + 1 < G::NKB16) ldmatrix_x4_trans(b0, b1, b2, b3, Ks + (j * 16 + lane) * HD);
+                    else ldmatrix_x2_trans(b0, b1, Ks + (j * 16 + (lane & 15)) * HD);
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        if (j + jj < G::NKB16) {
+                            const int kb0 = 2 * (j + jj), kb1 = kb0 + 1;
+                            const uint32_t a0 = pack_bf16(sc[kb0][0], sc[kb0][1]);
+                            const uint32_t a1 = pack_bf16(sc[kb0][2], sc[kb0][3]);
+                            uint32_t a2 = 0u, a3 = 0u;
+                            if (kb1 < NKB) {
+                                a2 = pack_bf16(sc[kb1][0], sc[kb1][1]);
+                                a3 = pack_bf16(sc[kb1][2], sc[kb1][3]);
+                            }
+                            mma_bf16_16816(o, a0, a1, a2, a3, jj ? b2 : b0, jj ? b3 : b1);
+                        }
                     }
-                    mma_bf16_16816(o, a0, a1, a2, a3, b0, b1);
                 }
                 if (va_ok)
                     *reinterpret_cast<uint32_t*>(dqg + (size_t)ra * p.lddqkv + 2 * q4) = pack_bf16(o[0] * p.scale, o[1] * p.scale);
@@ -614,11 +665,11 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float* kr = reinterpret_cast<const float*>(Kx) + (kb * 8 + 2 * q4 + e) * HD;
+                        const float* kr = reinterpret_cast<const float*>(Ks) + (kb * 8 + 2 * q4 + e) * HD;
 #pragma unroll
                         for (int d = 0; d < HD; ++d) {
-                            oa[d] = fmaf(s[kb][e], kr[d], oa[d]);
-                            ob[d] = fmaf(s[kb][2 + e], kr[d], ob[d]);
+                            oa[d] = fmaf(sc[kb][e], kr[d], oa[d]);
+                            ob[d] = fmaf(sc[kb][2 + e], kr[d], ob[d]);
                         }
                     }
                 }
@@ -641,26 +692,29 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 }
             }
         }
+        fence_proxy_async();
         __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(static_cast<TG*>(p.dpin) + tile * tile_elems + (size_t)row0 * G::STRIDE, st[s].sG,
+                     (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TG)));
+            bulk_commit();
+        }
 
         // ================= phase 2: dK += dS^T Q, dV += A'^T dO over this chunk's rows
-        slab_store<TG, G::STRIDE>(dpi + (size_t)row0 * L, sG, nrows, L, tid, nthr);
         if constexpr (!F32) {
 #pragma unroll
             for (int i = 0; i < MAXKB16; ++i) {
                 const int kblk = warp + i * nwarps;
-                if (kblk < nrb && kblk * 16 < G::KP) {
+                if (kblk < nkb16) {
                     const int key0 = kblk * 16;
-                    // the second 8-key half lies beyond the padded key range when NKB is odd
-                    const bool hi_ok = key0 + 8 < G::KP;
-                    // ldmatrix.x4.trans: lane -> row address of matrix m = lane/8
-                    //   m0: rows +0..7, keys key0..+7      m1: rows +0..7,  keys key0+8..
-                    //   m2: rows +8..15, keys key0..+7     m3: rows +8..15, keys key0+8..
+                    const bool hi_ok = key0 + 8 < G::KP;     // the second 8-key half may lie beyond the row stride
+                    // ldmatrix.x4.trans, matrix m = lane/8:  m0 rows +0..7 keys key0..+7 | m1 rows +0..7 keys +8..
+                    //                                        m2 rows +8..15 keys key0..  | m3 rows +8..15 keys +8..
                     const int m = lane >> 3, rr = lane & 7;
                     const int soff = (rr + ((m & 2) ? 8 : 0)) * G::STRIDE + key0 + (((m & 1) && hi_ok) ? 8 : 0);
                     for (int r = 0; r < nrb_chunk; ++r) {
-                        const int lr0 = r * 16;                 // local row of the chunk
-                        const int brow = row0 + lr0 + (lane & 15);   // Q / dO row for ldmatrix.x2
+                        const int lr0 = r * 16;
+                        const int brow = lr0 + (lane & 15);
                         uint32_t a0, a1, a2, a3, b0, b1;
                         ldmatrix_x4_trans(a0, a1, a2, a3, dSt + lr0 * G::STRIDE + soff);
                         if (!hi_ok) { a1 = 0u; a3 = 0u; }
@@ -678,43 +732,48 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 const int key = idx >> 3, d = idx & 7;
                 float xk = 0.f, xv = 0.f;
                 for (int r = 0; r < nrows; ++r) {
-                    xk = fmaf(reinterpret_cast<const float*>(dSt)[r * G::STRIDE + key], reinterpret_cast<const float*>(Qs)[(row0 + r) * HD + d], xk);
-                    xv = fmaf(reinterpret_cast<const float*>(Apt)[r * G::STRIDE + key], reinterpret_cast<const float*>(dOs)[(row0 + r) * HD + d], xv);
+                    xk = fmaf(reinterpret_cast<const float*>(dSt)[r * G::STRIDE + key], reinterpret_cast<const float*>(Qs)[r * HD + d], xk);
+                    xv = fmaf(reinterpret_cast<const float*>(Apt)[r * G::STRIDE + key], reinterpret_cast<const float*>(dOs)[r * HD + d], xv);
                 }
                 dKacc[idx] += xk;
                 dVacc[idx] += xv;
             }
         }
-    }
 
-    // ---- write dK, dV
-    if constexpr (!F32) {
+        // ---- last chunk of the tile: write dK, dV
+        if (chunk == p.nchunks - 1) {
+            T* dkg = static_cast<T*>(p.dk) + (size_t)b * L * p.lddqkv + h * HD;
+            T* dvg = static_cast<T*>(p.dv) + (size_t)b * L * p.lddqkv + h * HD;
+            if constexpr (!F32) {
 #pragma unroll
-        for (int i = 0; i < MAXKB16; ++i) {
-            const int kblk = warp + i * nwarps;
-            if (kblk < nrb && kblk * 16 < G::KP) {
-                const int ka = kblk * 16 + g, kb_ = ka + 8;
-                if (ka < L) {
-                    *reinterpret_cast<uint32_t*>(dkg + (size_t)ka * p.lddqkv + 2 * q4) = pack_bf16(dk_acc[i][0] * p.scale, dk_acc[i][1] * p.scale);
-                    *reinterpret_cast<uint32_t*>(dvg + (size_t)ka * p.lddqkv + 2 * q4) = pack_bf16(dv_acc[i][0], dv_acc[i][1]);
+                for (int i = 0; i < MAXKB16; ++i) {
+                    const int kblk = warp + i * nwarps;
+                    if (kblk < nkb16) {
+                        const int ka = kblk * 16 + g, kb_ = ka + 8;
+                        if (ka < L) {
+                            *reinterpret_cast<uint32_t*>(dkg + (size_t)ka * p.lddqkv + 2 * q4) = pack_bf16(dk_acc[i][0] * p.scale, dk_acc[i][1] * p.scale);
+                            *reinterpret_cast<uint32_t*>(dvg + (size_t)ka * p.lddqkv + 2 * q4) = pack_bf16(dv_acc[i][0], dv_acc[i][1]);
+                        }
+                        if (kb_ < L) {
+                            *reinterpret_cast<uint32_t*>(dkg + (size_t)kb_ * p.lddqkv + 2 * q4) = pack_bf16(dk_acc[i][2] * p.scale, dk_acc[i][3] * p.scale);
+                            *reinterpret_cast<uint32_t*>(dvg + (size_t)kb_ * p.lddqkv + 2 * q4) = pack_bf16(dv_acc[i][2], dv_acc[i][3]);
+                        }
+                    }
                 }
-                if (kb_ < L) {
-                    *reinterpret_cast<uint32_t*>(dkg + (size_t)kb_ * p.lddqkv + 2 * q4) = pack_bf16(dk_acc[i][2] * p.scale, dk_acc[i][3] * p.scale);
-                    *reinterpret_cast<uint32_t*>(dvg + (size_t)kb_ * p.lddqkv + 2 * q4) = pack_bf16(dv_acc[i][2], dv_acc[i][3]);
+            } else {
+                // each (key,d) accumulator is owned by one thread: no sync needed
+                for (int idx = tid; idx < L * HD; idx += nthr) {
+                    const int key = idx >> 3, d = idx & 7;
+                    dkg[(size_t)key * p.lddqkv + d] = dKacc[idx] * p.scale;
+                    dvg[(size_t)key * p.lddqkv + d] = dVacc[idx];
                 }
             }
         }
-    } else {
-        __syncthreads();
-        for (int idx = tid; idx < L * HD; idx += nthr) {
-            const int key = idx >> 3, d = idx & 7;
-            dkg[(size_t)key * p.lddqkv + d] = dKacc[idx] * p.scale;
-            dvg[(size_t)key * p.lddqkv + d] = dVacc[idx];
-        }
     }
+    if (tid == 0) bulk_wait_all<0>();
 }
 
-// ------------------------------------------------------------------ debug: keep mask
+// ------------------------------------------------------------------ debug: keep mask (dense (B,H,L,L))
 __global__ void dropout_mask_kernel(uint8_t* keep, int H, int L, uint32_t thresh16, unsigned long long seed) {
     const int bh = blockIdx.x;
     const uint32_t rkey = rng_stream_key(seed, (uint32_t)bh);
@@ -733,80 +792,116 @@ inline void drop_params(float p, uint32_t& thresh16, float& keep_scale) {
     keep_scale = (float)(65536.0 / (65536.0 - t));
 }
 
-template <typename T, int NKB> size_t fwd_smem(int crb, size_t sz_tp) {
-    using G = Geo<NKB>;
-    constexpr bool F32 = std::is_same<T, float>::value;
-    size_t kv = (size_t)G::KP * HD * sizeof(T) + (F32 ? (size_t)G::KP * HD : (size_t)HD * G::STRIDE) * sizeof(T);
-    return kv + (size_t)crb * 16 * G::STRIDE * sz_tp;
-}
-template <typename T, int NKB> size_t bwd_smem(int crb, int L, size_t sz_tp, size_t sz_tg) {
-    using G = Geo<NKB>;
-    constexpr bool F32 = std::is_same<T, float>::value;
-    const int LR = ((L + 15) / 16) * 16, NR = crb * 16;
-    size_t s = (F32 ? (size_t)G::KP * HD : (size_t)HD * G::STRIDE) * sizeof(T);
-    s += (size_t)G::KP * HD * sizeof(T) + 2 * (size_t)LR * HD * sizeof(T);
-    s += (size_t)NR * G::STRIDE * (sz_tp + sz_tg + 2 * sizeof(T));
-    if (F32) s += 2 * (size_t)G::KP * HD * sizeof(float);
-    return s;
+constexpr size_t SMEM_CAP = 220 * 1024;
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
-constexpr size_t SMEM_CAP = 200 * 1024;
-
-// warps per CTA: one per 16-row block, at most 8, balanced over the chunks
-inline int pick_warps(int nrb) {
-    const int chunks = (nrb + 7) / 8;
-    return (nrb + chunks - 1) / chunks;
+// rows per chunk: the whole tile when it has at most 8 sixteen-row blocks, else balanced chunks of <= 3 blocks
+inline void pick_chunks(int L, int& crb, int& nchunks) {
+    const int nrb = (L + 15) / 16;
+    if (nrb <= 8) { crb = nrb; nchunks = 1; return; }
+    nchunks = (nrb + 2) / 3;
+    crb = (nrb + nchunks - 1) / nchunks;
+    nchunks = (nrb + crb - 1) / crb;
 }
 
 template <typename T, typename TP, int NKB>
 int launch_fwd(FwdParams p, cudaStream_t st) {
-    const int nrb = (p.L + 15) / 16;
-    const int nw = pick_warps(nrb);
-    int crb = nw;
-    while (crb > 1 && fwd_smem<T, NKB>(crb, sizeof(TP)) > SMEM_CAP) --crb;
-    const size_t smem = fwd_smem<T, NKB>(crb, sizeof(TP));
-    MMDTI_REQUIRE(smem <= SMEM_CAP, "pair_attn_fwd: shared memory %zu exceeds cap", smem);
-    p.crb = crb;
+    pick_chunks(p.L, p.crb, p.nchunks);
+    auto smem_of = [](int crb) { return NSTAGE * ((FwdStage<T, TP, NKB>::bytes(crb * 16) + 127) & ~size_t(127)); };
+    while (p.crb > 1 && smem_of(p.crb) > SMEM_CAP) --p.crb;
+    p.nchunks = ((p.L + 15) / 16 + p.crb - 1) / p.crb;
+    const size_t smem = smem_of(p.crb);
+    MMDTI_REQUIRE(smem <= SMEM_CAP, "pair_attn_fwd: shared memory %zu exceeds cap (L=%d)", smem, p.L);
     auto kern = pair_attn_fwd_kernel<T, TP, NKB>;
-    MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<p.B * p.H, nw * 32, smem, st>>>(p);
+    static int occ = 0;
+    static size_t occ_smem = 0;
+    const int threads = p.crb * 32;
+    if (!occ || occ_smem != smem) {
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MMDTI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        if (occ < 1) occ = 1;
+        occ_smem = smem;
+    }
+    const long long ntiles = (long long)p.B * p.H;
+    const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * occ);
+    kern<<<grid, threads, smem, st>>>(p);
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }
+
 template <typename T, typename TP, typename TG, int NKB>
 int launch_bwd(BwdParams p, cudaStream_t st) {
-    const int nrb = (p.L + 15) / 16;
-    const int nw = pick_warps(nrb);      // ceil(nrb/nw) <= 3 since nw >= nrb/ceil(nrb/8) and nrb <= 17
-    MMDTI_REQUIRE((nrb + nw - 1) / nw <= 3, "pair_attn_bwd: L=%d too large", p.L);
-    int crb = nw;
-    while (crb > 1 && bwd_smem<T, NKB>(crb, p.L, sizeof(TP), sizeof(TG)) > SMEM_CAP) --crb;
-    const size_t smem = bwd_smem<T, NKB>(crb, p.L, sizeof(TP), sizeof(TG));
-    MMDTI_REQUIRE(smem <= 227 * 1024, "pair_attn_bwd: shared memory %zu exceeds 227 KB (L=%d)", smem, p.L);
-    p.crb = crb;
+    using G = Geo<NKB>;
+    pick_chunks(p.L, p.crb, p.nchunks);
+    constexpr bool F32 = std::is_same<T, float>::value;
+    constexpr bool ALIAS_DS = std::is_same<T, TG>::value;
+    auto smem_of = [](int crb) {
+        const int NR = crb * 16;
+        size_t s = NSTAGE * ((BwdStage<T, TP, TG, NKB>::bytes(NR) + 127) & ~size_t(127)) +
+                   (size_t)NR * G::STRIDE * sizeof(T) * (ALIAS_DS ? 1 : 2);
+        if (F32) s += 2 * (size_t)G::KP * HD * sizeof(float);
+        return s;
+    };
+    while (p.crb > 1 && smem_of(p.crb) > SMEM_CAP) --p.crb;
+    const int nkb16 = (p.L + 15) / 16;
+    p.nchunks = (nkb16 + p.crb - 1) / p.crb;
+    // phase 1 uses one warp per 16-row block of the chunk; phase 2 spreads the 16-key blocks over all warps
+    const int nwarps = std::max(p.crb, (nkb16 + G::MAXKB16 - 1) / G::MAXKB16);
+    MMDTI_REQUIRE(nwarps <= 8, "pair_attn_bwd: unsupported L=%d", p.L);
+    const size_t smem = smem_of(p.crb);
+    MMDTI_REQUIRE(smem <= SMEM_CAP, "pair_attn_bwd: shared memory %zu exceeds cap (L=%d)", smem, p.L);
     auto kern = pair_attn_bwd_kernel<T, TP, TG, NKB>;
-    MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<p.B * p.H, nw * 32, smem, st>>>(p);
+    static int occ = 0;
+    static size_t occ_smem = 0;
+    const int threads = nwarps * 32;
+    if (!occ || occ_smem != smem) {
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MMDTI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        if (occ < 1) occ = 1;
+        occ_smem = smem;
+    }
+    const long long ntiles = (long long)p.B * p.H;
+    const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * occ);
+    kern<<<grid, threads, smem, st>>>(p);
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }
 
 template <typename T, typename TP>
 int dispatch_fwd_nkb(const FwdParams& p, cudaStream_t st) {
-    const int nkb = (p.L + 7) / 8;
-    if (nkb <= 4) return launch_fwd<T, TP, 4>(p, st);
-    if (nkb <= 9) return launch_fwd<T, TP, 9>(p, st);
-    if (nkb <= 17) return launch_fwd<T, TP, 17>(p, st);
-    if (nkb <= 33) return launch_fwd<T, TP, 33>(p, st);
+    switch (mmdti_pair_nkb(p.L)) {
+        case 3: return launch_fwd<T, TP, 3>(p, st);
+        case 5: return launch_fwd<T, TP, 5>(p, st);
+        case 9: return launch_fwd<T, TP, 9>(p, st);
+        case 13: return launch_fwd<T, TP, 13>(p, st);
+        case 17: return launch_fwd<T, TP, 17>(p, st);
+        case 25: return launch_fwd<T, TP, 25>(p, st);
+        case 33: return launch_fwd<T, TP, 33>(p, st);
+    }
     mmdti_set_error("pair_attn_fwd: L=%d exceeds the supported maximum 264", p.L);
     return MMDTI_ERR_ARG;
 }
 template <typename T, typename TP, typename TG>
 int dispatch_bwd_nkb(const BwdParams& p, cudaStream_t st) {
-    const int nkb = (p.L + 7) / 8;
-    if (nkb <= 4) return launch_bwd<T, TP, TG, 4>(p, st);
-    if (nkb <= 9) return launch_bwd<T, TP, TG, 9>(p, st);
-    if (nkb <= 17) return launch_bwd<T, TP, TG, 17>(p, st);
-    if (nkb <= 33) return launch_bwd<T, TP, TG, 33>(p, st);
+    switch (mmdti_pair_nkb(p.L)) {
+        case 3: return launch_bwd<T, TP, TG, 3>(p, st);
+        case 5: return launch_bwd<T, TP, TG, 5>(p, st);
+        case 9: return launch_bwd<T, TP, TG, 9>(p, st);
+        case 13: return launch_bwd<T, TP, TG, 13>(p, st);
+        case 17: return launch_bwd<T, TP, TG, 17>(p, st);
+        case 25: return launch_bwd<T, TP, TG, 25>(p, st);
+        case 33: return launch_bwd<T, TP, TG, 33>(p, st);
+    }
     mmdti_set_error("pair_attn_bwd: L=%d exceeds the supported maximum 264", p.L);
     return MMDTI_ERR_ARG;
 }
@@ -814,13 +909,19 @@ int dispatch_bwd_nkb(const BwdParams& p, cudaStream_t st) {
 int check_common(const void* q, const void* k, const void* v, long long ld, int B, int H, int L, int act_dtype) {
     MMDTI_REQUIRE(B > 0 && H > 0 && L > 0, "pair_attn: empty problem B=%d H=%d L=%d", B, H, L);
     MMDTI_REQUIRE(act_dtype == MMDTI_F32 || act_dtype == MMDTI_BF16, "pair_attn: act_dtype must be f32 or bf16");
+    MMDTI_REQUIRE(mmdti_pair_nkb(L) > 0, "pair_attn: L=%d exceeds the supported maximum 264", L);
     const size_t esz = act_dtype == MMDTI_F32 ? 4 : 2;
-    MMDTI_REQUIRE(mmdti_aligned(q, 16) && mmdti_aligned(k, 16) && mmdti_aligned(v, 16) && (ld * esz) % 16 == 0,
+    MMDTI_REQUIRE(q && k && v && mmdti_aligned(q, 16) && mmdti_aligned(k, 16) && mmdti_aligned(v, 16) && (ld * esz) % 16 == 0,
                   "pair_attn: q/k/v must be 16-byte aligned with a 16-byte-multiple row stride");
     return MMDTI_OK;
 }
 
 }  // namespace
+
+extern "C" int mmdti_pair_ld(int L) {
+    const int nkb = mmdti_pair_nkb(L);
+    return nkb > 0 ? nkb * 8 : -1;
+}
 
 extern "C" int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, int64_t ldqkv, const void* pair_in,
                                    void* pair_out, void* o, int64_t ldo, int B, int H, int L, float scale,
@@ -834,6 +935,7 @@ extern "C" int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, 
     FwdParams p;
     p.q = q; p.k = k; p.v = v; p.o = o; p.pin = pair_in; p.pout = pair_out;
     p.ldqkv = ldqkv; p.ldo = ldo; p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed;
+    p.crb = 0; p.nchunks = 0;
     drop_params(dropout_p, p.thresh16, p.keep_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == MMDTI_F32) {
@@ -850,8 +952,8 @@ extern "C" int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, 
 }
 
 extern "C" int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, int64_t ldqkv, const void* s,
-                                   const void* o, const void* d_o, int64_t lddo, const void* d_pair_out, void* d_pair_in, void* dq,
-                                   void* dk, void* dv, int64_t lddqkv, int B, int H, int L, float scale,
+                                   const void* o, const void* d_o, int64_t lddo, const void* d_pair_out, void* d_pair_in,
+                                   void* dq, void* dk, void* dv, int64_t lddqkv, int B, int H, int L, float scale,
                                    float dropout_p, uint64_t seed, int act_dtype, int pair_dtype, int gpair_dtype,
                                    void* stream) {
     if (int rc = check_common(q, k, v, ldqkv, B, H, L, act_dtype)) return rc;
@@ -866,6 +968,7 @@ extern "C" int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, 
     p.q = q; p.k = k; p.v = v; p.s = s; p.o = o; p.d_o = d_o; p.dpout = d_pair_out; p.dpin = d_pair_in;
     p.dq = dq; p.dk = dk; p.dv = dv; p.ldqkv = ldqkv; p.lddo = lddo; p.lddqkv = lddqkv;
     p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed;
+    p.crb = 0; p.nchunks = 0;
     drop_params(dropout_p, p.thresh16, p.keep_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (act_dtype == MMDTI_F32) {

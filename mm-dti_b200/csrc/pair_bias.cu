@@ -27,7 +27,7 @@ struct BiasParams {
     const float *means, *stds, *mul, *bias, *w1, *b1, *w2, *b2;
     const unsigned char* key_pad;
     void* out;
-    int B, L, E;
+    int B, L, Lp, E;       // Lp = row stride of the padded (B,H,L,Lp) output
     long long npairs;     // B*L*L
 };
 
@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
     float* cof = isg + KB;                                           // [128] 1/(a sigma)
     float* muls = cof + KB;                                          // [E]
     float* biass = muls + p.E;                                       // [E]
-    TP* Ot = reinterpret_cast<TP*>(biass + p.E);                     // [64][OT_STRIDE]
-    unsigned char* negf = reinterpret_cast<unsigned char*>(Ot + NH * OT_STRIDE);   // [TM]
+    int* s_mol = reinterpret_cast<int*>(biass + p.E);                // [TM] molecule index (-1: no pair)
+    int* s_off = s_mol + TM;                                         // [TM] irow*Lp + j inside the (b,h) tile
+    TP* Ot = reinterpret_cast<TP*>(s_off + TM);                      // [64][OT_STRIDE]
+    unsigned char* negf = reinterpret_cast<unsigned char*>(Ot + NH * OT_STRIDE);   // [TM] bit0: -inf key, bit1: row end
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
 
@@ -70,20 +72,28 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
         const long long P0 = tile * TM;
         // ---- u of this warp's 16 pairs (lanes 0..15), broadcast by shuffle
         float u = 0.f;
+        __syncthreads();       // previous tile's readers are done with Ot / s_mol / s_off / negf
         if (lane < 16) {
             const long long P = P0 + warp * 16 + lane;
+            int mol = -1, off = 0;
+            unsigned char fl = 0;
             if (P < p.npairs) {
                 long long e = p.et[P];
                 if (e < 0) e = 0;
                 if (e >= p.E) e = p.E - 1;
                 u = fmaf(muls[e], p.dist[P], biass[e]);
-                if (p.key_pad) {
-                    const long long bidx = P / LL;
-                    const int j = (int)((P - bidx * LL) % p.L);
-                    negf[warp * 16 + lane] = p.key_pad[bidx * p.L + j];
-                }
+                const long long bidx = P / LL;
+                const int pp = (int)(P - bidx * LL), irow = pp / p.L, j = pp - irow * p.L;
+                mol = (int)bidx;
+                off = irow * p.Lp + j;
+                if (p.key_pad && p.key_pad[bidx * p.L + j]) fl |= 1;
+                if (j == p.L - 1) fl |= 2;
             }
+            s_mol[warp * 16 + lane] = mol;
+            s_off[warp * 16 + lane] = off;
+            negf[warp * 16 + lane] = fl;
         }
+        __syncwarp();
         const float ua = __shfl_sync(0xffffffffu, u, g), ub = __shfl_sync(0xffffffffu, u, g + 8);
 
         // ---- GEMM1: z(16x128) = G(16x128) W1^T, basis built on the fly as A fragments
@@ -143,8 +153,7 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
             }
         }
         // ---- transpose through smem: Ot[h][pair]
-        __syncthreads();       // previous tile's readers are done with Ot
-        const bool na = p.key_pad && negf[warp * 16 + g], nbm = p.key_pad && negf[warp * 16 + g + 8];
+        const bool na = negf[warp * 16 + g] & 1, nbm = negf[warp * 16 + g + 8] & 1;
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
             const int h0 = nb * 8 + 2 * q4;
@@ -157,12 +166,17 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
         }
         __syncthreads();
         TP* out = static_cast<TP*>(p.out);
+        const long long tile_elems = (long long)p.L * p.Lp;
+        const TP ninf = from_f<TP>(-INFINITY);
         for (int idx = tid; idx < NH * TM; idx += blockDim.x) {
             const int h = idx >> 6, i = idx & (TM - 1);
-            const long long P = P0 + i;
-            if (P < p.npairs) {
-                const long long bidx = P / LL, pp = P - bidx * LL;
-                out[(bidx * NH + h) * LL + pp] = Ot[h * OT_STRIDE + i];
+            const int mol = s_mol[i];
+            if (mol >= 0) {
+                TP* dst = out + ((long long)mol * NH + h) * tile_elems + s_off[i];
+                *dst = Ot[h * OT_STRIDE + i];
+                if (negf[i] & 2) {                       // last key of its row: write the -inf padding columns
+                    for (int c = 1; c <= p.Lp - p.L; ++c) dst[c] = ninf;
+                }
             }
         }
     }
@@ -196,13 +210,18 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_f32_kernel(const BiasParams
             for (int k = 0; k < KB; ++k) acc = fmaf(gk[k], W1s[n * KB + k], acc);
             hk[n] = gelu_erf(acc + p.b1[n]);
         }
-        const long long bidx = P / LL, pp = P - bidx * LL;
-        const bool neg = p.key_pad && p.key_pad[bidx * p.L + (int)(pp % p.L)];
+        const long long bidx = P / LL;
+        const int pp = (int)(P - bidx * LL), irow = pp / p.L, j = pp - irow * p.L;
+        const bool neg = p.key_pad && p.key_pad[bidx * p.L + j];
         TP* out = static_cast<TP*>(p.out);
+        const long long tile_elems = (long long)p.L * p.Lp;
         for (int h = 0; h < NH; ++h) {
             float acc = 0.f;
             for (int k = 0; k < KB; ++k) acc = fmaf(hk[k], W2s[h * KB + k], acc);
-            out[(bidx * NH + h) * LL + pp] = from_f<TP>(neg ? -INFINITY : acc + p.b2[h]);
+            TP* dst = out + (bidx * NH + h) * tile_elems + (long long)irow * p.Lp + j;
+            *dst = from_f<TP>(neg ? -INFINITY : acc + p.b2[h]);
+            if (j == p.L - 1)
+                for (int c = 1; c <= p.Lp - p.L; ++c) dst[c] = from_f<TP>(-INFINITY);
         }
     }
 }
@@ -232,7 +251,8 @@ __global__ void gauss_basis_kernel(const float* __restrict__ dist, const long lo
 
 // d_out (B,H,L,L) TG -> (npairs, H) TO   [transpose of the head axis]
 template <typename TG, typename TO>
-__global__ void bhll_to_pairs_kernel(const TG* __restrict__ in, TO* __restrict__ out, int B, int H, long long LL) {
+__global__ void bhll_to_pairs_kernel(const TG* __restrict__ in, TO* __restrict__ out, int B, int H, int L, int Lp) {
+    const long long LL = (long long)L * L;
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -241,7 +261,10 @@ __global__ void bhll_to_pairs_kernel(const TG* __restrict__ in, TO* __restrict__
         const long long pp = p0 + threadIdx.x;
         const int h = h0 + r;
         float v = 0.f;
-        if (pp < LL && h < H) v = to_f(in[((long long)b * H + h) * LL + pp]);
+        if (pp < LL && h < H) {
+            const int irow = (int)(pp / L), j = (int)(pp - (long long)irow * L);
+            v = to_f(in[(((long long)b * H + h) * L + irow) * Lp + j]);
+        }
         if (!(v == v) || fabsf(v) == INFINITY) v = 0.f;
         tile[r][threadIdx.x] = v;
     }
@@ -313,23 +336,49 @@ __global__ void __launch_bounds__(256) gauss_param_grad_kernel(const TI* __restr
 
 // ------------------------------------------------------------------ mask fill / pair outputs
 template <typename TP>
-__global__ void pair_mask_fill_kernel(TP* __restrict__ pair, const unsigned char* __restrict__ key_pad, int H, int L, float fill) {
-    // one CTA per (b,h,row-chunk): only masked key columns are written
+__global__ void pair_mask_fill_kernel(TP* __restrict__ pair, const unsigned char* __restrict__ key_pad, int H, int L, int ld,
+                                      float fill) {
+    // one CTA per (b,h); rows have stride ld (L for a dense tensor, Lp for the padded layout);
+    // only masked key columns are written
     extern __shared__ unsigned char smask[];
     const int bh = blockIdx.x, b = bh / H;
     for (int j = threadIdx.x; j < L; j += blockDim.x) smask[j] = key_pad[(long long)b * L + j];
     __syncthreads();
-    TP* tile = pair + (long long)bh * L * L;
+    TP* tile = pair + (long long)bh * L * ld;
     const TP v = from_f<TP>(fill);
     for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
-        const int j = e % L;
-        if (smask[j]) tile[e] = v;
+        const int i = e / L, j = e - i * L;
+        if (smask[j]) tile[i * ld + j] = v;
+    }
+}
+
+// dense (BH,L,L) TI -> padded (BH,L,Lp) TP, padding columns = -inf
+template <typename TI, typename TP>
+__global__ void pair_pad_kernel(const TI* __restrict__ in, TP* __restrict__ out, int L, int Lp) {
+    const long long bh = blockIdx.x;
+    const TI* src = in + bh * L * L;
+    TP* dst = out + bh * L * Lp;
+    for (int e = threadIdx.x; e < L * Lp; e += blockDim.x) {
+        const int i = e / Lp, j = e - i * Lp;
+        dst[e] = j < L ? from_f<TP>(to_f(src[i * L + j])) : from_f<TP>(-INFINITY);
+    }
+}
+// padded (BH,L,Lp) TG -> dense (BH,L,L) TO
+template <typename TG, typename TO>
+__global__ void pair_unpad_kernel(const TG* __restrict__ in, TO* __restrict__ out, int L, int Lp) {
+    const long long bh = blockIdx.x;
+    const TG* src = in + bh * L * Lp;
+    TO* dst = out + bh * L * L;
+    for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
+        const int i = e / L, j = e - i * L;
+        dst[e] = from_f<TO>(to_f(src[i * Lp + j]));
     }
 }
 
 template <typename TP>
 __global__ void pair_outputs_kernel(const TP* __restrict__ first, const TP* __restrict__ last, float* __restrict__ pair_out,
-                                    float* __restrict__ delta_out, int H, long long LL) {
+                                    float* __restrict__ delta_out, int H, int L, int Lp) {
+    const long long LL = (long long)L * L;
     __shared__ float ta[32][33], tb[32][33];
     const int b = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
@@ -339,7 +388,8 @@ __global__ void pair_outputs_kernel(const TP* __restrict__ first, const TP* __re
         const int h = h0 + r;
         float x = 0.f, d = 0.f;
         if (pp < LL && h < H) {
-            const long long idx = ((long long)b * H + h) * LL + pp;
+            const int irow = (int)(pp / L), j = (int)(pp - (long long)irow * L);
+            const long long idx = (((long long)b * H + h) * L + irow) * Lp + j;
             x = to_f(last[idx]);
             // attn_mask - input_attn_mask is NaN at -inf columns and then filled with 0
             // (models/transformers.py:163-164); the input already carries the -inf there.
@@ -383,7 +433,8 @@ extern "C" int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, 
     BiasParams p;
     p.dist = dist; p.et = reinterpret_cast<const long long*>(edge_type); p.means = means; p.stds = stds;
     p.mul = mul; p.bias = bias; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.key_pad = key_pad; p.out = out;
-    p.B = B; p.L = L; p.E = E; p.npairs = (long long)B * L * L;
+    p.B = B; p.L = L; p.Lp = mmdti_pair_nkb(L) * 8; p.E = E; p.npairs = (long long)B * L * L;
+    MMDTI_REQUIRE(p.Lp > 0, "pair_bias_fwd: L=%d exceeds the supported maximum 264", L);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (fp32_math) {
         const size_t smem = (size_t)(KB * KB + NH * KB) * sizeof(float);
@@ -402,7 +453,7 @@ extern "C" int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, 
     } else {
         const size_t esz = pair_dtype == MMDTI_F32 ? 4 : 2;
         const size_t smem = (size_t)(KB + NH) * WS * sizeof(bf16) + (size_t)(KB * 4 + NH + 2 * E) * sizeof(float) +
-                            (size_t)NH * OT_STRIDE * esz + TM + 16;
+                            (size_t)2 * TM * sizeof(int) + (size_t)NH * OT_STRIDE * esz + TM + 16;
         const long long ntiles = (p.npairs + TM - 1) / TM;
         const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * 3);
 #define LAUNCH_TC(TP)                                                                                              \
@@ -440,12 +491,15 @@ extern "C" int mmdti_pair_to_rows(const void* in, void* out, int B, int H, int L
     MMDTI_REQUIRE(in && out && B > 0 && H > 0 && L > 0, "pair_to_rows: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long LL = (long long)L * L;
+    const int Lp = mmdti_pair_nkb(L) * 8;
+    MMDTI_REQUIRE(Lp > 0, "pair_to_rows: L=%d exceeds the supported maximum 264", L);
     dim3 grid((unsigned)((LL + 31) / 32), (unsigned)((H + 31) / 32), (unsigned)B), block(32, 8);
-#define GO(TG, TO) bhll_to_pairs_kernel<TG, TO><<<grid, block, 0, st>>>(static_cast<const TG*>(in), static_cast<TO*>(out), B, H, LL)
+#define GO(TG, TO) bhll_to_pairs_kernel<TG, TO><<<grid, block, 0, st>>>(static_cast<const TG*>(in), static_cast<TO*>(out), B, H, L, Lp)
     if (in_dtype == MMDTI_F32 && out_dtype == MMDTI_F32) GO(float, float);
     else if (in_dtype == MMDTI_BF16 && out_dtype == MMDTI_BF16) GO(bf16, bf16);
     else if (in_dtype == MMDTI_F32 && out_dtype == MMDTI_BF16) GO(float, bf16);
     else if (in_dtype == MMDTI_BF16 && out_dtype == MMDTI_F32) GO(bf16, float);
+    else if (in_dtype == MMDTI_F16 && out_dtype == MMDTI_BF16) GO(__half, bf16);
     else { mmdti_set_error("pair_to_rows: unsupported dtype combination"); return MMDTI_ERR_ARG; }
 #undef GO
     MMDTI_LAUNCH_OK();
@@ -470,14 +524,14 @@ extern "C" int mmdti_gauss_param_grad(const void* dG, const float* dist, const i
     return MMDTI_OK;
 }
 
-extern "C" int mmdti_pair_mask_fill(void* pair, const uint8_t* key_pad, int B, int H, int L, int pair_dtype, float fill,
-                                    void* stream) {
-    MMDTI_REQUIRE(pair && key_pad && B > 0 && H > 0 && L > 0, "pair_mask_fill: bad arguments");
+extern "C" int mmdti_pair_mask_fill(void* pair, const uint8_t* key_pad, int B, int H, int L, int ld, int pair_dtype,
+                                    float fill, void* stream) {
+    MMDTI_REQUIRE(pair && key_pad && B > 0 && H > 0 && L > 0 && ld >= L, "pair_mask_fill: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = (size_t)L;
-    if (pair_dtype == MMDTI_F32) pair_mask_fill_kernel<float><<<B * H, 256, smem, st>>>(static_cast<float*>(pair), key_pad, H, L, fill);
-    else if (pair_dtype == MMDTI_BF16) pair_mask_fill_kernel<bf16><<<B * H, 256, smem, st>>>(static_cast<bf16*>(pair), key_pad, H, L, fill);
-    else if (pair_dtype == MMDTI_F16) pair_mask_fill_kernel<__half><<<B * H, 256, smem, st>>>(static_cast<__half*>(pair), key_pad, H, L, fill);
+    if (pair_dtype == MMDTI_F32) pair_mask_fill_kernel<float><<<B * H, 256, smem, st>>>(static_cast<float*>(pair), key_pad, H, L, ld, fill);
+    else if (pair_dtype == MMDTI_BF16) pair_mask_fill_kernel<bf16><<<B * H, 256, smem, st>>>(static_cast<bf16*>(pair), key_pad, H, L, ld, fill);
+    else if (pair_dtype == MMDTI_F16) pair_mask_fill_kernel<__half><<<B * H, 256, smem, st>>>(static_cast<__half*>(pair), key_pad, H, L, ld, fill);
     else { mmdti_set_error("pair_mask_fill: bad pair_dtype %d", pair_dtype); return MMDTI_ERR_ARG; }
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
@@ -488,12 +542,54 @@ extern "C" int mmdti_pair_outputs(const void* pair_first, const void* pair_last,
     MMDTI_REQUIRE(pair_first && pair_last && B > 0 && H > 0 && L > 0, "pair_outputs: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long LL = (long long)L * L;
+    const int Lp = mmdti_pair_nkb(L) * 8;
+    MMDTI_REQUIRE(Lp > 0, "pair_outputs: L=%d exceeds the supported maximum 264", L);
     dim3 grid((unsigned)((LL + 31) / 32), (unsigned)((H + 31) / 32), (unsigned)B), block(32, 8);
-#define GO(TP) pair_outputs_kernel<TP><<<grid, block, 0, st>>>(static_cast<const TP*>(pair_first), static_cast<const TP*>(pair_last), pair_out, delta_out, H, LL)
+#define GO(TP) pair_outputs_kernel<TP><<<grid, block, 0, st>>>(static_cast<const TP*>(pair_first), static_cast<const TP*>(pair_last), pair_out, delta_out, H, L, Lp)
     if (pair_dtype == MMDTI_F32) GO(float);
     else if (pair_dtype == MMDTI_BF16) GO(bf16);
     else if (pair_dtype == MMDTI_F16) GO(__half);
     else { mmdti_set_error("pair_outputs: bad pair_dtype %d", pair_dtype); return MMDTI_ERR_ARG; }
+#undef GO
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_pair_pad(const void* dense, void* padded, int BH, int L, int in_dtype, int pair_dtype, void* stream) {
+    MMDTI_REQUIRE(dense && padded && BH > 0 && L > 0, "pair_pad: bad arguments");
+    const int Lp = mmdti_pair_nkb(L) * 8;
+    MMDTI_REQUIRE(Lp > 0, "pair_pad: L=%d exceeds the supported maximum 264", L);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define GO(TI, TP) pair_pad_kernel<TI, TP><<<BH, 256, 0, st>>>(static_cast<const TI*>(dense), static_cast<TP*>(padded), L, Lp)
+    if (in_dtype == MMDTI_F32 && pair_dtype == MMDTI_F32) GO(float, float);
+    else if (in_dtype == MMDTI_F32 && pair_dtype == MMDTI_BF16) GO(float, bf16);
+    else if (in_dtype == MMDTI_F32 && pair_dtype == MMDTI_F16) GO(float, __half);
+    else if (in_dtype == MMDTI_BF16 && pair_dtype == MMDTI_BF16) GO(bf16, bf16);
+    else if (in_dtype == MMDTI_BF16 && pair_dtype == MMDTI_F32) GO(bf16, float);
+    else if (in_dtype == MMDTI_BF16 && pair_dtype == MMDTI_F16) GO(bf16, __half);
+    else if (in_dtype == MMDTI_F16 && pair_dtype == MMDTI_F16) GO(__half, __half);
+    else if (in_dtype == MMDTI_F16 && pair_dtype == MMDTI_F32) GO(__half, float);
+    else if (in_dtype == MMDTI_F16 && pair_dtype == MMDTI_BF16) GO(__half, bf16);
+    else { mmdti_set_error("pair_pad: unsupported dtype combination"); return MMDTI_ERR_ARG; }
+#undef GO
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_pair_unpad(const void* padded, void* dense, int BH, int L, int pair_dtype, int out_dtype, void* stream) {
+    MMDTI_REQUIRE(dense && padded && BH > 0 && L > 0, "pair_unpad: bad arguments");
+    const int Lp = mmdti_pair_nkb(L) * 8;
+    MMDTI_REQUIRE(Lp > 0, "pair_unpad: L=%d exceeds the supported maximum 264", L);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define GO(TG, TO) pair_unpad_kernel<TG, TO><<<BH, 256, 0, st>>>(static_cast<const TG*>(padded), static_cast<TO*>(dense), L, Lp)
+    if (pair_dtype == MMDTI_F32 && out_dtype == MMDTI_F32) GO(float, float);
+    else if (pair_dtype == MMDTI_BF16 && out_dtype == MMDTI_F32) GO(bf16, float);
+    else if (pair_dtype == MMDTI_F16 && out_dtype == MMDTI_F32) GO(__half, float);
+    else if (pair_dtype == MMDTI_BF16 && out_dtype == MMDTI_BF16) GO(bf16, bf16);
+    else if (pair_dtype == MMDTI_F16 && out_dtype == MMDTI_F16) GO(__half, __half);
+    else if (pair_dtype == MMDTI_F32 && out_dtype == MMDTI_BF16) GO(float, bf16);
+    else if (pair_dtype == MMDTI_F32 && out_dtype == MMDTI_F16) GO(float, __half);
+    else { mmdti_set_error("pair_unpad: unsupported dtype combination"); return MMDTI_ERR_ARG; }
 #undef GO
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;

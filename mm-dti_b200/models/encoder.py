@@ -83,8 +83,9 @@ class NonLinearHead(nn.Module):
                 g = x.layer
                 out = ops.pair_bias(x.x, x.edge_type, g.means.weight, g.stds.weight, g.mul.weight, g.bias.weight,
                                     self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
-                                    key_pad=key_pad)                      # (B,H,L,L)
-                return out.permute(0, 2, 3, 1)                             # (B,L,L,H) view
+                                    key_pad=key_pad)                      # padded (B,H,L,Lp)
+                L = x.x.shape[-1]
+                return out[..., :L].permute(0, 2, 3, 1)                    # (B,L,L,H) view
             x = x.materialize()
         x = self.linear1(x)
         x = self.activation_fn(x)
@@ -174,10 +175,11 @@ class UnimolEncoder(nn.Module):
         identical to the reference's padding_mask=None branch (Q15)."""
         padding_mask = src_tokens.eq(self.padding_idx)
         x = self.embed_tokens(src_tokens)
-        bias = self.gbf_proj(self.gbf(src_distance, src_edge_type), key_pad=padding_mask)
-        bias = bias.permute(0, 3, 1, 2).contiguous()
-        bias = bias.view(-1, bias.size(-2), bias.size(-1))
-        encoder_rep = self.encoder(x, padding_mask=padding_mask, attn_mask=bias, _mask_merged=True)[0]
+        g, pj = self.gbf, self.gbf_proj
+        # K1 straight into the padded (B,H,L,Lp) layout with the key-padding mask merged
+        bias = ops.pair_bias(src_distance, src_edge_type, g.means.weight, g.stds.weight, g.mul.weight, g.bias.weight,
+                             pj.linear1.weight, pj.linear1.bias, pj.linear2.weight, pj.linear2.bias, key_pad=padding_mask)
+        encoder_rep = self.encoder.forward_padded(x, bias, padding_mask)[0]
         return encoder_rep
 
     def batch_collate_fn(self, samples):

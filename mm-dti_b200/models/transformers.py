@@ -46,24 +46,29 @@ class TransformerEncoderWithPair(nn.Module):
         self.pair_outputs = True
 
     def forward(self, emb: torch.Tensor, attn_mask: Optional[torch.Tensor] = None,
-                padding_mask: Optional[torch.Tensor] = None, _mask_merged: bool = False):
+                padding_mask: Optional[torch.Tensor] = None):
         """emb (B,L,D); attn_mask (B*H,L,L) pair bias — MUTATED IN PLACE with -inf at padded key
         columns exactly like models/transformers.py:122-132; padding_mask (B,L) bool or None.
         Returns (x, pair (B,L,L,H), delta_pair (B,L,L,H), x_norm, delta_pair_norm)."""
+        bsz, seq_len = emb.size(0), emb.size(1)
+        H = self.attention_heads
+        assert attn_mask is not None
+        if padding_mask is not None:
+            if not attn_mask.is_contiguous():
+                raise ValueError("attn_mask must be contiguous (B*H, L, L)")
+            ops.pair_mask_fill_(attn_mask, padding_mask)          # the caller's tensor, in place (Q1)
+        pair = ops.PairPadFn.apply(attn_mask.reshape(bsz * H, seq_len, seq_len), bsz, H, seq_len, config.pair_dtype())
+        return self.forward_padded(emb, pair, padding_mask)
+
+    def forward_padded(self, emb, pair, padding_mask=None):
+        """Same as forward() for a pair bias that already is in the library's padded (B,H,L,Lp)
+        layout with the key-padding mask merged (-inf columns), e.g. straight from K1."""
         bsz, seq_len = emb.size(0), emb.size(1)
         H = self.attention_heads
         x = self.emb_layer_norm(emb)
         x = F.dropout(x, p=self.emb_dropout, training=self.training)
         if padding_mask is not None:
             x = x * (1 - padding_mask.unsqueeze(-1).type_as(x))
-        assert attn_mask is not None
-        if padding_mask is not None and not _mask_merged:
-            if not attn_mask.is_contiguous():
-                raise ValueError("attn_mask must be contiguous (B*H, L, L)")
-            ops.pair_mask_fill_(attn_mask, padding_mask)          # the caller's tensor, in place
-        pdt = config.pair_dtype()
-        pair = attn_mask if attn_mask.dtype == pdt else attn_mask.to(pdt)
-        pair = pair.view(bsz * H, seq_len, seq_len)
         pair_first = pair
         for layer in self.layers:
             x, pair, _ = layer(x, padding_mask=None, attn_bias=pair, return_attn=True)

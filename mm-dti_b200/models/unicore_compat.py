@@ -119,21 +119,27 @@ class SelfMultiheadAttention(nn.Module):
         pdt = config.pair_dtype()
         if attn_bias is None:
             attn_bias = torch.zeros((B * H, L, L), device=query.device, dtype=pdt)
-        if attn_bias.dtype != pdt:
-            attn_bias = attn_bias.to(pdt)
-        attn_bias = attn_bias.contiguous()
+        # internal callers hand over the padded (B,H,L,Lp) layout; the reference's dense
+        # (B*H,L,L) bias is padded here and the returned scores are un-padded again
+        padded_in = attn_bias.dim() == 4 and attn_bias.shape[-1] == ops.pair_ld(L) and attn_bias.dtype == pdt
+        if padded_in:
+            pair = attn_bias.contiguous()
+        else:
+            pair = ops.PairPadFn.apply(attn_bias.reshape(B * H, L, L), B, H, L, pdt)
         if key_padding_mask is not None:
-            attn_bias = attn_bias.clone()
-            ops.pair_mask_fill_(attn_bias, key_padding_mask)
+            pair = pair.clone()
+            ops.pair_mask_fill_(pair, key_padding_mask)
         qkv = _lin(query, self.in_proj, dt).reshape(B * L, 3 * D)
         p = self.dropout if self.training else 0.0
-        o, scores = ops.pair_attention(qkv, attn_bias, B, H, L, self.scaling, p, ops.next_seed() if p > 0 else 0,
+        o, scores = ops.pair_attention(qkv, pair, B, H, L, self.scaling, p, ops.next_seed() if p > 0 else 0,
                                        inplace_pair)
         o = _lin(o, self.out_proj, dt).view(B, L, D)
         if not return_attn:
             return o
+        if not padded_in:
+            scores = scores[..., :L].reshape(B * H, L, L)
         # Uni-Core also returns the (B*H,L,L) probabilities; they are never materialised here
-        return o, scores.view(B * H, L, L), None
+        return o, scores, None
 
 
 class TransformerEncoderLayer(nn.Module):

@@ -26,9 +26,49 @@ def reset_seed_counter():
     _seed_counter = 0
 
 
+def pair_ld(L):
+    """Row stride Lp of the padded (B,H,L,Lp) pair layout (include/mmdti_b200.h, PAIR LAYOUT)."""
+    fn = _lib.lib().mmdti_pair_ld
+    lp = fn(int(L))
+    if lp <= 0:
+        raise _lib.MMDTIError("sequence length L=%d exceeds the supported maximum 264" % L)
+    return lp
+
+
+class PairPadFn(torch.autograd.Function):
+    """dense (B*H, L, L) any float dtype -> padded (B, H, L, Lp) pair dtype (-inf padding)."""
+
+    @staticmethod
+    def forward(ctx, dense, B, H, L, out_dtype):
+        _lib.require_cuda(dense)
+        dense = dense.contiguous()
+        out = torch.empty((B, H, L, pair_ld(L)), device=dense.device, dtype=out_dtype)
+        call("mmdti_pair_pad", dense, out, i32(B * H), i32(L), i32(DTYPE_CODE[dense.dtype]), i32(DTYPE_CODE[out_dtype]),
+             stream_ptr())
+        ctx.meta = (B, H, L, dense.dtype, dense.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, L, in_dtype, shape = ctx.meta
+        g = g.contiguous()
+        out = torch.empty(shape, device=g.device, dtype=torch.float32)
+        call("mmdti_pair_unpad", g, out, i32(B * H), i32(L), i32(DTYPE_CODE[g.dtype]), i32(_lib.F32), stream_ptr())
+        return out.to(in_dtype), None, None, None, None
+
+
+def pair_unpad(padded, L, out_dtype=torch.float32):
+    """padded (B,H,L,Lp) -> dense (B*H, L, L) (no autograd; for outputs / tests)."""
+    B, H = padded.shape[0], padded.shape[1]
+    out = torch.empty((B * H, L, L), device=padded.device, dtype=out_dtype)
+    call("mmdti_pair_unpad", padded.contiguous(), out, i32(B * H), i32(L), i32(DTYPE_CODE[padded.dtype]),
+         i32(DTYPE_CODE[out_dtype]), stream_ptr())
+    return out
+
+
 # =========================================================================== K1
 class PairBiasFn(torch.autograd.Function):
-    """dist (B,L,L) f32, edge_type (B,L,L) int64 -> pair bias (B,H,L,L).
+    """dist (B,L,L) f32, edge_type (B,L,L) int64 -> pair bias in the padded (B,H,L,Lp) layout.
     Reference: models/mm_model.py:553-556 (gbf -> gbf_proj -> permute -> contiguous)."""
 
     @staticmethod
@@ -40,7 +80,7 @@ class PairBiasFn(torch.autograd.Function):
         edge_type = edge_type.contiguous().long()
         ps = [t.detach().contiguous().float() for t in (means, stds, mul, bias, w1, b1, w2, b2)]
         kp = key_pad.contiguous().to(torch.uint8) if key_pad is not None else None
-        out = torch.empty((B, H, L, L), device=dist.device, dtype=out_dtype)
+        out = torch.empty((B, H, L, pair_ld(L)), device=dist.device, dtype=out_dtype)
         call("mmdti_pair_bias_fwd", dist, edge_type, *ps, kp, out, i32(B), i32(L), i32(K), i32(H), i32(E),
              i32(DTYPE_CODE[out_dtype]), i32(1 if fp32_math else 0), stream_ptr())
         ctx.save_for_backward(dist, edge_type, *ps)
@@ -63,8 +103,6 @@ class PairBiasFn(torch.autograd.Function):
         d_w2 = torch.zeros(H, K, device=dev)
         d_b2 = torch.zeros(H, device=dev)
         d_out = d_out.contiguous()
-        if d_out.dtype not in (torch.float32, torch.bfloat16):
-            d_out = d_out.float()
         w1c, w2c, b1c = w1.to(cdt), w2.to(cdt), b1.to(cdt)
         # molecules per chunk: bound the (pairs,128) temporaries to ~256 MB
         per_mol = L * L * K * (4 if ctx.fp32_math else 2) * 6
@@ -130,20 +168,25 @@ class GaussBasisFn(torch.autograd.Function):
 
 
 def pair_mask_fill_(pair, key_pad, fill=float("-inf")):
-    """In place: pair[b,h,:,j] = fill where key_pad[b,j] (models/transformers.py:122-132)."""
+    """In place: pair[b,h,:,j] = fill where key_pad[b,j] (models/transformers.py:122-132).
+    ``pair`` is either the reference's dense (B*H,L,L) tensor or the padded (B,H,L,Lp) layout."""
     _lib.require_cuda(pair, key_pad)
     B, L = key_pad.shape
     if not pair.is_contiguous():
-        raise _lib.MMDTIError("pair_mask_fill_: the pair tensor must be contiguous (B*H,L,L)")
-    H = pair.numel() // (B * L * L)
+        raise _lib.MMDTIError("pair_mask_fill_: the pair tensor must be contiguous")
+    ld = pair.shape[-1]
+    if ld != L and ld != pair_ld(L):
+        raise _lib.MMDTIError("pair_mask_fill_: last dim %d is neither L=%d nor Lp=%d" % (ld, L, pair_ld(L)))
+    H = pair.numel() // (B * L * ld)
     kp = key_pad.contiguous().to(torch.uint8)
-    call("mmdti_pair_mask_fill", pair, kp, i32(B), i32(H), i32(L), i32(DTYPE_CODE[pair.dtype]), f32(fill), stream_ptr())
+    call("mmdti_pair_mask_fill", pair, kp, i32(B), i32(H), i32(L), i32(ld), i32(DTYPE_CODE[pair.dtype]), f32(fill),
+         stream_ptr())
     return pair
 
 
 # =========================================================================== K2
 class PairAttnFn(torch.autograd.Function):
-    """qkv (B*L, 3*H*8) [q|k|v], pair_in (B,H,L,L) -> o (B*L, H*8), pair_out (B,H,L,L).
+    """qkv (B*L, 3*H*8) [q|k|v], pair_in (B,H,L,Lp) -> o (B*L, H*8), pair_out (B,H,L,Lp).
     Reference: Uni-Core SelfMultiheadAttention(return_attn=True) core via
     models/transformers.py:136-139."""
 
@@ -153,8 +196,8 @@ class PairAttnFn(torch.autograd.Function):
         D = H * 8
         if qkv.shape != (B * L, 3 * D) or not qkv.is_contiguous():
             raise _lib.MMDTIError("pair_attn: qkv must be a contiguous (B*L, 3*H*8) tensor")
-        if pair_in.numel() != B * H * L * L or not pair_in.is_contiguous():
-            raise _lib.MMDTIError("pair_attn: pair must be a contiguous (B,H,L,L) tensor")
+        if pair_in.numel() != B * H * L * pair_ld(L) or not pair_in.is_contiguous():
+            raise _lib.MMDTIError("pair_attn: pair must be a contiguous padded (B,H,L,Lp=%d) tensor" % pair_ld(L))
         o = torch.empty((B * L, D), device=qkv.device, dtype=qkv.dtype)
         pair_out = pair_in if inplace_pair else torch.empty_like(pair_in)
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
@@ -205,7 +248,7 @@ def attn_dropout_mask(B, H, L, dropout_p, seed, device="cuda"):
 
 
 class PairOutputsFn(torch.autograd.Function):
-    """(pair_first, pair_last) (B,H,L,L) -> pair (B,L,L,H) f32, delta (B,L,L,H) f32
+    """(pair_first, pair_last) padded (B,H,L,Lp) -> pair (B,L,L,H) f32, delta (B,L,L,H) f32
     (models/transformers.py:163-172)."""
 
     @staticmethod
@@ -230,9 +273,11 @@ class PairOutputsFn(torch.autograd.Function):
             g_last = d_delta if g_last is None else g_last + d_delta
         if g_last is None:
             return None, None, None, None, None
-        valid = torch.isfinite(pair_last).view(B, H, L, L)
-        g_last = g_last.permute(0, 3, 1, 2) * valid
+        Lp = pair_last.shape[-1]
+        valid = torch.isfinite(pair_last[..., :L])
+        pad = (0, Lp - L)
+        g_last = torch.nn.functional.pad((g_last.permute(0, 3, 1, 2) * valid).to(pair_last.dtype), pad)
         g_first = None
         if d_delta is not None:
-            g_first = (-(d_delta.permute(0, 3, 1, 2) * valid)).to(first_dtype).contiguous().view(-1, L, L)
-        return g_first, g_last.to(pair_last.dtype).contiguous().view(pair_last.shape), None, None, None
+            g_first = torch.nn.functional.pad((-(d_delta.permute(0, 3, 1, 2) * valid)).to(first_dtype), pad).contiguous()
+        return g_first, g_last.contiguous(), None, None, None

@@ -55,11 +55,15 @@ def test_pair_attn_parity(act, pair, L, report):
     dev = "cuda"
     qkv_g = qkv.to(dev).requires_grad_(True)
     bias_g = bias.to(dev).requires_grad_(True)
-    o, s = ops.pair_attention(qkv_g, bias_g, B, H, L, 8 ** -0.5, 0.0, 0)
+    Lp = ops.pair_ld(L)
+    pair_t = ops.PairPadFn.apply(bias_g.view(B * H, L, L), B, H, L, bias_g.dtype)       # dense -> padded layout
+    o, s_pad = ops.pair_attention(qkv_g, pair_t, B, H, L, 8 ** -0.5, 0.0, 0)
     d_s_g = d_s.to(dev).clone()
     d_s_g.masked_fill_(pad.to(dev)[:, None, None, :], 0)
-    torch.autograd.backward([o, s], [d_o.to(dev), d_s_g])
+    torch.autograd.backward([o, s_pad], [d_o.to(dev), torch.nn.functional.pad(d_s_g, (0, Lp - L))])
     torch.cuda.synchronize()
+    assert torch.isinf(s_pad[..., L:]).all() and (s_pad[..., L:] < 0).all()           # padding columns stay -inf
+    s = s_pad[..., :L]
     ro, rs, rdqkv, rdb = _oracle(qkv.float(), bias.float(), d_o.float(), d_s.float(), B, H, L, 0.0, None)
     tol = TOL[act]
     errs = dict(o=rel_err(o.float(), ro), s=rel_err(s.float(), rs), dqkv=rel_err(qkv_g.grad.float(), rdqkv),
@@ -86,10 +90,12 @@ def test_pair_attn_dropout_replay(act, pair, report):
     dev = "cuda"
     qkv_g = qkv.to(dev).requires_grad_(True)
     bias_g = bias.to(dev).requires_grad_(True)
-    o, s = ops.pair_attention(qkv_g, bias_g, B, H, L, 8 ** -0.5, p, seed)
+    Lp = ops.pair_ld(L)
+    pair_t = ops.PairPadFn.apply(bias_g.view(B * H, L, L), B, H, L, bias_g.dtype)
+    o, s = ops.pair_attention(qkv_g, pair_t, B, H, L, 8 ** -0.5, p, seed)
     d_s_g = d_s.to(dev).clone()
     d_s_g.masked_fill_(pad.to(dev)[:, None, None, :], 0)
-    torch.autograd.backward([o, s], [d_o.to(dev), d_s_g])
+    torch.autograd.backward([o, s], [d_o.to(dev), torch.nn.functional.pad(d_s_g, (0, Lp - L))])
     keep = ops.attn_dropout_mask(B, H, L, p, seed).cpu()
     rate = keep.float().mean().item()
     thr = round(p * 65536)
@@ -101,7 +107,7 @@ def test_pair_attn_dropout_replay(act, pair, report):
     report("pair_attn_dropout", act, pair, {k: "%.2e" % v for k, v in errs.items()}, "keep_rate=%.4f" % rate)
     assert errs["o"] < tol["o"] and errs["dqkv"] < tol["g"] and errs["dbias"] < tol["g"], errs
     # determinism: same seed -> same output; different seed -> different mask
-    o2, _ = ops.pair_attention(qkv_g.detach(), bias_g.detach(), B, H, L, 8 ** -0.5, p, seed)
+    o2, _ = ops.pair_attention(qkv_g.detach(), pair_t.detach(), B, H, L, 8 ** -0.5, p, seed)
     assert torch.equal(o2, o.detach())
     keep2 = ops.attn_dropout_mask(B, H, L, p, seed + 1).cpu()
     assert (keep2 != keep).float().mean().item() > 0.05
@@ -115,13 +121,14 @@ def test_pair_attn_inplace_and_no_dpair(report):
     dev = "cuda"
     qkv_g = qkv.to(dev).requires_grad_(True)
     bias_g = bias.to(dev).requires_grad_(True)
-    o, s = ops.pair_attention(qkv_g, bias_g, B, H, L, 8 ** -0.5, 0.0, 0)
+    pair_t = ops.PairPadFn.apply(bias_g.view(B * H, L, L), B, H, L, bias_g.dtype)
+    o, s = ops.pair_attention(qkv_g, pair_t, B, H, L, 8 ** -0.5, 0.0, 0)
     o.backward(d_o.to(dev))
     g1, gb1 = qkv_g.grad.clone(), bias_g.grad.clone()
     ro, rs, rdqkv, rdb = _oracle(qkv.float(), bias.float(), d_o.float(), d_s.float() * 0, B, H, L, 0.0, None)
     assert rel_err(g1.float(), rdqkv) < 3e-2 and rel_err(gb1.float(), rdb) < 3e-2
     with torch.no_grad():
-        b2 = bias.to(dev).clone()
+        b2 = pair_t.detach().clone()
         o2, s2 = ops.pair_attention(qkv.to(dev), b2, B, H, L, 8 ** -0.5, 0.0, 0, True)
         assert s2.data_ptr() == b2.data_ptr()
         assert torch.equal(o2, o.detach()) and torch.equal(s2, s.detach())
@@ -132,8 +139,22 @@ def test_pair_attn_argument_errors():
     from mmdti_b200._lib import MMDTIError
     with pytest.raises(MMDTIError):
         ops.pair_attention(torch.zeros(10, 96), torch.zeros(1, 4, 10, 10), 1, 4, 10, 1.0)      # CPU tensors
-    with pytest.raises(MMDTIError):
-        ops.pair_attention(torch.zeros(10, 90, device="cuda"), torch.zeros(1, 4, 10, 10, device="cuda"), 1, 4, 10, 1.0)
+    with pytest.raises(MMDTIError):     # qkv of the wrong width
+        ops.pair_attention(torch.zeros(10, 90, device="cuda"), torch.zeros(1, 4, 10, 24, device="cuda"), 1, 4, 10, 1.0)
+    with pytest.raises(MMDTIError):     # dense instead of padded pair tensor
+        ops.pair_attention(torch.zeros(10, 96, device="cuda"), torch.zeros(1, 4, 10, 10, device="cuda"), 1, 4, 10, 1.0)
     with pytest.raises(MMDTIError):     # L beyond the supported maximum
-        ops.pair_attention(torch.zeros(300, 24, device="cuda", dtype=torch.bfloat16),
-                           torch.zeros(1, 1, 300, 300, device="cuda", dtype=torch.bfloat16), 1, 1, 300, 1.0)
+        ops.pair_ld(300)
+
+
+@pytest.mark.parametrize("L", [5, 66, 130])
+def test_pair_pad_unpad_roundtrip(L):
+    from mmdti_b200 import ops
+    B, H = 2, 3
+    x = torch.randn(B * H, L, L)
+    for dt in (torch.float32, torch.bfloat16, torch.float16):
+        xp = ops.PairPadFn.apply(x.cuda(), B, H, L, dt)
+        assert xp.shape == (B, H, L, ops.pair_ld(L)) and ops.pair_ld(L) % 16 == 8
+        assert torch.equal(xp[..., :L].cpu().reshape(B * H, L, L), x.to(dt))
+        assert torch.isinf(xp[..., L:]).all()
+        assert torch.equal(ops.pair_unpad(xp, L, torch.float32).cpu(), x.to(dt).float())

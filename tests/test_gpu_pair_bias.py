@@ -62,7 +62,7 @@ def test_pair_bias_keypad_fused_and_mask_fill(report):
             filled = ops.pair_mask_fill_(plain.clone().view(-1, 15, 15), pad.to(dev)).view_as(plain)
         want = pad[:, None, None, :].expand(4, 64, 15, 15)
         assert torch.equal(torch.isinf(fused.float().cpu()), want)
-        assert torch.equal(fused.cpu().view(torch.uint8 if False else fused.dtype), filled.cpu())
+        assert torch.equal(fused.cpu(), filled.cpu())
         # untouched entries are bit-identical to the unmasked tensor
         assert torch.equal(filled.cpu()[~want], plain.cpu()[~want])
     p = {k[2:]: v for k, v in g.items() if k.startswith("w.")}
@@ -79,7 +79,9 @@ def test_pair_outputs(report):
     pad[1, -3:] = True
     first.masked_fill_(pad[:, None, None, :], float("-inf"))
     last = first + torch.randn(B, H, L, L, generator=g)
-    pair, delta = ops.PairOutputsFn.apply(first.cuda(), last.cuda(), B, H, L)
+    fp = ops.PairPadFn.apply(first.cuda().view(B * H, L, L), B, H, L, torch.float32)
+    lp = ops.PairPadFn.apply(last.cuda().view(B * H, L, L), B, H, L, torch.float32)
+    pair, delta = ops.PairOutputsFn.apply(fp, lp, B, H, L)
     want_delta = (last - first).masked_fill(pad[:, None, None, :], 0).permute(0, 2, 3, 1)
     assert torch.equal(pair.cpu(), last.permute(0, 2, 3, 1))
     assert torch.equal(delta.cpu(), want_delta)
