@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the mmdti_b200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): the Uni-Mol conformer encoder alone — 15 layers, 64 heads,
+512-d, per-GPU batch 128 molecules x 64 atoms (L = 66 tokens), bf16, forward + backward of
+sum(all_repr * g) in training mode (dropout 0.1 as configured), synthetic molecules, random-init
+weights.  Metric: train molecules/s, whole job (weak scaling: 128 molecules per GPU).
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, N_ATOMS, LAYERS, HEADS, DIM = 128, 64, 15, 64, 512
+L = N_ATOMS + 2
+METRIC, UNIT = "train_molecules_per_sec", "molecules/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(seed):
+    from mmdti_b200.data import synthetic_molecules
+    tokens, dist, et, _ = synthetic_molecules(B_PER_GPU, N_ATOMS, seed=seed)
+    g = torch.randn(B_PER_GPU, L, DIM, generator=torch.Generator().manual_seed(seed + 7)) * 0.05
+    return tokens, dist, et, g
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port of the reference)
+def cpu_reference_run(steps, warmup, sample_b=32):
+    """The reference's CPU implementation of the same path (oracle/restate.py: its own
+    models/mm_model.py + models/transformers.py restated, Uni-Core layer restated), fp32, all host
+    threads, on a bounded sample of the workload: `sample_b` molecules of the 128-molecule batch
+    per step, same L / depth / width.  Returns (molecules/s, seconds per step, cores)."""
+    from oracle import restate
+    from oracle.detw import det_state_dict
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests_util import slice_shapes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5).items()}
+    tokens, dist, et, g = make_batch(1234)
+    tokens, dist, et, g = tokens[:sample_b], dist[:sample_b], et[:sample_b], g[:sample_b]
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        rep = restate.unimol_encoder(tokens, dist, et, p, heads=HEADS, n_layers=LAYERS)
+        (rep * g).sum().backward()
+        for v in p.values():
+            v.grad = None
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return sample_b / sec, sec, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    sample_b = 32
+    val, sec, cores = cpu_reference_run(steps, warm, sample_b)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms", "per_gpu_batch": B_PER_GPU,
+                   "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d of the %d molecules per step (same L=%d, 15 layers, fp32), oracle/restate.py "
+                                   "(the reference tree is not present on the GPU box)" % (sample_b, B_PER_GPU, L)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, local_rank, world):
+    import mmdti_b200
+    from mmdti_b200 import _lib, ops
+    from mmdti_b200.models.encoder import UnimolEncoder
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    mmdti_b200.set_precision(act="bf16", pair=os.environ.get("MMDTI_PAIR", "bf16"))
+    torch.manual_seed(0)
+    model = UnimolEncoder().to(dev).train()
+    step_model = model
+    if dist_on:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        step_model = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=64)
+
+    tokens, dmat, et, g = make_batch(1234 + rank)
+    pin = [t.pin_memory() for t in (tokens, dmat, et)]
+    d_tokens, d_dist, d_et, d_g = tokens.to(dev), dmat.to(dev), et.to(dev), g.to(dev)
+
+    def barrier():
+        if dist_on:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        rep = step_model(d_tokens, d_dist, d_et)
+        loss = (rep * d_g).sum()
+        loss.backward()
+        model.zero_grad(set_to_none=True)
+        return loss
+
+    def step_e2e():
+        t, d, e = (x.to(dev, non_blocking=True) for x in pin)
+        rep = step_model(t, d, e)
+        loss = (rep * d_g).sum()
+        loss.backward()
+        model.zero_grad(set_to_none=True)
+        return float(loss.item())                      # device -> host read of the step's result
+
+    def timed(fn, steps, timeline=False):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if timeline:
+            _lib.start_timeline()
+        n0 = _lib.launch_count
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        t = a.elapsed_time(b) * 1e-3
+        tl = _lib.stop_timeline() if timeline else None
+        launches = _lib.launch_count - n0
+        if dist_on:
+            tt = torch.tensor([t], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t, launches, tl
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_res, launches, tl = timed(step_resident, args.steps, timeline=True)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    t_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        mols = B_PER_GPU * world * args.steps
+        peak, peak_src = peaks()
+        # dominant kernel of ours by live CUDA-event time inside the timed region
+        esz = 2 if mmdti_b200.config.pair_dtype() != torch.float32 else 4
+        Lp = ops.pair_ld(L)
+        nel = B_PER_GPU * HEADS * L * Lp
+        qkvo = B_PER_GPU * L * DIM * 2
+        alg = {"mmdti_pair_attn_fwd": 2 * nel * esz + 4 * qkvo,            # read P, write P', q,k,v in, o out
+               "mmdti_pair_attn_bwd": 3 * nel * esz + 9 * qkvo}            # read S, dP'; write dP; q,k,v,o,dO in; dq,dk,dv out
+        breakdown = {k: {"calls_per_step": n / args.steps, "ms_per_step": 1e3 * s / args.steps} for k, (n, s) in (tl or {}).items()}
+        dom = max((k for k in breakdown if k in alg), key=lambda k: breakdown[k]["ms_per_step"], default=None)
+        roof = None
+        if dom:
+            n, s = tl[dom]
+            # the last layer's backward reads no dP' (MM-DTI discards the pair output): 1 of 15 launches
+            bytes_per_launch = alg[dom] - (nel * esz / LAYERS if dom.endswith("bwd") else 0)
+            ach = bytes_per_launch / (s / n) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "avg_launch_us": 1e6 * s / n, "share_of_step": (s / args.steps) / (t_res / args.steps)}
+        h2d = sum(t.numel() * t.element_size() for t in pin)
+        line = {
+            "metric": METRIC, "value": mols / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms", "per_gpu_batch": B_PER_GPU,
+                       "global_batch": B_PER_GPU * world, "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS,
+                       "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
+                       "parallelism": "dp%d" % world,
+                       "l2": "no flush: the per-step working set (15 x %.0f MB pair tensors + activations) exceeds the 126 MB L2"
+                             % (nel * esz / 1e6)},
+            "e2e": {"value": mols / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "kernel_breakdown": breakdown,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            val, sec, cores = cpu_reference_run(steps=3, warmup=1, sample_b=32)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "32 of the 128 molecules per step, 3 timed steps (%.1f s/step), fp32, "
+                                              "oracle/restate.py on the host cores" % sec}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # not launched under torchrun: re-exec one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,36 @@ int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, float dropo
 int mmdti_pair_outputs(const void* pair_first, const void* pair_last, float* pair_out,
                        float* delta_out, int B, int H, int L, int pair_dtype, void* stream);
 
+/* ---------------------------------------------------------------- fused elementwise around K2
+ * The non-GEMM pieces of Uni-Core's pre-LN TransformerEncoderLayer (call
+ * site models/transformers.py:82-91,136-139), one HBM pass each.  Dropout uses the same
+ * counter-based generator as K2: element i of the flat tensor is kept iff hash(seed, i) >=
+ * round(p*65536); kept values are scaled by 65536/(65536-thresh).
+ *
+ * LayerNorm (eps 1e-5): y = (x-mean)*rstd*w + b; x (rows,D) f32, y out_dtype (f32|bf16);
+ * mean/rstd (rows) f32 are saved for the backward.  D % 4 == 0, D <= 1024. */
+int mmdti_layernorm_fwd(const float* x, const float* w, const float* b, void* y, float* mean,
+                        float* rstd, int rows, int D, float eps, int out_dtype, void* stream);
+/* dx = (dx_add ? dx_add : 0) + dLN/dx (dx may alias dx_add); dw,db (D) f32 are ACCUMULATED. */
+int mmdti_layernorm_bwd(const void* dy, const float* x, const float* w, const float* mean,
+                        const float* rstd, const float* dx_add, float* dx, float* dw, float* db,
+                        int rows, int D, int dy_dtype, void* stream);
+/* out = res + dropout(a): res,out (n) f32 (may alias), a (n) a_dtype.  n % 4 == 0. */
+int mmdti_dropout_residual_fwd(const float* res, const void* a, float* out, int64_t n, float p,
+                               uint64_t seed, int a_dtype, void* stream);
+/* da = dropout'(dx) in da_dtype (rows,C); dbias (C) f32 += column sums of da (NULL to skip). */
+int mmdti_dropout_bwd(const float* dx, void* da, float* dbias, int rows, int C, float p,
+                      uint64_t seed, int da_dtype, void* stream);
+/* exact-erf GELU (unicore.utils.get_activation_fn("gelu") = F.gelu) and its backward:
+ * dz = du * gelu'(z); dbias (C) f32 += column sums of dz (NULL to skip). */
+int mmdti_gelu_fwd(const void* z, void* u, int64_t n, int dtype, void* stream);
+int mmdti_gelu_bwd(const void* du, const void* z, void* dz, float* dbias, int rows, int C, int dtype,
+                   void* stream);
+/* out (C) f32 += column sums of x (rows,C) — bias gradients. */
+int mmdti_colsum(const void* x, float* out, int rows, int C, int dtype, void* stream);
+/* Debug/test export: keep mask (uint8, n) of the flat-tensor dropout for `seed`. */
+int mmdti_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,13 +41,38 @@ def _arg(a):
     return a
 
 
+_timeline = None          # when a list: (name, start_event, end_event) per call (bench.py's live kernel timing)
+
+
+def start_timeline():
+    global _timeline
+    _timeline = []
+
+
+def stop_timeline():
+    """-> {name: (n_calls, total_seconds)}; call after torch.cuda.synchronize()."""
+    global _timeline
+    tl, _timeline = _timeline or [], None
+    out = {}
+    for name, a, b in tl:
+        n, t = out.get(name, (0, 0.0))
+        out[name] = (n + 1, t + a.elapsed_time(b) * 1e-3)
+    return out
+
+
 def call(name, *args):
     """Invoke an `int mmdti_*(...)` entry point; tensors -> device pointers; raises on error."""
     global launch_count
     fn = getattr(lib(), name)
-    rc = fn(*[_arg(a) for a in args])
+    if _timeline is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+    rc = fn(*[_arg(a_) for a_ in args])
     if rc != 0:
         raise MMDTIError("%s failed (%d): %s" % (name, rc, lib().mmdti_last_error().decode()))
+    if _timeline is not None:
+        b.record()
+        _timeline.append((name, a, b))
     launch_count += 1
 
 

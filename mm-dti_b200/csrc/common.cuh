@@ -141,7 +141,7 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t
 // ---------------------------------------------------------------- counter-based dropout RNG
 // lowbias32 avalanche hash; the keep decision of element (stream, row, col) depends only on
 // (seed, stream, row, col), so forward, backward and the debug dump agree under any tiling.
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16;
     x *= 0x7feb352dU;
     x ^= x >> 15;

@@ -1,0 +1,480 @@
+// Fused elementwise / row-reduction kernels around K2 (all HBM-bound, vectorised, one pass):
+//   LayerNorm forward (+cast) and backward (+residual-gradient add, +dw/db reduction),
+//   dropout + residual add (forward) and its backward (+bias-gradient column sums),
+//   exact-erf GELU forward / backward (+bias-gradient column sums), column sums.
+// Reference: Uni-Core TransformerEncoderLayer (pre-LN) as used by models/transformers.py:82-91,
+// 136-139: x = r + dropout(out_proj(attn(LN(x)))); x = r + dropout(fc2(gelu(fc1(LN(x))))).
+#include "common.cuh"
+
+#include <math.h>
+#include <algorithm>
+
+namespace {
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// keep decision of flat element idx (pairs of consecutive elements share one hash)
+__device__ __forceinline__ uint32_t ew_bits(uint32_t key, unsigned long long idx) {
+    const unsigned long long pr = idx >> 1;
+    return mix32(key ^ (uint32_t)pr ^ mix32((uint32_t)(pr >> 32) + 0x27d4eb2fU));
+}
+__device__ __forceinline__ bool ew_keep(uint32_t key, unsigned long long idx, uint32_t thresh16) {
+    return rng_keep(ew_bits(key, idx), (uint32_t)(idx & 1), thresh16);
+}
+
+inline void drop_params(float p, uint32_t& thresh16, float& keep_scale) {
+    double t = floor((double)p * 65536.0 + 0.5);
+    if (t < 0) t = 0;
+    if (t > 65535) t = 65535;
+    thresh16 = (uint32_t)t;
+    keep_scale = (float)(65536.0 / (65536.0 - t));
+}
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(p);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        uint2 u;
+        u.x = pack_bf16(v[0], v[1]);
+        u.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = u;
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm forward
+// one warp per row; NV float4 per lane (D <= 128*NV); x f32 -> y TO; mean/rstd saved
+template <typename TO, int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, TO* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                                            int D, float eps) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+        const float* xr = x + row * D;
+        float v[NV][4];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) load4(xr + c, v[i]);
+            else v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+            s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+        }
+        const float mu = warp_sum(s) / D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mu; q += d * d; }
+            }
+        }
+        const float rs = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float wv[4], bv[4], o[4];
+                load4(w + c, wv);
+                load4(b + c, bv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = (v[i][e] - mu) * rs * wv[e] + bv[e];
+                store4(y + row * D + c, o);
+            }
+        }
+        if (lane == 0) {
+            if (mean) mean[row] = mu;
+            if (rstd) rstd[row] = rs;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dx_out = (add ? dx_add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*w
+// dw += sum_rows dy*xhat, db += sum_rows dy   (warp partials -> smem -> atomics)
+template <typename TI, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ dx_add,
+                                                            float* __restrict__ dx, float* __restrict__ dw,
+                                                            float* __restrict__ db, int rows, int D) {
+    extern __shared__ float red[];       // [wpb][2][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float aw[NV][4], ab[NV][4], wv[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) aw[i][e] = ab[i][e] = wv[i][e] = 0.f;
+        if (c < D) load4(w + c, wv[i]);
+    }
+    for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+        const float mu = mean[row], rs = rstd[row];
+        float g[NV][4], xh[NV][4];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float dyv[4], xv[4];
+                load4(dy + row * D + c, dyv);
+                load4(x + row * D + c, xv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    xh[i][e] = (xv[e] - mu) * rs;
+                    g[i][e] = dyv[e] * wv[i][e];
+                    c1 += g[i][e];
+                    c2 += g[i][e] * xh[i][e];
+                    aw[i][e] += dyv[e] * xh[i][e];
+                    ab[i][e] += dyv[e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) g[i][e] = xh[i][e] = 0.f;
+            }
+        }
+        c1 = warp_sum(c1) / D;
+        c2 = warp_sum(c2) / D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float o[4];
+                if (dx_add) load4(dx_add + row * D + c, o);
+                else o[0] = o[1] = o[2] = o[3] = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] += rs * (g[i][e] - c1 - xh[i][e] * c2);
+                store4(dx + row * D + c, o);
+            }
+        }
+    }
+    float* rw = red + (size_t)warp * 2 * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < D) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { rw[c + e] = aw[i][e]; rw[D + c + e] = ab[i][e]; }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < wpb; ++k) s += red[(size_t)k * 2 * D + c];
+        if (c < D) atomicAdd(dw + c, s);
+        else atomicAdd(db + (c - D), s);
+    }
+}
+
+// ------------------------------------------------------------------ dropout + residual
+// out(f32) = res(f32) + dropout(a)   (a: TI)
+template <typename TI>
+__global__ void __launch_bounds__(256) dropout_residual_fwd_kernel(const float* __restrict__ res, const TI* __restrict__ a,
+                                                                   float* __restrict__ out, long long n4, uint32_t key,
+                                                                   uint32_t thresh16, float keep_scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float r[4], v[4];
+        load4(res + i * 4, r);
+        load4(a + i * 4, v);
+        if (thresh16) {
+            const uint32_t b0 = ew_bits(key, (unsigned long long)i * 4), b1 = ew_bits(key, (unsigned long long)i * 4 + 2);
+            v[0] = rng_keep(b0, 0, thresh16) ? v[0] * keep_scale : 0.f;
+            v[1] = rng_keep(b0, 1, thresh16) ? v[1] * keep_scale : 0.f;
+            v[2] = rng_keep(b1, 0, thresh16) ? v[2] * keep_scale : 0.f;
+            v[3] = rng_keep(b1, 1, thresh16) ? v[3] * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[e] += v[e];
+        store4(out + i * 4, r);
+    }
+}
+
+// ------------------------------------------------------------------ GELU (exact erf)
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ u, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float v[4];
+        load4(z + i * 4, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = gelu_f(v[e]);
+        store4(u + i * 4, v);
+    }
+}
+// ------------------------------------------------------------------ row map + column sums
+// One traversal for the three "produce a (rows,C) tensor and its column sums" kernels:
+//   OP_COLSUM      : acc += in0
+//   OP_GELU_BWD    : out = in0 * gelu'(in1);           acc += out
+//   OP_DROPOUT_BWD : out = mask * keep_scale * in0;    acc += out      (in0 is f32)
+// A thread owns 8 consecutive columns (16-byte accesses for bf16), a CTA owns a contiguous
+// block of rows and keeps UNROLL row passes in flight; per-CTA partial sums leave by one
+// atomicAdd per column.
+enum { OP_COLSUM = 0, OP_GELU_BWD = 1, OP_DROPOUT_BWD = 2 };
+
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        float2 f;
+        f = unpack_bf16(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16(u.w); v[6] = f.x; v[7] = f.y;
+    }
+}
+// stores 8 values and returns them as stored (rounded to T)
+template <typename T> __device__ __forceinline__ void store8(T* p, float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+        uint4 u;
+        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]); u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+        float2 f;
+        f = unpack_bf16(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16(u.w); v[6] = f.x; v[7] = f.y;
+    }
+}
+
+template <typename TIN0, typename TIO, int OP>
+__global__ void __launch_bounds__(256) rowmap_colsum_kernel(const TIN0* __restrict__ in0, const TIO* __restrict__ in1,
+                                                            TIO* __restrict__ out, float* __restrict__ colsum, int rows, int C,
+                                                            uint32_t key, uint32_t thresh16, float keep_scale) {
+    constexpr int UNROLL = 4;
+    extern __shared__ float part[];                   // [rpp][C] when rpp > 1
+    const int tpr = C >> 3;                           // threads per row (8 columns each); host guarantees tpr <= 256
+    const int rpp = blockDim.x / tpr;                 // rows per pass
+    const int tcol = threadIdx.x % tpr, trow = threadIdx.x / tpr;
+    const bool active = trow < rpp;
+    const int rows_per_cta = (rows + gridDim.x - 1) / gridDim.x;
+    const int r_begin = blockIdx.x * rows_per_cta, r_end = min(rows, r_begin + rows_per_cta);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    if (active) {
+        for (int r0 = r_begin + trow; r0 < r_end; r0 += rpp * UNROLL) {
+            float a[UNROLL][8], b[UNROLL][8];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int r = r0 + u * rpp;
+                if (r < r_end) {
+                    const long long idx = (long long)r * C + tcol * 8;
+                    load8(in0 + idx, a[u]);
+                    if constexpr (OP == OP_GELU_BWD) load8(in1 + idx, b[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int r = r0 + u * rpp;
+                if (r < r_end) {
+                    const long long idx = (long long)r * C + tcol * 8;
+                    if constexpr (OP == OP_GELU_BWD) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) a[u][e] *= gelu_grad_f(b[u][e]);
+                        store8(out + idx, a[u]);
+                    } else if constexpr (OP == OP_DROPOUT_BWD) {
+                        if (thresh16) {
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const uint32_t bits = ew_bits(key, (unsigned long long)idx + e);
+                                a[u][e] = rng_keep(bits, 0, thresh16) ? a[u][e] * keep_scale : 0.f;
+                                a[u][e + 1] = rng_keep(bits, 1, thresh16) ? a[u][e + 1] * keep_scale : 0.f;
+                            }
+                        }
+                        store8(out + idx, a[u]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] += a[u][e];
+                }
+            }
+        }
+    }
+    if (!colsum) return;
+    if (rpp > 1) {
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part[trow * C + tcol * 8 + e] = acc[e];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int k = 0; k < rpp; ++k) s += part[k * C + c];
+            atomicAdd(colsum + c, s);
+        }
+    } else if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(colsum + tcol * 8 + e, acc[e]);
+    }
+}
+
+__global__ void ew_mask_kernel(uint8_t* keep, long long n, uint32_t key, uint32_t thresh16) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        keep[i] = ew_keep(key, (unsigned long long)i, thresh16) ? 1 : 0;
+}
+
+inline int ew_grid(long long work_items, int per_block) {
+    return (int)std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, (long long)num_sms() * 8));
+}
+
+}  // namespace
+
+#define DISPATCH_NV(D, CALL)                                                        \
+    if ((D) <= 128) { CALL(1); }                                                    \
+    else if ((D) <= 256) { CALL(2); }                                               \
+    else if ((D) <= 512) { CALL(4); }                                               \
+    else { CALL(8); }
+
+extern "C" int mmdti_layernorm_fwd(const float* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+                                   int rows, int D, float eps, int out_dtype, void* stream) {
+    MMDTI_REQUIRE(x && w && b && y && rows > 0 && D > 0 && D % 4 == 0 && D <= 1024, "layernorm_fwd: need D %% 4 == 0 and D <= 1024 (D=%d)", D);
+    MMDTI_REQUIRE(out_dtype == MMDTI_F32 || out_dtype == MMDTI_BF16, "layernorm_fwd: out_dtype must be f32 or bf16");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(rows, 8);
+#define CALL(NV)                                                                                                            \
+    if (out_dtype == MMDTI_F32) layernorm_fwd_kernel<float, NV><<<grid, 256, 0, st>>>(x, w, b, static_cast<float*>(y), mean, rstd, rows, D, eps); \
+    else layernorm_fwd_kernel<bf16, NV><<<grid, 256, 0, st>>>(x, w, b, static_cast<bf16*>(y), mean, rstd, rows, D, eps)
+    DISPATCH_NV(D, CALL)
+#undef CALL
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_layernorm_bwd(const void* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                                   const float* dx_add, float* dx, float* dw, float* db, int rows, int D, int dy_dtype,
+                                   void* stream) {
+    MMDTI_REQUIRE(dy && x && w && mean && rstd && dx && dw && db && rows > 0 && D % 4 == 0 && D <= 1024,
+                  "layernorm_bwd: bad arguments (D=%d)", D);
+    MMDTI_REQUIRE(dy_dtype == MMDTI_F32 || dy_dtype == MMDTI_BF16, "layernorm_bwd: dy_dtype must be f32 or bf16");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = std::min(ew_grid(rows, 8), num_sms() * 2);
+    const size_t smem = (size_t)8 * 2 * D * sizeof(float);
+#define CALL(NV)                                                                                                         \
+    if (dy_dtype == MMDTI_F32) {                                                                                         \
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        layernorm_bwd_kernel<float, NV><<<grid, 256, smem, st>>>(static_cast<const float*>(dy), x, w, mean, rstd, dx_add, dx, dw, db, rows, D); \
+    } else {                                                                                                             \
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        layernorm_bwd_kernel<bf16, NV><<<grid, 256, smem, st>>>(static_cast<const bf16*>(dy), x, w, mean, rstd, dx_add, dx, dw, db, rows, D); \
+    }
+    DISPATCH_NV(D, CALL)
+#undef CALL
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_dropout_residual_fwd(const float* res, const void* a, float* out, int64_t n, float p, uint64_t seed,
+                                          int a_dtype, void* stream) {
+    MMDTI_REQUIRE(res && a && out && n > 0 && n % 4 == 0, "dropout_residual_fwd: n must be a positive multiple of 4");
+    MMDTI_REQUIRE(p >= 0.f && p < 1.f, "dropout_residual_fwd: p out of range");
+    uint32_t th;
+    float ks;
+    drop_params(p, th, ks);
+    const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(n / 4, 256);
+    if (a_dtype == MMDTI_F32) dropout_residual_fwd_kernel<float><<<grid, 256, 0, st>>>(res, static_cast<const float*>(a), out, n / 4, key, th, ks);
+    else if (a_dtype == MMDTI_BF16) dropout_residual_fwd_kernel<bf16><<<grid, 256, 0, st>>>(res, static_cast<const bf16*>(a), out, n / 4, key, th, ks);
+    else { mmdti_set_error("dropout_residual_fwd: a_dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+template <typename TIN0, typename TIO, int OP>
+static int launch_rowmap(const void* in0, const void* in1, void* out, float* colsum, int rows, int C, uint32_t key, uint32_t th,
+                         float ks, cudaStream_t st) {
+    const int tpr = C / 8;
+    const int rpp = 256 / tpr;
+    const size_t smem = rpp > 1 ? (size_t)rpp * C * sizeof(float) : 0;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 4 * rpp - 1) / (4 * rpp), (long long)num_sms() * 2));
+    rowmap_colsum_kernel<TIN0, TIO, OP><<<grid, 256, smem, st>>>(static_cast<const TIN0*>(in0), static_cast<const TIO*>(in1),
+                                                                  static_cast<TIO*>(out), colsum, rows, C, key, th, ks);
+    return 0;
+}
+
+extern "C" int mmdti_dropout_bwd(const float* dx, void* da, float* dbias, int rows, int C, float p, uint64_t seed,
+                                 int da_dtype, void* stream) {
+    MMDTI_REQUIRE(dx && da && rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "dropout_bwd: need C %% 8 == 0 and C <= 2048 (C=%d)", C);
+    uint32_t th;
+    float ks;
+    drop_params(p, th, ks);
+    const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (da_dtype == MMDTI_F32) launch_rowmap<float, float, OP_DROPOUT_BWD>(dx, nullptr, da, dbias, rows, C, key, th, ks, st);
+    else if (da_dtype == MMDTI_BF16) launch_rowmap<float, bf16, OP_DROPOUT_BWD>(dx, nullptr, da, dbias, rows, C, key, th, ks, st);
+    else { mmdti_set_error("dropout_bwd: da_dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_gelu_fwd(const void* z, void* u, int64_t n, int dtype, void* stream) {
+    MMDTI_REQUIRE(z && u && n > 0 && n % 4 == 0, "gelu_fwd: n must be a positive multiple of 4");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(n / 4, 256);
+    if (dtype == MMDTI_F32) gelu_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(z), static_cast<float*>(u), n / 4);
+    else if (dtype == MMDTI_BF16) gelu_fwd_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(z), static_cast<bf16*>(u), n / 4);
+    else { mmdti_set_error("gelu_fwd: dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_gelu_bwd(const void* du, const void* z, void* dz, float* dbias, int rows, int C, int dtype,
+                              void* stream) {
+    MMDTI_REQUIRE(du && z && dz && rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "gelu_bwd: need C %% 8 == 0 and C <= 2048 (C=%d)", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == MMDTI_F32) launch_rowmap<float, float, OP_GELU_BWD>(du, z, dz, dbias, rows, C, 0, 0, 1.f, st);
+    else if (dtype == MMDTI_BF16) launch_rowmap<bf16, bf16, OP_GELU_BWD>(du, z, dz, dbias, rows, C, 0, 0, 1.f, st);
+    else { mmdti_set_error("gelu_bwd: dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_colsum(const void* x, float* out, int rows, int C, int dtype, void* stream) {
+    MMDTI_REQUIRE(x && out && rows > 0 && C > 0 && C % 8 == 0 && C <= 2048, "colsum: need C %% 8 == 0 and C <= 2048 (C=%d)", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == MMDTI_F32) launch_rowmap<float, float, OP_COLSUM>(x, nullptr, nullptr, out, rows, C, 0, 0, 1.f, st);
+    else if (dtype == MMDTI_BF16) launch_rowmap<bf16, bf16, OP_COLSUM>(x, nullptr, nullptr, out, rows, C, 0, 0, 1.f, st);
+    else { mmdti_set_error("colsum: dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, void* stream) {
+    MMDTI_REQUIRE(keep && n > 0, "dropout_mask: bad arguments");
+    uint32_t th;
+    float ks;
+    drop_params(p, th, ks);
+    const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
+    ew_mask_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keep, n, key, th);
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}

@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) st[s].carve(smem_raw + s * stage_bytes, NR);
 
-    // one-time init: zero K/V/Q (rows beyond L stay zero for ever), barriers
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) zero_fill(st[s].K, (2 * G::KROWS + NR) * HD, tid, nthr);
+    // one-time init: zero the whole ring (K/V rows beyond L stay zero for ever; slab rows the TMA never
+    // writes must hold finite bit patterns, not NaNs), barriers
+    for (size_t i = tid; i < NSTAGE * stage_bytes / 4; i += nthr) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
@@ -401,10 +401,11 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
     float* dKacc = reinterpret_cast<float*>(ALIAS_DS ? dSt_own : dSt_own + NR * G::STRIDE);   // f32 path only
     float* dVacc = dKacc + G::KP * HD;
 
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-        zero_fill(st[s].K, (2 * G::KROWS + 3 * NR) * HD, tid, nthr);
-        zero_fill(st[s].sG, NR * G::STRIDE, tid, nthr);
+    // one-time init: zero the whole ring and the A'/dS buffers: K/V rows beyond L stay zero for ever, and
+    // slab rows the TMA never writes must hold finite bit patterns (a NaN there would leak into dK/dV)
+    {
+        const size_t words = (NSTAGE * stage_bytes + (size_t)NR * G::STRIDE * sizeof(T) * (ALIAS_DS ? 1 : 2)) / 4;
+        for (size_t i = tid; i < words; i += nthr) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
     }
     if (tid == 0) {
 #pragma unroll

@@ -60,6 +60,25 @@ class TransformerEncoderWithPair(nn.Module):
         pair = ops.PairPadFn.apply(attn_mask.reshape(bsz * H, seq_len, seq_len), bsz, H, seq_len, config.pair_dtype())
         return self.forward_padded(emb, pair, padding_mask)
 
+    def _lowp_weights(self):
+        """bf16 copies of every layer's GEMM operands, refreshed with one multi-tensor copy per step."""
+        dt = config.act_dtype()
+        if dt == torch.float32:
+            return None
+        src = []
+        for layer in self.layers:
+            sa = layer.self_attn
+            src += [sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias, layer.fc1.weight,
+                    layer.fc1.bias, layer.fc2.weight, layer.fc2.bias]
+        src = [t.detach() for t in src]
+        cache = getattr(self, "_lowp_cache", None)
+        if (cache is None or len(cache) != len(src) or cache[0].dtype != dt or cache[0].device != src[0].device
+                or any(c.shape != s_.shape for c, s_ in zip(cache, src))):
+            cache = [torch.empty_like(t, dtype=dt) for t in src]
+            self._lowp_cache = cache
+        torch._foreach_copy_(cache, src)
+        return cache
+
     def forward_padded(self, emb, pair, padding_mask=None):
         """Same as forward() for a pair bias that already is in the library's padded (B,H,L,Lp)
         layout with the key-padding mask merged (-inf columns), e.g. straight from K1."""
@@ -70,8 +89,10 @@ class TransformerEncoderWithPair(nn.Module):
         if padding_mask is not None:
             x = x * (1 - padding_mask.unsqueeze(-1).type_as(x))
         pair_first = pair
-        for layer in self.layers:
-            x, pair, _ = layer(x, padding_mask=None, attn_bias=pair, return_attn=True)
+        lowp = self._lowp_weights()
+        for i, layer in enumerate(self.layers):
+            x, pair, _ = layer(x, padding_mask=None, attn_bias=pair, return_attn=True,
+                               lowp=None if lowp is None else lowp[8 * i:8 * i + 8])
 
         if not self.pair_outputs:
             if self.final_layer_norm is not None:

@@ -160,8 +160,38 @@ class TransformerEncoderLayer(nn.Module):
         self.final_layer_norm = LayerNorm(embed_dim)
         self.post_ln = post_ln
 
-    def forward(self, x, attn_bias=None, padding_mask=None, return_attn=False, inplace_pair=False):
+    def _fusable(self, x, attn_bias, padding_mask, return_attn):
+        return (return_attn and not self.post_ln and self.activation_fn is F.gelu and padding_mask is None
+                and (self.activation_dropout == 0.0 or not self.training) and self.self_attn.head_dim == 8
+                and attn_bias is not None and attn_bias.dim() == 4 and x.is_cuda
+                and attn_bias.shape[-1] == ops.pair_ld(x.shape[1]) and attn_bias.dtype == config.pair_dtype()
+                and x.shape[-1] % 4 == 0 and x.shape[-1] <= 1024)
+
+    def lowp_weights(self, dt):
+        """low-precision copies of the GEMM operands (refreshed by the owning encoder once per step)."""
+        sa = self.self_attn
+        return [t.detach().to(dt) for t in (sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias,
+                                            self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)]
+
+    def forward(self, x, attn_bias=None, padding_mask=None, return_attn=False, inplace_pair=False, lowp=None):
         dt = config.act_dtype()
+        if self._fusable(x, attn_bias, padding_mask, return_attn):
+            # single autograd node with a hand-written backward (ops.EncoderLayerFn)
+            B, L, D = x.shape
+            sa = self.self_attn
+            train = self.training
+            p_attn = self.attention_dropout if train else 0.0
+            p_drop = self.dropout if train else 0.0
+            seeds = (ops.next_seed(), ops.next_seed(), ops.next_seed()) if train else (0, 0, 0)
+            cfg = (B, self.attention_heads, L, sa.scaling, p_attn, p_drop, seeds, dt)
+            if dt == torch.float32:
+                lowp = None
+            x, scores = ops.EncoderLayerFn.apply(
+                x, attn_bias.contiguous(), self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias,
+                sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias,
+                self.final_layer_norm.weight, self.final_layer_norm.bias, self.fc1.weight, self.fc1.bias,
+                self.fc2.weight, self.fc2.bias, lowp, cfg)
+            return x, scores, None
         residual = x
         if not self.post_ln:
             x = self.self_attn_layer_norm(x)

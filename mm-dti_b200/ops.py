@@ -281,3 +281,128 @@ class PairOutputsFn(torch.autograd.Function):
         if d_delta is not None:
             g_first = torch.nn.functional.pad((-(d_delta.permute(0, 3, 1, 2) * valid)).to(first_dtype), pad).contiguous()
         return g_first, g_last.contiguous(), None, None, None
+
+
+# =========================================================================== fused encoder layer
+def _mm_f32(a, b):
+    """a @ b with an fp32 result (weight gradients keep full accumulator precision)."""
+    if a.dtype == torch.float32:
+        return torch.mm(a, b)
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a, b).float()
+
+
+def layernorm_fwd(x2d, w, b, out_dtype, eps=1e-5):
+    rows, D = x2d.shape
+    y = torch.empty((rows, D), device=x2d.device, dtype=out_dtype)
+    stats = torch.empty((2, rows), device=x2d.device, dtype=torch.float32)
+    call("mmdti_layernorm_fwd", x2d, w, b, y, stats[0], stats[1], i32(rows), i32(D), f32(eps), i32(DTYPE_CODE[out_dtype]),
+         stream_ptr())
+    return y, stats
+
+
+class EncoderLayerFn(torch.autograd.Function):
+    """One pre-LN Uni-Core TransformerEncoderLayer with return_attn=True (SURVEY.md Appendix A;
+    call site models/transformers.py:136-139) as a single autograd node with a hand-written
+    backward: LayerNorm / dropout+residual / GELU / bias-gradient reductions are mmdti kernels,
+    the four dense projections are library GEMMs (cuBLASLt), K2 is the pair-biased attention.
+    x (B,L,D) f32 residual stream; pair_in padded (B,H,L,Lp)."""
+
+    @staticmethod
+    def forward(ctx, x, pair_in, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc1, b_fc1, w_fc2, b_fc2,
+                lowp, cfg):
+        B, H, L, scale, p_attn, p_drop, seeds, dt = cfg
+        _lib.require_cuda(x, pair_in)
+        D = x.shape[-1]
+        rows = B * L
+        code = DTYPE_CODE[dt]
+        sp = stream_ptr()
+        if lowp is None:
+            lowp = [t.detach().to(dt) for t in (w_in, b_in, w_out, b_out, w_fc1, b_fc1, w_fc2, b_fc2)]
+        w_in_l, b_in_l, w_out_l, b_out_l, w_fc1_l, b_fc1_l, w_fc2_l, b_fc2_l = lowp
+        x2d = x.detach().reshape(rows, D).contiguous().float()
+        ln1_wd, ln1_bd, ln2_wd, ln2_bd = (t.detach().float().contiguous() for t in (ln1_w, ln1_b, ln2_w, ln2_b))
+        pair_in = pair_in.detach()
+        h1, st1 = layernorm_fwd(x2d, ln1_wd, ln1_bd, dt)
+        qkv = torch.addmm(b_in_l, h1, w_in_l.t())
+        o = torch.empty((rows, D), device=x.device, dtype=dt)
+        pair_out = torch.empty_like(pair_in)
+        call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_in, pair_out, o, i64(D),
+             i32(B), i32(H), i32(L), f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_in.dtype]), sp)
+        a = torch.addmm(b_out_l, o, w_out_l.t())
+        x1 = torch.empty_like(x2d)
+        call("mmdti_dropout_residual_fwd", x2d, a, x1, i64(rows * D), f32(p_drop), u64(seeds[1]), i32(code), sp)
+        h2, st2 = layernorm_fwd(x1, ln2_wd, ln2_bd, dt)
+        z = torch.addmm(b_fc1_l, h2, w_fc1_l.t())
+        u = torch.empty_like(z)
+        call("mmdti_gelu_fwd", z, u, i64(z.numel()), i32(code), sp)
+        f = torch.addmm(b_fc2_l, u, w_fc2_l.t())
+        x2 = torch.empty_like(x2d)
+        call("mmdti_dropout_residual_fwd", x1, f, x2, i64(rows * D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+        ctx.save_for_backward(x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_wd, ln2_wd, w_in_l, w_out_l,
+                              w_fc1_l, w_fc2_l)
+        ctx.cfg = cfg
+        ctx.set_materialize_grads(False)
+        return x2.view(B, L, D), pair_out
+
+    @staticmethod
+    def backward(ctx, dx2, dpair_out):
+        (x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_w, ln2_w, w_in_l, w_out_l, w_fc1_l,
+         w_fc2_l) = ctx.saved_tensors
+        B, H, L, scale, p_attn, p_drop, seeds, dt = ctx.cfg
+        rows, D = x2d.shape
+        F_ = z.shape[1]
+        code = DTYPE_CODE[dt]
+        sp = stream_ptr()
+        dev = x2d.device
+        if dx2 is None:
+            dx2 = torch.zeros((rows, D), device=dev, dtype=torch.float32)
+        dx2 = dx2.reshape(rows, D).contiguous().float()
+        if dpair_out is not None:
+            dpair_out = dpair_out.contiguous()
+            if dpair_out.dtype != pair_out.dtype:
+                dpair_out = dpair_out.to(pair_out.dtype)
+        # one zeroed buffer for all reduced gradients of this layer
+        red = torch.zeros(4 * D + 2 * D + F_ + 3 * D, device=dev, dtype=torch.float32)
+        dw_ln1, db_ln1, dw_ln2, db_ln2 = red[0:D], red[D:2 * D], red[2 * D:3 * D], red[3 * D:4 * D]
+        db_out, db_fc2 = red[4 * D:5 * D], red[5 * D:6 * D]
+        db_fc1 = red[6 * D:6 * D + F_]
+        db_in = red[6 * D + F_:]
+        # ---- feed-forward block
+        df = torch.empty((rows, D), device=dev, dtype=dt)
+        call("mmdti_dropout_bwd", dx2, df, db_fc2, i32(rows), i32(D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+        du = torch.mm(df, w_fc2_l)
+        dW_fc2 = _mm_f32(df.t(), u)
+        dz = torch.empty_like(z)
+        call("mmdti_gelu_bwd", du, z, dz, db_fc1, i32(rows), i32(F_), i32(code), sp)
+        dh2 = torch.mm(dz, w_fc1_l)
+        dW_fc1 = _mm_f32(dz.t(), h2)
+        dx1 = torch.empty_like(x2d)
+        call("mmdti_layernorm_bwd", dh2, x1, ln2_w, st2[0], st2[1], dx2, dx1, dw_ln2, db_ln2, i32(rows), i32(D), i32(code), sp)
+        # ---- attention block
+        da = torch.empty((rows, D), device=dev, dtype=dt)
+        call("mmdti_dropout_bwd", dx1, da, db_out, i32(rows), i32(D), f32(p_drop), u64(seeds[1]), i32(code), sp)
+        d_o = torch.mm(da, w_out_l)
+        dW_out = _mm_f32(da.t(), o)
+        dqkv = torch.empty_like(qkv)
+        dpair_in = torch.empty_like(pair_out)
+        call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_out, o, d_o, i64(D),
+             dpair_out, dpair_in, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L),
+             f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_out.dtype]),
+             i32(DTYPE_CODE[pair_out.dtype]), sp)
+        call("mmdti_colsum", dqkv, db_in, i32(rows), i32(3 * D), i32(code), sp)
+        dh1 = torch.mm(dqkv, w_in_l)
+        dW_in = _mm_f32(dqkv.t(), h1)
+        dx = dx1          # in place: dx = dx1 + dLN1
+        call("mmdti_layernorm_bwd", dh1, x2d, ln1_w, st1[0], st1[1], dx1, dx, dw_ln1, db_ln1, i32(rows), i32(D), i32(code), sp)
+        return (dx.view(B, L, D), dpair_in, dw_ln1, db_ln1, dW_in, db_in, dW_out, db_out, dw_ln2, db_ln2, dW_fc1, db_fc1,
+                dW_fc2, db_fc2, None, None)
+
+
+def dropout_mask(n, p, seed, device="cuda"):
+    """Debug/test export of the flat-tensor dropout keep mask for `seed`."""
+    keep = torch.empty(n, device=device, dtype=torch.uint8)
+    call("mmdti_dropout_mask", keep, i64(n), f32(p), u64(seed), stream_ptr())
+    return keep.bool()
