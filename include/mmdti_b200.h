@@ -163,6 +163,116 @@ int mmdti_colsum(const void* x, float* out, int rows, int C, int dtype, void* st
 /* Debug/test export: keep mask (uint8, n) of the flat-tensor dropout for `seed`. */
 int mmdti_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, void* stream);
 
+/* ---------------------------------------------------------------- K3 / K4: contrastive similarity
+ * One two-phase engine serves InfoNCE (models/infonce.py:70-98), ConR = CT_Regress
+ * (models/contrastive.py:3-59), SupCon-style CT_Single (:62-112) and CT_Multi (:114-169).  The
+ * N x N similarity matrix is never written:
+ *   phase 1 (sim_stats): s_ij = <a_i, b_j> / t for the M local anchor rows against all N keys
+ *                        -> per-row statistics (M, 8) f32
+ *   finalize:            statistics -> loss contribution and the per-row coefficients of phase 2
+ *   phase 2 (sim_grad):  recompute s_ij, form the gradient coefficient H_ij,
+ *                        dA_i = sum_j H_ij b_j   (M, D) f32
+ * mode: MMDTI_SIM_INFONCE | _REGRESS | _SINGLE | _MULTI.  Anchor row r is GLOBAL sample
+ * row_offset + r (data parallel: a rank owns rows [row_offset, row_offset+M) of the all-gathered
+ * batch); label arrays are indexed by global sample.
+ *   y, yhat   (N) f32: mean(depth,1), mean(output,1)      [REGRESS]   w_thr = w, e_push = e
+ *   key       (N, C) int64 labels                           [SINGLE: C = 1; MULTI: C classes, coef]
+ *   wrow/wcol (N) f32 or NULL: pushing weight w_ij = wrow[i] * wcol[j] (REGRESS: * |y_i-y_j| * e)
+ * Masks are evaluated exactly as the reference does (fp32 subtract/abs/compare, integer equality):
+ * bit-exact; mmdti_ct_masks exports them for the tests.
+ * Statistics layout (row stride 8): InfoNCE {sum_j exp(z_ij - 1/t), z_ii}; CT {sum_P e^s, sum_N w e^s,
+ * |P|, |N|, sum_P s}.
+ *
+ * *_f32: plain fp32 FMA (validation mode, 1e-5 parity), D <= 512.
+ * *_tc : bf16 operands on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
+ *        staged by TMA), fp32 statistics; A,B are the zero-padded bf16 copies written by
+ *        mmdti_rownorm_fwd with row stride Dp (a multiple of 64, <= 512). */
+#define MMDTI_SIM_INFONCE 0
+#define MMDTI_SIM_REGRESS 1
+#define MMDTI_SIM_SINGLE 2
+#define MMDTI_SIM_MULTI 3
+#define MMDTI_SIM_NSTAT 8
+
+/* F.normalize(dim=-1, eps) (models/infonce.py:104-105, models/contrastive.py:21-22): x (N, D) f32 with
+ * row stride ldx -> any of: xhat_f32 (N, D), xhat_bf16 (N, Dp) zero-padded columns [D, Dp),
+ * inv_norm (N) = 1 / max(||x||, eps). */
+int mmdti_rownorm_fwd(const float* x, int64_t ldx, float* xhat_f32, void* xhat_bf16, int Dp,
+                      float* inv_norm, int N, int D, float eps, void* stream);
+/* dx = coef * (g - xhat <xhat, g>) * inv_norm, coef = scale * (gscale ? *gscale : 1); gscale is a
+ * device scalar (the upstream loss gradient).  accumulate != 0: dx += . */
+int mmdti_rownorm_bwd(const float* g, const float* xhat, const float* inv_norm, float* dx,
+                      int64_t lddx, int N, int D, float scale, const float* gscale, float eps,
+                      int accumulate, void* stream);
+int mmdti_sim_stats_f32(const float* A, const float* B, int M, int N, int D, int row_offset, int mode,
+                        float temperature, const float* y, const float* yhat, float w_thr,
+                        float e_push, const int64_t* key, int C, float coef_multi, const float* wrow,
+                        const float* wcol, float* stats, void* stream);
+int mmdti_sim_grad_f32(const float* A, const float* B, int M, int N, int D, int row_offset, int mode,
+                       float temperature, const float* y, const float* yhat, float w_thr,
+                       float e_push, const int64_t* key, int C, float coef_multi, const float* wrow,
+                       const float* wcol, const float* rs_row, const float* rs_col, float* dA,
+                       void* stream);
+int mmdti_sim_stats_tc(const void* A, const void* B, int M, int N, int Dp, int row_offset, int mode,
+                       float temperature, const float* y, const float* yhat, float w_thr,
+                       float e_push, const int64_t* key, int C, float coef_multi, const float* wrow,
+                       const float* wcol, float* stats, void* stream);
+int mmdti_sim_grad_tc(const void* A, const void* B, int M, int N, int Dp, int row_offset, int mode,
+                      float temperature, const float* y, const float* yhat, float w_thr, float e_push,
+                      const int64_t* key, int C, float coef_multi, const float* wrow,
+                      const float* wcol, const float* rs_row, const float* rs_col, float* dA,
+                      int64_t lddA, void* stream);
+/* InfoNCE: stats (M,8) -> lse (M) = log sum_j exp(z_ij); *loss += scale * sum_i (lse_i - z_ii). */
+int mmdti_infonce_finalize(const float* stats, float* lse, float* loss, int M, float temperature,
+                           float scale, void* stream);
+/* CT: stats (M,8) -> rowstat (M,2) {c_i, alpha_i}; *loss += sum_i loss_i / N
+ * (Z_i = sum_P e^s + (N - |P|) + sum_N w e^s: the exp(0)=1 quirk of contrastive.py:53). */
+int mmdti_ct_finalize(const float* stats, float* rowstat, float* loss, int M, int N, int mode,
+                      float w_thr, void* stream);
+/* Debug/test export of the boolean masks (N,N) uint8 for mode REGRESS | SINGLE | MULTI. */
+int mmdti_ct_masks(int mode, int N, const float* y, const float* yhat, float w_thr,
+                   const int64_t* key, int C, float coef_multi, uint8_t* pos, uint8_t* neg,
+                   void* stream);
+
+/* ---------------------------------------------------------------- K5: FDS
+ * models/fds.py + utils/util.py:159-169 without leaving the device.
+ * mmdti_fds_bin: bins[i] = int((label_i - min_value) // bin_width) in fp32 exactly like
+ *   models/fds.py:125,164 (torch floor_divide); present (bucket_num - bucket_start) int32 flags the
+ *   in-range bins that occur in the batch (the reference loops over torch.unique(bins): the edge
+ *   buckets absorb the tails only when the edge bin itself occurs). labels: element i at labels[i*ld]. */
+int mmdti_fds_bin(const float* labels, int64_t ld, int N, float min_value, float bin_width,
+                  int bucket_start, int bucket_num, int32_t* bins, int32_t* present, void* stream);
+/* FDS.smooth (models/fds.py:157-190): x (N,D) f32 row stride ldx, IN PLACE:
+ * x = (x - m1[b]) * sqrt(clamp(v2[b]/v1[b], .1, 10)) + m2[b] per calibrate_mean_var's three branches.
+ * m1,v1 = running_{mean,var}_last_epoch, m2,v2 = smoothed_{mean,var}_last_epoch (nb, D). */
+int mmdti_fds_smooth_fwd(float* x, int64_t ldx, const int32_t* bins, const int32_t* present, int N,
+                         int D, int bucket_start, int bucket_num, const float* m1, const float* v1,
+                         const float* m2, const float* v2, void* stream);
+int mmdti_fds_smooth_bwd(const float* dy, float* dx, const int32_t* bins, const int32_t* present,
+                         int N, int D, int bucket_start, int bucket_num, const float* v1,
+                         const float* v2, void* stream);
+/* FDS.update_running_stats (models/fds.py:116-155) in four steps so that data-parallel ranks can
+ * all-reduce {count, sum1} and {m2} in between:
+ *   group:       rows grouped by bucket -> seg (nb+1) offsets, order (N) row indices, count (nb) f32
+ *   bucket_sums: sum1 (nb,D) = per-bucket column sums
+ *   bucket_m2:   m2 (nb,D) = per-bucket sum of (x - sum1/count)^2   (count = global count)
+ *   ema:         mean = sum1/count, var = m2/(count-1) (count==1: m2/1); tracked += count;
+ *                running = (1-f) cur + f running, f = first_update ? 0 : (momentum >= 0 ? momentum
+ *                : 1 - count/tracked)          -- only buckets with count > 0 are touched. */
+int mmdti_fds_group(const int32_t* bins, const int32_t* present, int N, int bucket_start,
+                    int bucket_num, int32_t* seg, int32_t* order, float* count, void* stream);
+int mmdti_fds_bucket_sums(const float* x, int64_t ldx, const int32_t* seg, const int32_t* order,
+                          float* sum1, int N, int D, int nb, void* stream);
+int mmdti_fds_bucket_m2(const float* x, int64_t ldx, const int32_t* seg, const int32_t* order,
+                        const float* sum1, const float* count, float* m2, int N, int D, int nb,
+                        void* stream);
+int mmdti_fds_ema(const float* count, const float* sum1, const float* m2, float* running_mean,
+                  float* running_var, float* num_samples_tracked, int nb, int D, float momentum,
+                  int first_update, void* stream);
+/* FDS._update_last_epoch_stats (models/fds.py:86-99): out[b] = sum_k window[k] in[reflect(b+k-half)]
+ * along the bucket axis (F.pad reflect + conv1d); in/out (nb, D) f32, in != out. */
+int mmdti_fds_window(const float* in, const float* window, float* out, int nb, int D, int ks,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,448 @@
+// K3 / K4 on the 5th-generation tensor cores: the two-phase contrastive-similarity engine with
+// tcgen05.mma (bf16 operands, fp32 accumulators in TMEM), operands staged by TMA (128B swizzle) and
+// a warp-specialised mbarrier pipeline.  One CTA owns a stripe of BM = 128 anchor rows (resident in
+// shared memory for the whole kernel) and walks key tiles of BN keys.
+//
+//   warp 0      TMA producer: A stripe once, then one B tile (BN keys x Dp, as Dp/64 swizzled chunks)
+//               per pipeline stage
+//   warp 1      MMA issuer (one thread):
+//                 MMA1  S[buf]  = A . B_tile^T        (K = Dp; both operands K-major)      -> s_full
+//                 MMA2  dA     += H[hb] . B_tile      (K = BN; H K-major, B MN-major: the SAME
+//                                                       shared-memory tile read transposed)  phase 2 only
+//               issued software-pipelined: MMA1(t+1) goes out before MMA2(t), so the tensor pipe
+//               computes the next similarity tile while the epilogue warps turn tile t into H
+//   warps 2..5  epilogue: thread r owns anchor row r (TMEM lane r): tcgen05.ld the S row, apply the
+//               per-pair functor of sim_common.cuh (masks / exp / weights),
+//                 phase 1: accumulate the row statistics in registers
+//                 phase 2: write H (bf16, swizzled K-major) to shared memory for MMA2
+//
+// TMEM: S double-buffered (2 x BN columns) + dA (<= 256 columns).  Output dims beyond 256 are covered
+// by blockIdx.z halves (S is recomputed per half).  The N x N matrix never leaves the SM.
+//
+// Reference math: models/infonce.py:70-98, models/contrastive.py:3-169 via sim_common.cuh.
+#define SIM_EXP(x) __expf(x)
+#include "sim_common.cuh"
+
+#include <cuda.h>
+#include <algorithm>
+
+int sim_check_aux(const SimAux& a, int phase);
+SimAux sim_make_aux(int mode, int N, int row_offset, float temperature, const float* y, const float* yhat, float w_thr,
+                    float e_push, const int64_t* key, int C, float coef_multi, const float* wrow, const float* wcol,
+                    const float* rs_row, const float* rs_col);
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int CHUNK_K = 64;                 // bf16 elements per 128-byte swizzled row
+constexpr int A_CHUNK_BYTES = BM * 128;     // one K-chunk of the A stripe
+constexpr int H_ATOM_BYTES = BM * 128;      // one [128][64] bf16 swizzle atom of H
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_DA_COL = 256;
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
+    // bounded wait: a pipeline bug traps instead of hanging the GPU
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+        "[%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout; version 1)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor: bf16 x bf16 -> f32, M = 128, N = n; b_mn = 1: B operand is MN-major
+__host__ __device__ constexpr uint32_t instr_desc(int n, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcParams {
+    SimAux aux;
+    float* out;          // phase 1: stats (M, 8); phase 2: dA (M, ldout)
+    long long ldout;
+    int M, D, nkc, nstage, tiles_per_split, use_atomics;
+};
+
+struct SmemLayout {
+    uint32_t a_off, b_off, h_off, bar_off, total;
+    uint32_t b_stage_bytes;
+};
+__host__ __device__ inline SmemLayout smem_layout(int nkc, int bn, int nstage, int phase) {
+    SmemLayout s;
+    s.a_off = 0;
+    s.b_off = nkc * A_CHUNK_BYTES;
+    s.b_stage_bytes = nkc * bn * 128;
+    s.h_off = s.b_off + nstage * s.b_stage_bytes;
+    const uint32_t h_bytes = phase == 2 ? 2u * ((bn + 63) / 64) * H_ATOM_BYTES : 0u;
+    s.bar_off = s.h_off + h_bytes;
+    s.total = s.bar_off + 256;
+    return s;
+}
+
+template <int PHASE, int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 128-byte swizzle atoms need 1024-byte aligned tiles: align by hand (the launch adds 1 KB of slack)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const SimAux& aux = p.aux;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkc = p.nkc, nstage = p.nstage;
+    const SmemLayout lay = smem_layout(nkc, BN, nstage, PHASE);
+    unsigned char* sA = smem + lay.a_off;
+    unsigned char* sB = smem + lay.b_off;
+    unsigned char* sH = smem + lay.h_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+    uint64_t* a_full = bars + 0;
+    uint64_t* d_full = bars + 1;
+    uint64_t* s_full = bars + 2;      // [2]
+    uint64_t* s_empty = bars + 4;     // [2]
+    uint64_t* h_full = bars + 6;      // [2]
+    uint64_t* h_empty = bars + 8;     // [2]
+    uint64_t* full = bars + 10;       // [MAX_STAGES]
+    uint64_t* empty = bars + 16;      // [MAX_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+    const int i0 = blockIdx.x * BM;
+    const int ntiles_all = (aux.N + BN - 1) / BN;
+    const int t_begin = blockIdx.y * p.tiles_per_split;
+    const int T = min(ntiles_all, t_begin + p.tiles_per_split) - t_begin;      // tiles of this CTA (>= 1)
+    const int dcol0 = PHASE == 2 ? blockIdx.z * 256 : 0;
+    const int ND = PHASE == 2 ? min(nkc * CHUNK_K - dcol0, 256) : 0;          // output columns of this CTA
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(d_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 128);
+            mbar_init(&h_full[i], 128);
+            mbar_init(&h_empty[i], 1);
+        }
+        for (int i = 0; i < MAX_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================= TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(a_full, (uint32_t)(nkc * A_CHUNK_BYTES));
+            for (int kc = 0; kc < nkc; ++kc) tma_load_2d(sA + kc * A_CHUNK_BYTES, &tmA, kc * CHUNK_K, i0, a_full);
+            for (int t = 0; t < T; ++t) {
+                const int st = t % nstage, use = t / nstage;
+                if (use > 0) mbar_wait_g(&empty[st], (use - 1) & 1);
+                mbar_arrive_expect_tx(&full[st], lay.b_stage_bytes);
+                unsigned char* dst = sB + (size_t)st * lay.b_stage_bytes;
+                const int j0 = (t_begin + t) * BN;
+                for (int kc = 0; kc < nkc; ++kc) tma_load_2d(dst + kc * BN * 128, &tmB, kc * CHUNK_K, j0, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================= MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = instr_desc(BN, 0);
+            const uint32_t idesc_d = instr_desc(ND > 0 ? ND : 16, 1);
+            const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB), h_addr = smem_u32(sH);
+            auto mma2 = [&](int u) {
+                const int hb = u & 1, st = u % nstage;
+                mbar_wait_g(&h_full[hb], (u >> 1) & 1);
+                tc_fence_after();
+                const uint32_t bst = b_addr + st * lay.b_stage_bytes + (dcol0 / CHUNK_K) * BN * 128;
+                const uint32_t hst = h_addr + hb * ((BN + 63) / 64) * H_ATOM_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BN / 16; ++ks) {
+                    const uint64_t ad = smem_desc(hst + (ks >> 2) * H_ATOM_BYTES + (ks & 3) * 32, 16, 1024);
+                    const uint64_t bd = smem_desc(bst + ks * 16 * 128, BN * 128, 1024);
+                    tc_mma(tmem_base + TMEM_DA_COL, ad, bd, idesc_d, (u > 0 || ks > 0) ? 1u : 0u);
+                }
+                tc_commit(&h_empty[hb]);
+                tc_commit(&empty[st]);
+            };
+            mbar_wait_g(a_full, 0);
+            for (int t = 0; t < T; ++t) {
+                const int buf = t & 1, st = t % nstage;
+                if (t >= 2) mbar_wait_g(&s_empty[buf], ((t >> 1) - 1) & 1);
+                mbar_wait_g(&full[st], (t / nstage) & 1);
+                tc_fence_after();
+                const uint32_t bst = b_addr + st * lay.b_stage_bytes;
+                for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t ad = smem_desc(a_addr + kc * A_CHUNK_BYTES + k4 * 32, 16, 1024);
+                        const uint64_t bd = smem_desc(bst + kc * BN * 128 + k4 * 32, 16, 1024);
+                        tc_mma(tmem_base + buf * BN, ad, bd, idesc_s, (kc > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&s_full[buf]);
+                if (PHASE == 1) tc_commit(&empty[st]);
+                if (PHASE == 2 && t > 0) mma2(t - 1);
+            }
+            if (PHASE == 2) {
+                mma2(T - 1);
+                tc_commit(d_full);
+            }
+        }
+    } else {
+        // ================================================= epilogue warps (TMEM lane quadrant = warp % 4)
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                  // anchor row of this thread inside the stripe
+        const bool row_ok = (i0 + r) < p.M;
+        const int gi = aux.row_offset + i0 + r;          // global anchor index
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        RowAcc racc;
+        racc.clear();
+        float ri0 = 0.f, ri1 = 0.f;
+        if (PHASE == 2 && row_ok) {
+            if (aux.mode == SIM_INFONCE) ri0 = aux.rs_row[i0 + r];
+            else { ri0 = aux.rs_row[2 * (i0 + r)]; ri1 = aux.rs_row[2 * (i0 + r) + 1]; }
+        }
+        for (int t = 0; t < T; ++t) {
+            const int buf = t & 1;
+            const int j0 = (t_begin + t) * BN;
+            mbar_wait_g(&s_full[buf], (t >> 1) & 1);
+            tc_fence_after();
+            if (PHASE == 2 && t >= 2) mbar_wait_g(&h_empty[buf], ((t >> 1) - 1) & 1);
+            unsigned char* hrow = sH + buf * ((BN + 63) / 64) * H_ATOM_BYTES + r * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(lane_addr + buf * BN + c0, v);
+                if (PHASE == 1) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const int j = j0 + c0 + c;
+                            if (j < aux.N) sim_stats_accum(aux, racc, gi, j, __uint_as_float(v[c]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float h2[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int c = g8 * 8 + e * 2 + u;
+                                const int j = j0 + c0 + c;
+                                h2[u] = (row_ok && j < aux.N) ? sim_grad_coeff(aux, gi, j, __uint_as_float(v[c]), ri0, ri1) : 0.f;
+                            }
+                            w[e] = pack_bf16(h2[0], h2[1]);
+                        }
+                        const int col8 = (c0 >> 3) + g8;                   // 16-byte chunk index along K
+                        unsigned char* dst = hrow + (col8 >> 3) * H_ATOM_BYTES + (((col8 & 7) ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&s_empty[buf]);
+            if (PHASE == 2) {
+                fence_proxy_async();
+                mbar_arrive(&h_full[buf]);
+            }
+        }
+        if (PHASE == 1) {
+            if (row_ok) {
+                float* dst = p.out + (long long)(i0 + r) * SIM_NSTAT;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if (p.use_atomics) atomicAdd(dst + k, racc.v[k]);
+                    else dst[k] = racc.v[k];
+                }
+            }
+        } else {
+            mbar_wait_g(d_full, 0);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ND; c0 += 32) {
+                uint32_t v[32];
+                tc_ld32(lane_addr + TMEM_DA_COL + c0, v);
+                if (row_ok) {
+                    float* dst = p.out + (long long)(i0 + r) * p.ldout + dcol0 + c0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (dcol0 + c0 + c < p.D) {
+                            if (p.use_atomics) atomicAdd(dst + c, __uint_as_float(v[c]));
+                            else dst[c] = __uint_as_float(v[c]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// (rows, Dp) bf16 row-major -> 2-D map with a (64 x box_rows) box, 128-byte swizzle, zero OOB fill
+int make_map(CUtensorMap* map, const void* base, int rows, int Dp, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { mmdti_set_error("cuTensorMapEncodeTiled is not available from the driver"); return MMDTI_ERR_CUDA; }
+    const cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)Dp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)CHUNK_K, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { mmdti_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MMDTI_ERR_CUDA; }
+    return MMDTI_OK;
+}
+
+template <int PHASE, int BN>
+int launch_bn(const void* A, const void* B, int M, int N, int Dp, int D, const SimAux& aux, float* out, long long ldout,
+              cudaStream_t st) {
+    const int nkc = Dp / CHUNK_K;
+    int nstage = MAX_STAGES;
+    SmemLayout lay = smem_layout(nkc, BN, nstage, PHASE);
+    while (nstage > 2 && lay.total + 1024 > 227 * 1024) lay = smem_layout(nkc, BN, --nstage, PHASE);
+    if (lay.total + 1024 > 227 * 1024) { mmdti_set_error("sim_tc: shared memory budget exceeded (Dp=%d BN=%d)", Dp, BN); return MMDTI_ERR_ARG; }
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, A, M, Dp, BM)) return rc;
+    if (int rc = make_map(&tmB, B, N, Dp, BN)) return rc;
+    const int stripes = (M + BM - 1) / BM;
+    const int ntiles = (N + BN - 1) / BN;
+    const int halves = PHASE == 2 ? (Dp + 255) / 256 : 1;
+    int jsplit = 1;
+    if (stripes * halves < 2 * num_sms()) jsplit = std::max(1, std::min(ntiles, (2 * num_sms()) / (stripes * halves)));
+    const int per = (ntiles + jsplit - 1) / jsplit;
+    jsplit = (ntiles + per - 1) / per;
+    TcParams p;
+    p.aux = aux; p.out = out; p.ldout = ldout; p.M = M; p.D = D; p.nkc = nkc; p.nstage = nstage;
+    p.tiles_per_split = per; p.use_atomics = jsplit > 1;
+    const size_t outbytes = PHASE == 1 ? (size_t)M * SIM_NSTAT * sizeof(float) : (size_t)M * ldout * sizeof(float);
+    if (jsplit > 1 || PHASE == 1) MMDTI_CUDA_OK(cudaMemsetAsync(out, 0, outbytes, st));
+    auto kern = sim_tc_kernel<PHASE, BN>;
+    const int smem_bytes = (int)lay.total + 1024;
+    MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    dim3 grid(stripes, jsplit, halves);
+    kern<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+template <int PHASE>
+int launch(const void* A, const void* B, int M, int N, int Dp, int D, const SimAux& aux, float* out, long long ldout, cudaStream_t st) {
+    MMDTI_REQUIRE(Dp >= 64 && Dp <= 512 && Dp % 64 == 0, "sim_tc: Dp must be a multiple of 64 in [64, 512] (got %d)", Dp);
+    MMDTI_REQUIRE(mmdti_aligned(A, 16) && mmdti_aligned(B, 16), "sim_tc: operands must be 16-byte aligned");
+    if (Dp <= 128) return launch_bn<PHASE, 128>(A, B, M, N, Dp, D, aux, out, ldout, st);
+    if (Dp <= 256) return launch_bn<PHASE, 64>(A, B, M, N, Dp, D, aux, out, ldout, st);
+    return launch_bn<PHASE, 32>(A, B, M, N, Dp, D, aux, out, ldout, st);
+}
+
+}  // namespace
+
+extern "C" int mmdti_sim_stats_tc(const void* A, const void* B, int M, int N, int Dp, int row_offset, int mode, float temperature,
+                                  const float* y, const float* yhat, float w_thr, float e_push, const int64_t* key, int C,
+                                  float coef_multi, const float* wrow, const float* wcol, float* stats, void* stream) {
+    MMDTI_REQUIRE(A && B && stats && M > 0, "sim_stats_tc: bad arguments");
+    const SimAux aux = sim_make_aux(mode, N, row_offset, temperature, y, yhat, w_thr, e_push, key, C, coef_multi, wrow, wcol, nullptr, nullptr);
+    if (int rc = sim_check_aux(aux, 1)) return rc;
+    return launch<1>(A, B, M, N, Dp, Dp, aux, stats, SIM_NSTAT, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mmdti_sim_grad_tc(const void* A, const void* B, int M, int N, int Dp, int row_offset, int mode, float temperature,
+                                 const float* y, const float* yhat, float w_thr, float e_push, const int64_t* key, int C,
+                                 float coef_multi, const float* wrow, const float* wcol, const float* rs_row, const float* rs_col,
+                                 float* dA, int64_t lddA, void* stream) {
+    MMDTI_REQUIRE(A && B && dA && M > 0 && lddA >= 1 && lddA <= Dp, "sim_grad_tc: bad arguments (need 1 <= lddA <= Dp)");
+    const SimAux aux = sim_make_aux(mode, N, row_offset, temperature, y, yhat, w_thr, e_push, key, C, coef_multi, wrow, wcol, rs_row, rs_col);
+    if (int rc = sim_check_aux(aux, 2)) return rc;
+    return launch<2>(A, B, M, N, Dp, (int)lddA, aux, dA, lddA, static_cast<cudaStream_t>(stream));
+}

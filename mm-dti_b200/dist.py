@@ -1,0 +1,101 @@
+"""Data-parallel plumbing of the hot path (one process per GPU, torch.distributed; NCCL over
+NVLink on the GPU box, gloo in the CPU tests).  The reference is single-process (SURVEY.md §2:
+"no distributed code"); this is the new work §8(e) names:
+
+  exchange 1 (forward)   all-gather of the contrastive operands (unit embeddings of both
+                         modalities, pooled features, labels / predictions / weights) so that
+                         InfoNCE / SupCon / ConR see global-batch negatives; a second, tiny
+                         all-gather of the per-row statistics before the gradient phase
+  exchange 2 (backward)  gradient all-reduce (bucketed, flat buffers)
+  FDS epoch statistics   all-reduce of per-bucket {count, sum} and {second moment}
+
+Each rank evaluates ITS anchor rows against the global keys and obtains the complete gradient
+of the global loss w.r.t. its own rows, so no reduce-scatter of key-side gradients is needed
+(ops_sim.py).  Ranks must hold equal local batch sizes."""
+import torch
+import torch.distributed as dist
+
+
+class DataParallelCtx:
+    """Handle passed as ``dp=`` to the contrastive ops / FDS.
+
+    grad_scale: factor applied to the local gradients of a GLOBAL loss.  Every rank returns the
+    same global loss and the exact d(global loss)/d(local rows); a gradient all-reduce that
+    AVERAGES over ranks (DistributedDataParallel, ``allreduce_grads(average=True)``) would divide
+    it by world, so the default grad_scale = world cancels that; use 1.0 with a summing reduce."""
+
+    def __init__(self, group=None, grad_scale=None):
+        if not dist.is_initialized():
+            raise RuntimeError("DataParallelCtx needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.grad_scale = float(self.world if grad_scale is None else grad_scale)
+
+    def all_gather_rows(self, t):
+        """(M, ...) on every rank -> (world*M, ...), rank-major."""
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    def all_reduce_sum(self, t):
+        t = t.contiguous().clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_reduce_max_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+
+def allreduce_grads(params, group=None, average=True, bucket_bytes=64 << 20):
+    """Exchange 2: all-reduce ``p.grad`` of every parameter in flat same-dtype buckets of about
+    ``bucket_bytes`` (NVSwitch: size buckets for launch latency, not link count).  Parameters whose
+    grad is None on this rank contribute zeros (every rank must issue the same collectives)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    by_dtype = {}
+    for p in params:
+        if not p.requires_grad:
+            continue
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        by_dtype.setdefault(p.grad.dtype, []).append(p.grad)
+    n_coll = 0
+    for dt, grads in by_dtype.items():
+        bucket, size = [], 0
+        buckets = []
+        for g in grads:
+            nb = g.numel() * g.element_size()
+            if bucket and size + nb > bucket_bytes:
+                buckets.append(bucket)
+                bucket, size = [], 0
+            bucket.append(g)
+            size += nb
+        if bucket:
+            buckets.append(bucket)
+        works = []
+        for b in buckets:
+            flat = torch.cat([g.reshape(-1) for g in b])
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, b))
+            n_coll += 1
+        for w, flat, b in works:
+            w.wait()
+            if average:
+                flat.div_(world)
+            off = 0
+            for g in b:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+    return n_coll
+
+
+def shard_rows(n_total, rank, world):
+    """[start, stop) of the rows a rank owns when n_total samples are split evenly."""
+    if n_total % world:
+        raise ValueError("global batch %d is not divisible by the world size %d" % (n_total, world))
+    m = n_total // world
+    return rank * m, rank * m + m
