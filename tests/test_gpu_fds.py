@@ -118,6 +118,6 @@ def test_fds_data_parallel_emulation():
         m.update_running_stats(feats[sl].cuda(), labels[sl].cuda(), 0)
         return m
 
-    for m in run_emulated(W, ranked):
+    for m in run_emulated(W, ranked, sweeps=4):      # present -> {count,sum} -> m2: three dependent exchanges
         for k in ("running_mean", "running_var", "num_samples_tracked"):
             assert rel_err(getattr(m, k), getattr(ref, k)) < 1e-5, k
