@@ -5,8 +5,8 @@
 
 Workload (BASELINE.json configs[1]): the Uni-Mol conformer encoder alone — 15 layers, 64 heads,
 512-d, per-GPU batch 128 molecules x 64 atoms (L = 66 tokens), bf16, forward + backward of
-sum(all_repr * g) in training mode (dropout 0.1 as configured), synthetic molecules, random-init
-weights.  Metric: train molecules/s, whole job (weak scaling: 128 molecules per GPU).
+sum(all_repr * g) in training mode (dropout 0.1 as configured) + Adam step, synthetic molecules,
+random-init weights.  At N = 1 the step is captured once in a CUDA graph and replayed.  Metric: train molecules/s, whole job (weak scaling: 128 molecules per GPU).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -101,13 +101,14 @@ def cpu_reference_run(steps, warmup, sample_b=32):
     p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5).items()}
     tokens, dist, et, g = make_batch(1234)
     tokens, dist, et, g = tokens[:sample_b], dist[:sample_b], et[:sample_b], g[:sample_b]
+    opt = torch.optim.Adam(list(p.values()), lr=1e-4, eps=1e-6)        # tasks/trainer.py:160
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         rep = restate.unimol_encoder(tokens, dist, et, p, heads=HEADS, n_layers=LAYERS)
         (rep * g).sum().backward()
-        for v in p.values():
-            v.grad = None
+        opt.step()
+        opt.zero_grad(set_to_none=True)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
@@ -159,26 +160,46 @@ def run_ours(args, rank, local_rank, world):
     tokens, dmat, et, g = make_batch(1234 + rank)
     pin = [t.pin_memory() for t in (tokens, dmat, et)]
     d_tokens, d_dist, d_et, d_g = tokens.to(dev), dmat.to(dev), et.to(dev), g.to(dev)
+    use_graph = (not args.no_graph) and not dist_on
+    # Adam(eps 1e-6) as in tasks/trainer.py:160; fused + capturable so that it can live inside the CUDA graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
 
     def barrier():
         if dist_on:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        rep = step_model(d_tokens, d_dist, d_et)
-        loss = (rep * d_g).sum()
-        loss.backward()
-        model.zero_grad(set_to_none=True)
-        return loss
-
-    def step_e2e():
-        t, d, e = (x.to(dev, non_blocking=True) for x in pin)
+    def full_step(t, d, e):
         rep = step_model(t, d, e)
         loss = (rep * d_g).sum()
         loss.backward()
-        model.zero_grad(set_to_none=True)
-        return float(loss.item())                      # device -> host read of the step's result
+        opt.step()
+        return loss.detach()
+
+    def step_eager():
+        loss = full_step(d_tokens, d_dist, d_et)
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    if use_graph:
+        from mmdti_b200.graph import GraphedStep
+        opt.zero_grad(set_to_none=True)
+        graphed = GraphedStep(full_step, [d_tokens, d_dist, d_et], device=dev)
+
+        def step_resident():
+            return graphed(d_tokens, d_dist, d_et)
+
+        def step_e2e():
+            # pinned host inputs -> static device buffers (H2D inside the timed path), replay, D2H read of the loss
+            return float(graphed(*pin).item())
+    else:
+        step_resident = step_eager
+
+        def step_e2e():
+            t, d, e = (x.to(dev, non_blocking=True) for x in pin)
+            loss = full_step(t, d, e)
+            opt.zero_grad(set_to_none=True)
+            return float(loss.item())                  # device -> host read of the step's result
 
     def timed(fn, steps, timeline=False):
         barrier()
@@ -205,11 +226,21 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_res, launches, tl = timed(step_resident, args.steps, timeline=True)
+    t_res, launches, tl = timed(step_resident, args.steps, timeline=not use_graph)
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
     t_e2e, _, _ = timed(step_e2e, args.steps)
+    tl_steps = args.steps
+    if use_graph:
+        # per-kernel CUDA-event times cannot be taken inside a graph replay: one extra EAGER pass of the same
+        # step (same kernels, same arguments), used only for the roofline / breakdown fields
+        graphed.close()
+        opt.zero_grad(set_to_none=True)
+        tl_steps = min(args.steps, 3)
+        for _ in range(2):
+            step_eager()
+        _, _, tl = timed(step_eager, tl_steps, timeline=True)
 
     if rank == 0:
         mols = B_PER_GPU * world * args.steps
@@ -221,7 +252,7 @@ def run_ours(args, rank, local_rank, world):
         qkvo = B_PER_GPU * L * DIM * 2
         alg = {"mmdti_pair_attn_fwd": 2 * nel * esz + 4 * qkvo,            # read P, write P', q,k,v in, o out
                "mmdti_pair_attn_bwd": 3 * nel * esz + 9 * qkvo}            # read S, dP'; write dP; q,k,v,o,dO in; dq,dk,dv out
-        breakdown = {k: {"calls_per_step": n / args.steps, "ms_per_step": 1e3 * s / args.steps} for k, (n, s) in (tl or {}).items()}
+        breakdown = {k: {"calls_per_step": n / tl_steps, "ms_per_step": 1e3 * s / tl_steps} for k, (n, s) in (tl or {}).items()}
         dom = max((k for k in breakdown if k in alg), key=lambda k: breakdown[k]["ms_per_step"], default=None)
         roof = None
         if dom:
@@ -231,7 +262,9 @@ def run_ours(args, rank, local_rank, world):
             ach = bytes_per_launch / (s / n) / 1e9
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "avg_launch_us": 1e6 * s / n, "share_of_step": (s / args.steps) / (t_res / args.steps)}
+                    "avg_launch_us": 1e6 * s / n, "share_of_step": (s / tl_steps) / (t_res / args.steps),
+                    "timing": "CUDA events around each launch on the launching stream"
+                              + (" (separate eager pass: the timed region replays a CUDA graph)" if use_graph else "")}
         h2d = sum(t.numel() * t.element_size() for t in pin)
         line = {
             "metric": METRIC, "value": mols / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -240,6 +273,7 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms", "per_gpu_batch": B_PER_GPU,
                        "global_batch": B_PER_GPU * world, "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS,
                        "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
+                       "optimizer": "Adam(eps=1e-6), torch fused", "cuda_graph": bool(use_graph),
                        "parallelism": "dp%d" % world,
                        "l2": "no flush: the per-step working set (15 x %.0f MB pair tensors + activations) exceeds the 126 MB L2"
                              % (nel * esz / 1e6)},
@@ -268,6 +302,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

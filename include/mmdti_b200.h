@@ -45,6 +45,12 @@ extern "C" {
 int mmdti_version(void);
 const char* mmdti_last_error(void);
 
+/* CUDA-graph support: register a device-resident uint64 counter (or NULL to clear).  Every dropout
+ * kernel then derives its masks from (seed, *counter), so a captured training step that increments
+ * the counter once per replay draws fresh masks each step; forward, backward and the debug mask
+ * exports of one step (same counter value) still agree. */
+int mmdti_set_seed_offset(const uint64_t* device_counter);
+
 /* row stride Lp of the padded pair layout for sequence length L (-1 if L > 264) */
 int mmdti_pair_ld(int L);
 /* dense (BH, L, L) in_dtype -> padded (BH, L, Lp) pair_dtype (padding columns = -inf), and back */

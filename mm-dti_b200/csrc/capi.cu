@@ -15,3 +15,10 @@ void mmdti_set_error(const char* fmt, ...) {
 
 extern "C" int mmdti_version(void) { return 100; }
 extern "C" const char* mmdti_last_error(void) { return g_err; }
+
+static const unsigned long long* g_seed_off = nullptr;
+const unsigned long long* mmdti_seed_offset_ptr() { return g_seed_off; }
+extern "C" int mmdti_set_seed_offset(const uint64_t* device_counter) {
+    g_seed_off = reinterpret_cast<const unsigned long long*>(device_counter);
+    return MMDTI_OK;
+}

@@ -163,6 +163,17 @@ __device__ __forceinline__ bool rng_keep(uint32_t bits, uint32_t col, uint32_t t
     return r >= thresh16;
 }
 
+// Device-resident RNG offset (CUDA-graph replays): when the host registered a device counter with
+// mmdti_set_seed_offset(), every dropout kernel adds *counter to its seed, so a captured step draws fresh
+// masks on every replay while forward / backward / debug dumps of ONE step still agree.
+const unsigned long long* mmdti_seed_offset_ptr();
+__device__ __forceinline__ unsigned long long rng_effective_seed(unsigned long long seed, const unsigned long long* off) {
+    return off ? seed + (*off) * 0x9E3779B97F4A7C15ULL : seed;
+}
+__device__ __forceinline__ uint32_t rng_effective_key(uint32_t key, const unsigned long long* off) {
+    return off ? mix32(key + (uint32_t)(*off) * 0x9E3779B1U + (uint32_t)((*off) >> 32)) : key;
+}
+
 // exact unsigned division by a small runtime constant: q = n / d for n*d < 2^32
 struct FastDiv {
     uint32_t d, m;

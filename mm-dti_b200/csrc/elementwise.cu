@@ -190,8 +190,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict
 // out(f32) = res(f32) + dropout(a)   (a: TI)
 template <typename TI>
 __global__ void __launch_bounds__(256) dropout_residual_fwd_kernel(const float* __restrict__ res, const TI* __restrict__ a,
-                                                                   float* __restrict__ out, long long n4, uint32_t key,
+                                                                   float* __restrict__ out, long long n4, uint32_t key, const unsigned long long* seed_off,
                                                                    uint32_t thresh16, float keep_scale) {
+    key = rng_effective_key(key, seed_off);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float r[4], v[4];
         load4(res + i * 4, r);
@@ -269,7 +270,8 @@ template <typename T> __device__ __forceinline__ void store8(T* p, float (&v)[8]
 template <typename TIN0, typename TIO, int OP>
 __global__ void __launch_bounds__(256) rowmap_colsum_kernel(const TIN0* __restrict__ in0, const TIO* __restrict__ in1,
                                                             TIO* __restrict__ out, float* __restrict__ colsum, int rows, int C,
-                                                            uint32_t key, uint32_t thresh16, float keep_scale) {
+                                                            uint32_t key, const unsigned long long* seed_off, uint32_t thresh16, float keep_scale) {
+    key = rng_effective_key(key, seed_off);
     constexpr int UNROLL = 4;
     extern __shared__ float part[];                   // [rpp][C] when rpp > 1
     const int tpr = C >> 3;                           // threads per row (8 columns each); host guarantees tpr <= 256
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(256) rowmap_colsum_kernel(const TIN0* __restri
     }
 }
 
-__global__ void ew_mask_kernel(uint8_t* keep, long long n, uint32_t key, uint32_t thresh16) {
+__global__ void ew_mask_kernel(uint8_t* keep, long long n, uint32_t key, const unsigned long long* seed_off, uint32_t thresh16) {
+    key = rng_effective_key(key, seed_off);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         keep[i] = ew_keep(key, (unsigned long long)i, thresh16) ? 1 : 0;
 }
@@ -402,8 +405,8 @@ extern "C" int mmdti_dropout_residual_fwd(const float* res, const void* a, float
     const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = ew_grid(n / 4, 256);
-    if (a_dtype == MMDTI_F32) dropout_residual_fwd_kernel<float><<<grid, 256, 0, st>>>(res, static_cast<const float*>(a), out, n / 4, key, th, ks);
-    else if (a_dtype == MMDTI_BF16) dropout_residual_fwd_kernel<bf16><<<grid, 256, 0, st>>>(res, static_cast<const bf16*>(a), out, n / 4, key, th, ks);
+    if (a_dtype == MMDTI_F32) dropout_residual_fwd_kernel<float><<<grid, 256, 0, st>>>(res, static_cast<const float*>(a), out, n / 4, key, mmdti_seed_offset_ptr(), th, ks);
+    else if (a_dtype == MMDTI_BF16) dropout_residual_fwd_kernel<bf16><<<grid, 256, 0, st>>>(res, static_cast<const bf16*>(a), out, n / 4, key, mmdti_seed_offset_ptr(), th, ks);
     else { mmdti_set_error("dropout_residual_fwd: a_dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
@@ -417,7 +420,7 @@ static int launch_rowmap(const void* in0, const void* in1, void* out, float* col
     const size_t smem = rpp > 1 ? (size_t)rpp * C * sizeof(float) : 0;
     const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 4 * rpp - 1) / (4 * rpp), (long long)num_sms() * 2));
     rowmap_colsum_kernel<TIN0, TIO, OP><<<grid, 256, smem, st>>>(static_cast<const TIN0*>(in0), static_cast<const TIO*>(in1),
-                                                                  static_cast<TIO*>(out), colsum, rows, C, key, th, ks);
+                                                                  static_cast<TIO*>(out), colsum, rows, C, key, mmdti_seed_offset_ptr(), th, ks);
     return 0;
 }
 
@@ -474,7 +477,7 @@ extern "C" int mmdti_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t se
     float ks;
     drop_params(p, th, ks);
     const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
-    ew_mask_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keep, n, key, th);
+    ew_mask_kernel<<<ew_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keep, n, key, mmdti_seed_offset_ptr(), th);
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }

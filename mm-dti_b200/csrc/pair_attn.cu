@@ -46,6 +46,7 @@ struct FwdParams {
     float scale, keep_scale;
     uint32_t thresh16;
     unsigned long long seed;
+    const unsigned long long* seed_off;
     int crb, nchunks;     // 16-row blocks per chunk, chunks per tile
 };
 
@@ -57,6 +58,7 @@ struct BwdParams {
     float scale, keep_scale;
     uint32_t thresh16;
     unsigned long long seed;
+    const unsigned long long* seed_off;
     int crb, nchunks;
 };
 
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
                 sumb += sc[kb][2] + sc[kb][3];
             }
             if (do_drop) {
-                const uint32_t rkey = rng_stream_key(p.seed, (uint32_t)tile);
+                const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
                     const int col = kb * 8 + 2 * q4;
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             delb = quad_sum(delb);
 
             // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
-            const uint32_t rkey = rng_stream_key(p.seed, (uint32_t)tile);
+            const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
             const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
@@ -775,7 +777,9 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
 }
 
 // ------------------------------------------------------------------ debug: keep mask (dense (B,H,L,L))
-__global__ void dropout_mask_kernel(uint8_t* keep, int H, int L, uint32_t thresh16, unsigned long long seed) {
+__global__ void dropout_mask_kernel(uint8_t* keep, int H, int L, uint32_t thresh16, unsigned long long seed,
+                                    const unsigned long long* seed_off) {
+    seed = rng_effective_seed(seed, seed_off);
     const int bh = blockIdx.x;
     const uint32_t rkey = rng_stream_key(seed, (uint32_t)bh);
     for (int e = threadIdx.x; e < L * L; e += blockDim.x) {
@@ -935,7 +939,7 @@ extern "C" int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, 
     MMDTI_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "pair_attn_fwd: dropout_p out of range");
     FwdParams p;
     p.q = q; p.k = k; p.v = v; p.o = o; p.pin = pair_in; p.pout = pair_out;
-    p.ldqkv = ldqkv; p.ldo = ldo; p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed;
+    p.ldqkv = ldqkv; p.ldo = ldo; p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed; p.seed_off = mmdti_seed_offset_ptr();
     p.crb = 0; p.nchunks = 0;
     drop_params(dropout_p, p.thresh16, p.keep_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -968,7 +972,7 @@ extern "C" int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, 
     BwdParams p;
     p.q = q; p.k = k; p.v = v; p.s = s; p.o = o; p.d_o = d_o; p.dpout = d_pair_out; p.dpin = d_pair_in;
     p.dq = dq; p.dk = dk; p.dv = dv; p.ldqkv = ldqkv; p.lddo = lddo; p.lddqkv = lddqkv;
-    p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed;
+    p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed; p.seed_off = mmdti_seed_offset_ptr();
     p.crb = 0; p.nchunks = 0;
     drop_params(dropout_p, p.thresh16, p.keep_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -990,7 +994,7 @@ extern "C" int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, 
     uint32_t thresh16;
     float ks;
     drop_params(dropout_p, thresh16, ks);
-    dropout_mask_kernel<<<B * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(keep, H, L, thresh16, seed);
+    dropout_mask_kernel<<<B * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(keep, H, L, thresh16, seed, mmdti_seed_offset_ptr());
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }

@@ -372,6 +372,10 @@ EncodeTiledFn encode_fn() {
 
 // (rows, Dp) bf16 row-major -> 2-D map with a (64 x box_rows) box, 128-byte swizzle, zero OOB fill
 int make_map(CUtensorMap* map, const void* base, int rows, int Dp, int box_rows) {
+    // the driver entry point needs the primary context bound to THIS thread (autograd runs the backward
+    // on its own thread, which may not have made a runtime call yet)
+    static thread_local bool bound = false;
+    if (!bound) { cudaFree(0); bound = true; }
     EncodeTiledFn fn = encode_fn();
     if (!fn) { mmdti_set_error("cuTensorMapEncodeTiled is not available from the driver"); return MMDTI_ERR_CUDA; }
     const cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};

@@ -1,0 +1,63 @@
+"""CUDA-graph capture of a whole training step (forward + backward [+ optimizer]).
+
+The reference launches ~25 kernels per layer with CUDA_LAUNCH_BLOCKING=1 (models/mm_model.py:7);
+here one step is ~300 launches of fused kernels and library GEMMs, which leaves the host as the
+bottleneck at config-2 sizes.  Shapes are static per (batch, L), so the step is captured once and
+replayed: one graph launch per step.
+
+Dropout stays correct under replay: the seeds baked into the captured kernel arguments are combined
+on the device with a counter (`mmdti_set_seed_offset`) that the graph itself increments at the start
+of every replay, so each step draws fresh masks while forward and backward of one step agree."""
+import torch
+
+from . import _lib
+
+
+class GraphedStep:
+    """step_fn(*device_tensors) -> tensor or tuple of tensors (e.g. the loss).  step_fn must run the
+    complete step on the current stream (forward, backward, optionally optimizer.step()) and must not
+    synchronise with the host.  Parameters' .grad are left in static buffers (set .grad to None before
+    construction, do not set it to None afterwards).
+
+    example_inputs: tensors defining the static input signature; host (pinned) tensors are allowed,
+    in which case every call copies them to the static device buffers inside the timed path."""
+
+    def __init__(self, step_fn, example_inputs, device=None, warmup=3):
+        if not torch.cuda.is_available():
+            raise _lib.MMDTIError("GraphedStep needs a CUDA device")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.static_in = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in example_inputs]
+        for dst, src in zip(self.static_in, example_inputs):
+            dst.copy_(src)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        _lib.call("mmdti_set_seed_offset", self.counter)
+        _lib.launch_count -= 1                       # registration is not a kernel launch
+
+        def body():
+            self.counter.add_(1)
+            return step_fn(*self.static_in)
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        n0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = body()
+        self.launches_per_replay = _lib.launch_count - n0      # own kernels captured in the graph
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        _lib.launch_count += self.launches_per_replay
+        return self.static_out
+
+    def close(self):
+        _lib.call("mmdti_set_seed_offset", None)
+        _lib.launch_count -= 1
