@@ -76,7 +76,19 @@ int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, const float
                         void* out, int B, int L, int K, int H, int E, int pair_dtype, int fp32_math,
                         void* stream);
 
-/* Pieces of the backward of the above (the 128-wide GEMMs in between currently run as library
+/* Fused backward of the above (bf16 tensor-core math, fp32 accumulation): from d_out (B,H,L,Lp)
+ * gpair_dtype (non-finite entries are read as 0) ACCUMULATE (+=) the gradients of every parameter:
+ * d_means,d_stds (K), d_mul,d_bias (E), d_w1 (K,K), d_b1 (K), d_w2 (H,K), d_b2 (H), all f32.
+ * The basis / hidden activations are recomputed on chip; nothing of size pairs x 128 touches HBM
+ * (SURVEY.md Appendix B, K1).  There is no gradient to dist / edge_type. */
+int mmdti_pair_bias_bwd(const void* d_out, const float* dist, const int64_t* edge_type,
+                        const float* means, const float* stds, const float* mul, const float* bias,
+                        const float* w1, const float* b1, const float* w2, float* d_means,
+                        float* d_stds, float* d_mul, float* d_bias, float* d_w1, float* d_b1,
+                        float* d_w2, float* d_b2, int B, int L, int K, int H, int E, int gpair_dtype,
+                        void* stream);
+
+/* Pieces of the fp32 validation-mode backward (the 128-wide GEMMs in between run as fp32 library
  * GEMMs on the host side, see mm-dti_b200/ops.py:PairBiasFn.backward):
  *  - mmdti_gauss_basis: the (npairs,128) basis g (out_dtype f32|bf16), i.e. GaussianLayer.forward
  *    alone (models/mm_model.py:254-269);

@@ -32,6 +32,18 @@ struct BiasParams {
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU for the bf16 tensor-core path: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
+// the bf16 rounding of the result), 2 MUFU + 9 FMA-class instructions instead of erff's ~30
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float e = __expf(-0.5f * x * x);
+    const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erfa = fmaf(-poly * t, e, 1.f);
+    return x * (0.5f + copysignf(0.5f * erfa, x));
+}
 
 // ------------------------------------------------------------------ tensor-core forward
 template <typename TP>
@@ -139,8 +151,8 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
             for (int hf = 0; hf < 2; ++hf) {
                 const int nb = kk * 2 + hf, c0 = nb * 8 + 2 * q4;
                 const float bb0 = b1s[c0], bb1 = b1s[c0 + 1];
-                a[hf * 2 + 0] = pack_bf16(gelu_erf(z[nb][0] + bb0), gelu_erf(z[nb][1] + bb1));
-                a[hf * 2 + 1] = pack_bf16(gelu_erf(z[nb][2] + bb0), gelu_erf(z[nb][3] + bb1));
+                a[hf * 2 + 0] = pack_bf16(gelu_fast(z[nb][0] + bb0), gelu_fast(z[nb][1] + bb1));
+                a[hf * 2 + 1] = pack_bf16(gelu_fast(z[nb][2] + bb0), gelu_fast(z[nb][3] + bb1));
             }
             const int mrow = lane & 7, msel = lane >> 3;
 #pragma unroll

@@ -103,6 +103,13 @@ class PairBiasFn(torch.autograd.Function):
         d_w2 = torch.zeros(H, K, device=dev)
         d_b2 = torch.zeros(H, device=dev)
         d_out = d_out.contiguous()
+        if not ctx.fp32_math:
+            # production path: one fused tensor-core kernel, nothing of size pairs x 128 reaches HBM
+            call("mmdti_pair_bias_bwd", d_out, dist, edge_type, means, stds, mul, bias, w1, b1, w2, d_means, d_stds, d_mul,
+                 d_bias, d_w1, d_b1, d_w2, d_b2, i32(B), i32(L), i32(K), i32(H), i32(E), i32(DTYPE_CODE[d_out.dtype]),
+                 stream_ptr())
+            return (None, None, d_means.view(1, K), d_stds.view(1, K), d_mul.view(E, 1), d_bias.view(E, 1),
+                    d_w1, d_b1, d_w2, d_b2, None, None, None)
         w1c, w2c, b1c = w1.to(cdt), w2.to(cdt), b1.to(cdt)
         # molecules per chunk: bound the (pairs,128) temporaries to ~256 MB
         per_mol = L * L * K * (4 if ctx.fp32_math else 2) * 6
