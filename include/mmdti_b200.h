@@ -165,6 +165,19 @@ int mmdti_layernorm_fwd(const float* x, const float* w, const float* b, void* y,
 int mmdti_layernorm_bwd(const void* dy, const float* x, const float* w, const float* mean,
                         const float* rstd, const float* dx_add, float* dx, float* dw, float* db,
                         int rows, int D, int dy_dtype, void* stream);
+/* Fused pairs used by the encoder layer (one HBM pass instead of two each):
+ *   dropres_layernorm_fwd: xo = res + dropout(a) (f32, stored);  y = LN(xo) (f32|bf16 = dtype of a);
+ *   layernorm_bwd_dropout: dx = dx_add + dLN/dx (f32, stored);  da = dropout'(dx) (dtype of dy);
+ *                          dbias += colsum(da);  dw,db += LayerNorm parameter gradients.
+ * Same masks as dropout_residual_fwd / dropout_bwd for the same (p, seed). */
+int mmdti_dropres_layernorm_fwd(const float* res, const void* a, float* xo, const float* w,
+                                const float* b, void* y, float* mean, float* rstd, int rows, int D,
+                                float eps, float p, uint64_t seed, int a_dtype, int out_dtype,
+                                void* stream);
+int mmdti_layernorm_bwd_dropout(const void* dy, const float* x, const float* w, const float* mean,
+                                const float* rstd, const float* dx_add, float* dx, float* dw,
+                                float* db, void* da, float* dbias, int rows, int D, float p,
+                                uint64_t seed, int dy_dtype, void* stream);
 /* out = res + dropout(a): res,out (n) f32 (may alias), a (n) a_dtype.  n % 4 == 0. */
 int mmdti_dropout_residual_fwd(const float* res, const void* a, float* out, int64_t n, float p,
                                uint64_t seed, int a_dtype, void* stream);
@@ -173,7 +186,7 @@ int mmdti_dropout_bwd(const float* dx, void* da, float* dbias, int rows, int C, 
                       uint64_t seed, int da_dtype, void* stream);
 /* exact-erf GELU (unicore.utils.get_activation_fn("gelu") = F.gelu) and its backward:
  * dz = du * gelu'(z); dbias (C) f32 += column sums of dz (NULL to skip). */
-int mmdti_gelu_fwd(const void* z, void* u, int64_t n, int dtype, void* stream);
+int mmdti_gelu_fwd(const void* z, void* u, int64_t n, int dtype, void* stream);   /* n % 8 == 0 */
 int mmdti_gelu_bwd(const void* du, const void* z, void* dz, float* dbias, int rows, int C, int dtype,
                    void* stream);
 /* out (C) f32 += column sums of x (rows,C) — bias gradients. */

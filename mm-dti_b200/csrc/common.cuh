@@ -100,6 +100,11 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// one 16-byte reduction instead of four scalar atomics (sm_90+): the L2 atomic units see a quarter of the ops
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- tensor-core wrappers
 // D(16x8,f32) += A(16x8,bf16,row) * B(8x8,bf16,col)
 __device__ __forceinline__ void mma_bf16_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {

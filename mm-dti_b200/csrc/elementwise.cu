@@ -109,29 +109,102 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     }
 }
 
-// ------------------------------------------------------------------ LayerNorm backward
-// dx_out = (add ? dx_add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*w
-// dw += sum_rows dy*xhat, db += sum_rows dy   (warp partials -> smem -> atomics)
-template <typename TI, int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
-                                                            const float* __restrict__ w, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, const float* __restrict__ dx_add,
-                                                            float* __restrict__ dx, float* __restrict__ dw,
-                                                            float* __restrict__ db, int rows, int D) {
-    extern __shared__ float red[];       // [wpb][2][D]
+// ------------------------------------------------------------------ dropout + residual + LayerNorm forward (fused)
+// xo = res + dropout(a) (f32, stored: it is the next residual);  y = LN(xo) (TO);  mean/rstd saved.
+// The dropout mask is the one of dropout_residual_fwd (same key, same flat index), so dropout_bwd agrees.
+template <typename TA, typename TO, int NV>
+__global__ void __launch_bounds__(256) dropres_layernorm_fwd_kernel(const float* __restrict__ res, const TA* __restrict__ a,
+                                                                    float* __restrict__ xo, const float* __restrict__ w,
+                                                                    const float* __restrict__ b, TO* __restrict__ y,
+                                                                    float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                                                    int D, float eps, uint32_t key, const unsigned long long* seed_off,
+                                                                    uint32_t thresh16, float keep_scale) {
+    key = rng_effective_key(key, seed_off);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    float aw[NV][4], ab[NV][4], wv[NV][4];
+    for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+        float v[NV][4];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float av[4];
+                const long long idx = row * D + c;
+                load4(res + idx, v[i]);
+                load4(a + idx, av);
+                if (thresh16) {
+                    const uint32_t b0 = ew_bits(key, (unsigned long long)idx), b1 = ew_bits(key, (unsigned long long)idx + 2);
+                    av[0] = rng_keep(b0, 0, thresh16) ? av[0] * keep_scale : 0.f;
+                    av[1] = rng_keep(b0, 1, thresh16) ? av[1] * keep_scale : 0.f;
+                    av[2] = rng_keep(b1, 0, thresh16) ? av[2] * keep_scale : 0.f;
+                    av[3] = rng_keep(b1, 1, thresh16) ? av[3] * keep_scale : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[i][e] += av[e];
+                store4(xo + idx, v[i]);
+            } else v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+            s += v[i][0] + v[i][1] + v[i][2] + v[i][3];
+        }
+        const float mu = warp_sum(s) / D;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { const float d = v[i][e] - mu; q += d * d; }
+            }
+        }
+        const float rs = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float wv[4], bv[4], o[4];
+                load4(w + c, wv);
+                load4(b + c, bv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = (v[i][e] - mu) * rs * wv[e] + bv[e];
+                store4(y + row * D + c, o);
+            }
+        }
+        if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward + dropout backward (fused)
+// dx = dx_add + dLN/dx (f32, stored: the residual gradient);  da = dropout'(dx) (TDA);  dbias += colsum(da);
+// dw, db += LayerNorm parameter gradients.  Same mask as dropout_bwd (key, flat index).
+template <typename TI, typename TDA, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_dropout_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
+                                                                    const float* __restrict__ w, const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, const float* __restrict__ dx_add,
+                                                                    float* __restrict__ dx, float* __restrict__ dw,
+                                                                    float* __restrict__ db, TDA* __restrict__ da,
+                                                                    float* __restrict__ dbias, int rows, int D, uint32_t key,
+                                                                    const unsigned long long* seed_off, uint32_t thresh16,
+                                                                    float keep_scale) {
+    key = rng_effective_key(key, seed_off);
+    extern __shared__ float red[];       // [wpb][3][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float aw[NV][4], ab[NV][4], ad[NV][4], wv[NV][4];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = (i * 32 + lane) * 4;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) aw[i][e] = ab[i][e] = wv[i][e] = 0.f;
+        for (int e = 0; e < 4; ++e) aw[i][e] = ab[i][e] = ad[i][e] = wv[i][e] = 0.f;
         if (c < D) load4(w + c, wv[i]);
     }
     for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
         const float mu = mean[row], rs = rstd[row];
-        float g[NV][4], xh[NV][4];
+        float g[NV][4], xh[NV][4], addv[NV][4];
         float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D && dx_add) load4(dx_add + row * D + c, addv[i]);
+            else addv[i][0] = addv[i][1] = addv[i][2] = addv[i][3] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = (i * 32 + lane) * 4;
@@ -160,10 +233,107 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict
             const int c = (i * 32 + lane) * 4;
             if (c < D) {
                 float o[4];
-                if (dx_add) load4(dx_add + row * D + c, o);
-                else o[0] = o[1] = o[2] = o[3] = 0.f;
+                const long long idx = row * D + c;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) o[e] += rs * (g[i][e] - c1 - xh[i][e] * c2);
+                for (int e = 0; e < 4; ++e) o[e] = addv[i][e] + rs * (g[i][e] - c1 - xh[i][e] * c2);
+                store4(dx + idx, o);
+                if (thresh16) {
+                    const uint32_t b0 = ew_bits(key, (unsigned long long)idx), b1 = ew_bits(key, (unsigned long long)idx + 2);
+                    o[0] = rng_keep(b0, 0, thresh16) ? o[0] * keep_scale : 0.f;
+                    o[1] = rng_keep(b0, 1, thresh16) ? o[1] * keep_scale : 0.f;
+                    o[2] = rng_keep(b1, 0, thresh16) ? o[2] * keep_scale : 0.f;
+                    o[3] = rng_keep(b1, 1, thresh16) ? o[3] * keep_scale : 0.f;
+                }
+                store4(da + idx, o);
+                if constexpr (sizeof(TDA) == 2) {           // sum what was stored (rounded), like dropout_bwd
+                    const float2 f0 = unpack_bf16(pack_bf16(o[0], o[1])), f1 = unpack_bf16(pack_bf16(o[2], o[3]));
+                    ad[i][0] += f0.x; ad[i][1] += f0.y; ad[i][2] += f1.x; ad[i][3] += f1.y;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ad[i][e] += o[e];
+                }
+            }
+        }
+    }
+    float* rw = red + (size_t)warp * 3 * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < D) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { rw[c + e] = aw[i][e]; rw[D + c + e] = ab[i][e]; rw[2 * D + c + e] = ad[i][e]; }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x * 4; c < 3 * D; c += blockDim.x * 4) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int k = 0; k < wpb; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(red + (size_t)k * 3 * D + c);
+            s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+        }
+        red_add_v4(c < D ? dw + c : (c < 2 * D ? db + (c - D) : dbias + (c - 2 * D)), s0, s1, s2, s3);
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dx_out = (add ? dx_add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*w
+// dw += sum_rows dy*xhat, db += sum_rows dy   (warp partials -> smem -> atomics)
+template <typename TI, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ dx_add,
+                                                            float* __restrict__ dx, float* __restrict__ dw,
+                                                            float* __restrict__ db, int rows, int D) {
+    extern __shared__ float red[];       // [wpb][2][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    float aw[NV][4], ab[NV][4], wv[NV][4];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) aw[i][e] = ab[i][e] = wv[i][e] = 0.f;
+        if (c < D) load4(w + c, wv[i]);
+    }
+    for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+        const float mu = mean[row], rs = rstd[row];
+        float g[NV][4], xh[NV][4], addv[NV][4];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D && dx_add) load4(dx_add + row * D + c, addv[i]);
+            else addv[i][0] = addv[i][1] = addv[i][2] = addv[i][3] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float dyv[4], xv[4];
+                load4(dy + row * D + c, dyv);
+                load4(x + row * D + c, xv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    xh[i][e] = (xv[e] - mu) * rs;
+                    g[i][e] = dyv[e] * wv[i][e];
+                    c1 += g[i][e];
+                    c2 += g[i][e] * xh[i][e];
+                    aw[i][e] += dyv[e] * xh[i][e];
+                    ab[i][e] += dyv[e];
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) g[i][e] = xh[i][e] = 0.f;
+            }
+        }
+        c1 = warp_sum(c1) / D;
+        c2 = warp_sum(c2) / D;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = addv[i][e] + rs * (g[i][e] - c1 - xh[i][e] * c2);
                 store4(dx + row * D + c, o);
             }
         }
@@ -178,11 +348,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict
         }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < wpb; ++k) s += red[(size_t)k * 2 * D + c];
-        if (c < D) atomicAdd(dw + c, s);
-        else atomicAdd(db + (c - D), s);
+    for (int c = threadIdx.x * 4; c < 2 * D; c += blockDim.x * 4) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int k = 0; k < wpb; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(red + (size_t)k * 2 * D + c);
+            s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+        }
+        red_add_v4(c < D ? dw + c : db + (c - D), s0, s1, s2, s3);
     }
 }
 
@@ -217,14 +389,54 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
     const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+// bf16 tensors: exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the bf16
+// rounding of the result): 2 MUFU + ~10 FMA-class instructions instead of erff + expf (~50); exp(-x^2/2) is
+// shared between erf and the normal density of the gradient.
+__device__ __forceinline__ void gelu_fast_pair(float x, float& val, float& grad) {
+    const float e = __expf(-0.5f * x * x);
+    const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erfa = fmaf(-poly * t, e, 1.f);
+    const float cdf = 0.5f + copysignf(0.5f * erfa, x);
+    val = x * cdf;
+    grad = fmaf(x * e, 0.3989422804014327f, cdf);
+}
+template <typename T> __device__ __forceinline__ float gelu_t(float x) {
+    if constexpr (sizeof(T) == 4) return gelu_f(x);
+    float v, g;
+    gelu_fast_pair(x, v, g);
+    return v;
+}
+template <typename T> __device__ __forceinline__ float gelu_grad_t(float x) {
+    if constexpr (sizeof(T) == 4) return gelu_grad_f(x);
+    float v, g;
+    gelu_fast_pair(x, v, g);
+    return g;
+}
 template <typename T>
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ u, long long n4) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float v[4];
-        load4(z + i * 4, v);
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ u, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        if constexpr (sizeof(T) == 4) { load4(z + i * 8, *reinterpret_cast<float(*)[4]>(&v[0])); load4(z + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&v[4])); }
+        else {
+            const uint4 q = *reinterpret_cast<const uint4*>(z + i * 8);
+            float2 f;
+            f = unpack_bf16(q.x); v[0] = f.x; v[1] = f.y;
+            f = unpack_bf16(q.y); v[2] = f.x; v[3] = f.y;
+            f = unpack_bf16(q.z); v[4] = f.x; v[5] = f.y;
+            f = unpack_bf16(q.w); v[6] = f.x; v[7] = f.y;
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = gelu_f(v[e]);
-        store4(u + i * 4, v);
+        for (int e = 0; e < 8; ++e) v[e] = gelu_t<T>(v[e]);
+        if constexpr (sizeof(T) == 4) { store4(u + i * 8, *reinterpret_cast<float(*)[4]>(&v[0])); store4(u + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&v[4])); }
+        else {
+            uint4 q;
+            q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(u + i * 8) = q;
+        }
     }
 }
 // ------------------------------------------------------------------ row map + column sums
@@ -302,7 +514,7 @@ __global__ void __launch_bounds__(256) rowmap_colsum_kernel(const TIN0* __restri
                     const long long idx = (long long)r * C + tcol * 8;
                     if constexpr (OP == OP_GELU_BWD) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) a[u][e] *= gelu_grad_f(b[u][e]);
+                        for (int e = 0; e < 8; ++e) a[u][e] *= gelu_grad_t<TIO>(b[u][e]);
                         store8(out + idx, a[u]);
                     } else if constexpr (OP == OP_DROPOUT_BWD) {
                         if (thresh16) {
@@ -328,14 +540,17 @@ __global__ void __launch_bounds__(256) rowmap_colsum_kernel(const TIN0* __restri
             for (int e = 0; e < 8; ++e) part[trow * C + tcol * 8 + e] = acc[e];
         }
         __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            float s = 0.f;
-            for (int k = 0; k < rpp; ++k) s += part[k * C + c];
-            atomicAdd(colsum + c, s);
+        for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            for (int k = 0; k < rpp; ++k) {
+                const float4 v = *reinterpret_cast<const float4*>(part + k * C + c);
+                s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+            }
+            red_add_v4(colsum + c, s0, s1, s2, s3);
         }
     } else if (active) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(colsum + tcol * 8 + e, acc[e]);
+        red_add_v4(colsum + tcol * 8, acc[0], acc[1], acc[2], acc[3]);
+        red_add_v4(colsum + tcol * 8 + 4, acc[4], acc[5], acc[6], acc[7]);
     }
 }
 
@@ -379,7 +594,7 @@ extern "C" int mmdti_layernorm_bwd(const void* dy, const float* x, const float* 
                   "layernorm_bwd: bad arguments (D=%d)", D);
     MMDTI_REQUIRE(dy_dtype == MMDTI_F32 || dy_dtype == MMDTI_BF16, "layernorm_bwd: dy_dtype must be f32 or bf16");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = std::min(ew_grid(rows, 8), num_sms() * 2);
+    const int grid = std::min(ew_grid(rows, 8), num_sms() * 4);
     const size_t smem = (size_t)8 * 2 * D * sizeof(float);
 #define CALL(NV)                                                                                                         \
     if (dy_dtype == MMDTI_F32) {                                                                                         \
@@ -388,6 +603,63 @@ extern "C" int mmdti_layernorm_bwd(const void* dy, const float* x, const float* 
     } else {                                                                                                             \
         MMDTI_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         layernorm_bwd_kernel<bf16, NV><<<grid, 256, smem, st>>>(static_cast<const bf16*>(dy), x, w, mean, rstd, dx_add, dx, dw, db, rows, D); \
+    }
+    DISPATCH_NV(D, CALL)
+#undef CALL
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_dropres_layernorm_fwd(const float* res, const void* a, float* xo, const float* w, const float* b, void* y,
+                                          float* mean, float* rstd, int rows, int D, float eps, float p, uint64_t seed, int a_dtype,
+                                          int out_dtype, void* stream) {
+    MMDTI_REQUIRE(res && a && xo && w && b && y && mean && rstd && rows > 0 && D > 0 && D % 4 == 0 && D <= 1024,
+                  "dropres_layernorm_fwd: need D %% 4 == 0 and D <= 1024 (D=%d)", D);
+    MMDTI_REQUIRE(p >= 0.f && p < 1.f, "dropres_layernorm_fwd: p out of range");
+    MMDTI_REQUIRE((a_dtype == MMDTI_F32 && out_dtype == MMDTI_F32) || (a_dtype == MMDTI_BF16 && out_dtype == MMDTI_BF16),
+                  "dropres_layernorm_fwd: a / y must both be f32 or both bf16");
+    uint32_t th;
+    float ks;
+    drop_params(p, th, ks);
+    const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(rows, 8);
+#define CALL(NV)                                                                                                             \
+    if (out_dtype == MMDTI_F32)                                                                                               \
+        dropres_layernorm_fwd_kernel<float, float, NV><<<grid, 256, 0, st>>>(res, static_cast<const float*>(a), xo, w, b, static_cast<float*>(y), \
+                                                                             mean, rstd, rows, D, eps, key, mmdti_seed_offset_ptr(), th, ks); \
+    else                                                                                                                      \
+        dropres_layernorm_fwd_kernel<bf16, bf16, NV><<<grid, 256, 0, st>>>(res, static_cast<const bf16*>(a), xo, w, b, static_cast<bf16*>(y), \
+                                                                           mean, rstd, rows, D, eps, key, mmdti_seed_offset_ptr(), th, ks)
+    DISPATCH_NV(D, CALL)
+#undef CALL
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_layernorm_bwd_dropout(const void* dy, const float* x, const float* w, const float* mean, const float* rstd,
+                                           const float* dx_add, float* dx, float* dw, float* db, void* da, float* dbias, int rows,
+                                           int D, float p, uint64_t seed, int dy_dtype, void* stream) {
+    MMDTI_REQUIRE(dy && x && w && mean && rstd && dx_add && dx && dw && db && da && dbias && rows > 0 && D % 4 == 0 && D <= 1024,
+                  "layernorm_bwd_dropout: bad arguments (D=%d)", D);
+    MMDTI_REQUIRE(dy_dtype == MMDTI_F32 || dy_dtype == MMDTI_BF16, "layernorm_bwd_dropout: dy_dtype must be f32 or bf16");
+    MMDTI_REQUIRE(p >= 0.f && p < 1.f, "layernorm_bwd_dropout: p out of range");
+    uint32_t th;
+    float ks;
+    drop_params(p, th, ks);
+    const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = std::min(ew_grid(rows, 8), num_sms() * 4);
+    const size_t smem = (size_t)8 * 3 * D * sizeof(float);
+#define CALL(NV)                                                                                                         \
+    if (dy_dtype == MMDTI_F32) {                                                                                         \
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_dropout_kernel<float, float, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        layernorm_bwd_dropout_kernel<float, float, NV><<<grid, 256, smem, st>>>(static_cast<const float*>(dy), x, w, mean, rstd, dx_add, dx, dw, db, \
+                                                                            static_cast<float*>(da), dbias, rows, D, key, mmdti_seed_offset_ptr(), th, ks); \
+    } else {                                                                                                             \
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_dropout_kernel<bf16, bf16, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        layernorm_bwd_dropout_kernel<bf16, bf16, NV><<<grid, 256, smem, st>>>(static_cast<const bf16*>(dy), x, w, mean, rstd, dx_add, dx, dw, db, \
+                                                                          static_cast<bf16*>(da), dbias, rows, D, key, mmdti_seed_offset_ptr(), th, ks); \
     }
     DISPATCH_NV(D, CALL)
 #undef CALL
@@ -440,11 +712,11 @@ extern "C" int mmdti_dropout_bwd(const float* dx, void* da, float* dbias, int ro
 }
 
 extern "C" int mmdti_gelu_fwd(const void* z, void* u, int64_t n, int dtype, void* stream) {
-    MMDTI_REQUIRE(z && u && n > 0 && n % 4 == 0, "gelu_fwd: n must be a positive multiple of 4");
+    MMDTI_REQUIRE(z && u && n > 0 && n % 8 == 0, "gelu_fwd: n must be a positive multiple of 8");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = ew_grid(n / 4, 256);
-    if (dtype == MMDTI_F32) gelu_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(z), static_cast<float*>(u), n / 4);
-    else if (dtype == MMDTI_BF16) gelu_fwd_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(z), static_cast<bf16*>(u), n / 4);
+    const int grid = ew_grid(n / 8, 256);
+    if (dtype == MMDTI_F32) gelu_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(z), static_cast<float*>(u), n / 8);
+    else if (dtype == MMDTI_BF16) gelu_fwd_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(z), static_cast<bf16*>(u), n / 8);
     else { mmdti_set_error("gelu_fwd: dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;

@@ -340,8 +340,10 @@ class EncoderLayerFn(torch.autograd.Function):
              i32(B), i32(H), i32(L), f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_in.dtype]), sp)
         a = torch.addmm(b_out_l, o, w_out_l.t())
         x1 = torch.empty_like(x2d)
-        call("mmdti_dropout_residual_fwd", x2d, a, x1, i64(rows * D), f32(p_drop), u64(seeds[1]), i32(code), sp)
-        h2, st2 = layernorm_fwd(x1, ln2_wd, ln2_bd, dt)
+        h2 = torch.empty((rows, D), device=x.device, dtype=dt)
+        st2 = torch.empty((2, rows), device=x.device, dtype=torch.float32)
+        call("mmdti_dropres_layernorm_fwd", x2d, a, x1, ln2_wd, ln2_bd, h2, st2[0], st2[1], i32(rows), i32(D), f32(1e-5),
+             f32(p_drop), u64(seeds[1]), i32(code), i32(code), sp)
         z = torch.addmm(b_fc1_l, h2, w_fc1_l.t())
         u = torch.empty_like(z)
         call("mmdti_gelu_fwd", z, u, i64(z.numel()), i32(code), sp)
@@ -387,10 +389,10 @@ class EncoderLayerFn(torch.autograd.Function):
         dh2 = torch.mm(dz, w_fc1_l)
         dW_fc1 = _mm_f32(dz.t(), h2)
         dx1 = torch.empty_like(x2d)
-        call("mmdti_layernorm_bwd", dh2, x1, ln2_w, st2[0], st2[1], dx2, dx1, dw_ln2, db_ln2, i32(rows), i32(D), i32(code), sp)
-        # ---- attention block
+        # ---- attention block (LayerNorm-2 backward fused with the dropout backward of the attention output)
         da = torch.empty((rows, D), device=dev, dtype=dt)
-        call("mmdti_dropout_bwd", dx1, da, db_out, i32(rows), i32(D), f32(p_drop), u64(seeds[1]), i32(code), sp)
+        call("mmdti_layernorm_bwd_dropout", dh2, x1, ln2_w, st2[0], st2[1], dx2, dx1, dw_ln2, db_ln2, da, db_out, i32(rows),
+             i32(D), f32(p_drop), u64(seeds[1]), i32(code), sp)
         d_o = torch.mm(da, w_out_l)
         dW_out = _mm_f32(da.t(), o)
         dqkv = torch.empty_like(qkv)

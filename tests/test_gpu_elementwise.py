@@ -128,3 +128,46 @@ def test_fused_layer_training_mode_replay(act, pair, report):
         errs["d_" + k] = rel_err(named[k].grad, prm[k].grad)
     report("fused_layer_train", act, pair, {k: "%.1e" % v for k, v in errs.items()})
     assert max(errs.values()) < (5e-5 if act == "fp32" else 4e-2), errs
+
+
+@pytest.mark.parametrize("D", [64, 512])
+@pytest.mark.parametrize("dt,code", [(torch.float32, 0), (torch.bfloat16, 1)])
+def test_fused_dropres_layernorm_pairs(D, dt, code):
+    """dropout+residual+LayerNorm (fwd) and LayerNorm-bwd+dropout-bwd equal the two-kernel sequences
+    they replace (same masks, exported by mmdti_dropout_mask)."""
+    from mmdti_b200 import ops
+    from mmdti_b200._lib import call, f32, i32, stream_ptr, u64
+    rows, p, seed = 91, 0.1, 4242
+    g = torch.Generator().manual_seed(D + code)
+    res, a = torch.randn(rows, D, generator=g), torch.randn(rows, D, generator=g).to(dt)
+    w, b = torch.randn(D, generator=g), torch.randn(D, generator=g)
+    keep = ops.dropout_mask(rows * D, p, seed).view(rows, D).cpu()
+    thr = round(p * 65536)
+    scale = 65536.0 / (65536 - thr)
+    xo = torch.empty(rows, D, device="cuda")
+    y = torch.empty(rows, D, device="cuda", dtype=dt)
+    st = torch.empty(2, rows, device="cuda")
+    call("mmdti_dropres_layernorm_fwd", res.cuda(), a.cuda(), xo, w.cuda(), b.cuda(), y, st[0], st[1], i32(rows), i32(D), f32(1e-5),
+         f32(p), u64(seed), i32(code), i32(code), stream_ptr())
+    want_x = res + a.float() * keep * scale
+    assert rel_err(xo, want_x) < 1e-6
+    want_y = F.layer_norm(want_x.double(), (D,), w.double(), b.double(), 1e-5)
+    assert rel_err(y.float(), want_y) < (2e-6 if dt == torch.float32 else 6e-3)
+    # backward pair, against mmdti_layernorm_bwd followed by mmdti_dropout_bwd
+    dy = torch.randn(rows, D, generator=g).to(dt)
+    add = torch.randn(rows, D, generator=g)
+    dx_ref = torch.empty(rows, D, device="cuda")
+    dw_ref, db_ref = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    call("mmdti_layernorm_bwd", dy.cuda(), xo, w.cuda(), st[0], st[1], add.cuda(), dx_ref, dw_ref, db_ref, i32(rows), i32(D),
+         i32(code), stream_ptr())
+    da_ref = torch.empty(rows, D, device="cuda", dtype=dt)
+    dbias_ref = torch.zeros(D, device="cuda")
+    call("mmdti_dropout_bwd", dx_ref, da_ref, dbias_ref, i32(rows), i32(D), f32(p), u64(seed), i32(code), stream_ptr())
+    dx = torch.empty(rows, D, device="cuda")
+    dw, db, dbias = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    da = torch.empty(rows, D, device="cuda", dtype=dt)
+    call("mmdti_layernorm_bwd_dropout", dy.cuda(), xo, w.cuda(), st[0], st[1], add.cuda(), dx, dw, db, da, dbias, i32(rows), i32(D),
+         f32(p), u64(seed), i32(code), stream_ptr())
+    assert rel_err(dx, dx_ref) < 1e-6 and rel_err(dw, dw_ref) < 1e-5 and rel_err(db, db_ref) < 1e-5
+    assert torch.equal(da, da_ref)
+    assert rel_err(dbias, dbias_ref) < 1e-5
