@@ -158,15 +158,29 @@ __device__ __forceinline__ uint32_t rng_stream_key(unsigned long long seed, uint
     uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
     return mix32(lo ^ mix32(stream * 0x9E3779B1U + hi + 0x85EBCA6BU));
 }
-// 32 random bits shared by the column pair (col & ~1, col | 1) of `row`; low 16 bits belong to
-// the even column, high 16 bits to the odd one.  rows < 2^21, cols < 2^11.
+// 64 random bits for the "quad" of `row`: the column pairs (2*q4, 2*q4+1) of the 8-column blocks kb = 2m
+// (word .x) and kb = 2m+1 (word .y), m = col >> 4, q4 = (col & 7) >> 1.  Low 16 bits of a word belong to
+// the even column, high 16 bits to the odd one.  One avalanche hash + one multiply-xorshift per 4 elements.
+// rows < 2^21, cols < 2^11.
+__device__ __forceinline__ uint2 rng_quad_bits(uint32_t key, uint32_t row, uint32_t col) {
+    const uint32_t qidx = ((col >> 4) << 2) | ((col & 7u) >> 1);
+    uint2 w;
+    w.x = mix32(key ^ ((row << 10) | qidx));
+    w.y = w.x * 0x9E3779B1U;
+    w.y ^= w.y >> 15;
+    return w;
+}
+// the 32-bit word holding the bits of element (row, col)
 __device__ __forceinline__ uint32_t rng_pair_bits(uint32_t key, uint32_t row, uint32_t col) {
-    return mix32(key ^ ((row << 10) | (col >> 1)));
+    const uint2 w = rng_quad_bits(key, row, col);
+    return (col & 8u) ? w.y : w.x;
 }
 __device__ __forceinline__ bool rng_keep(uint32_t bits, uint32_t col, uint32_t thresh16) {
     uint32_t r = (col & 1u) ? (bits >> 16) : (bits & 0xffffu);
     return r >= thresh16;
 }
+// per-halfword keep mask (0xFFFF = keep) of a 32-bit word of random bits
+__device__ __forceinline__ uint32_t rng_keep_mask2(uint32_t bits, uint32_t thresh2) { return __vcmpgeu2(bits, thresh2); }
 
 // Device-resident RNG offset (CUDA-graph replays): when the host registered a device counter with
 // mmdti_set_seed_offset(), every dropout kernel adds *counter to its seed, so a captured step draws fresh

@@ -111,8 +111,15 @@ struct FwdStage {
     }
 };
 
+// threads per CTA never exceed 32 * ceil(NKB/2) (one warp per 16-row block of a <= 8-block chunk); the
+// register budget is capped so that ~640 threads stay resident per SM (4 CTAs of 160 threads at L = 66)
+template <int NKB> struct FwdLaunch {
+    static constexpr int MAXT = (NKB + 1) / 2 * 32 < 256 ? (NKB + 1) / 2 * 32 : 256;
+    static constexpr int MINB = 640 / MAXT < 1 ? 1 : (640 / MAXT > 8 ? 8 : 640 / MAXT);
+};
+
 template <typename T, typename TP, int NKB>
-__global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pair_attn_fwd_kernel(const FwdParams p) {
     using G = Geo<NKB>;
     constexpr bool F32 = std::is_same<T, float>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -122,10 +129,14 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
     const int g = lane >> 2, q4 = lane & 3;
     const int L = p.L, NR = p.crb * 16;
 
-    FwdStage<T, TP, NKB> st[NSTAGE];
     const size_t stage_bytes = (FwdStage<T, TP, NKB>::bytes(NR) + 127) & ~size_t(127);
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) st[s].carve(smem_raw + s * stage_bytes, NR);
+    // stage views are re-derived from the shared-memory base on every use: keeps the pointers provably
+    // shared (LDS/STS instead of generic LD/ST through a local array of pointers)
+    auto stage = [&](int s) {
+        FwdStage<T, TP, NKB> x;
+        x.carve(smem_raw + (size_t)s * stage_bytes, NR);
+        return x;
+    };
 
     // one-time init: zero the whole ring (K/V rows beyond L stay zero for ever; slab rows the TMA never
     // writes must hold finite bit patterns, not NaNs), barriers
@@ -137,29 +148,31 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
     }
     __syncthreads();
 
-    const long long ntiles = (long long)p.B * p.H;
-    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
-    const long long w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
+    const int ntiles = p.B * p.H;
+    const int t0 = (int)((long long)ntiles * blockIdx.x / gridDim.x), t1 = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+    const int w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
     const size_t tile_elems = (size_t)L * G::STRIDE;
+    const FastDiv div_h((uint32_t)p.H), div_c((uint32_t)p.nchunks);
+    const uint32_t thresh2 = p.thresh16 | (p.thresh16 << 16);
 
-    auto prefetch = [&](long long w, int s) {
-        const long long tile = w / p.nchunks;
-        const int chunk = (int)(w - tile * p.nchunks);
-        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+    auto prefetch = [&](int w, int s) {
+        const int tile = (int)div_c.div((uint32_t)w);
+        const int chunk = w - tile * p.nchunks;
+        const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
         if (tid == 0) {
             const uint32_t bytes = (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP));
             mbar_arrive_expect_tx(&full_bar[s], bytes);
-            bulk_g2s(st[s].slab, static_cast<const TP*>(p.pin) + tile * tile_elems + (size_t)row0 * G::STRIDE, bytes,
+            bulk_g2s(stage(s).slab, static_cast<const TP*>(p.pin) + (size_t)tile * tile_elems + (size_t)row0 * G::STRIDE, bytes,
                      &full_bar[s]);
         }
         const T* qg = static_cast<const T*>(p.q) + (size_t)b * L * p.ldqkv + h * HD;
         const T* kg = static_cast<const T*>(p.k) + (size_t)b * L * p.ldqkv + h * HD;
         const T* vg = static_cast<const T*>(p.v) + (size_t)b * L * p.ldqkv + h * HD;
         for (int i = tid; i < 2 * L + nrows; i += nthr) {
-            if (i < L) cp_head_row(st[s].K + i * HD, kg + (size_t)i * p.ldqkv);
-            else if (i < 2 * L) cp_head_row(st[s].V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
-            else cp_head_row(st[s].Q + (i - 2 * L) * HD, qg + (size_t)(row0 + i - 2 * L) * p.ldqkv);
+            if (i < L) cp_head_row(stage(s).K + i * HD, kg + (size_t)i * p.ldqkv);
+            else if (i < 2 * L) cp_head_row(stage(s).V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
+            else cp_head_row(stage(s).Q + (i - 2 * L) * HD, qg + (size_t)(row0 + i - 2 * L) * p.ldqkv);
         }
         cp_async_commit();
     };
@@ -168,11 +181,11 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
     if (w0 < w1) prefetch(w0, 0);
 
     int it = 0;
-    for (long long w = w0; w < w1; ++w, ++it) {
+    for (int w = w0; w < w1; ++w, ++it) {
         const int s = it & 1;
-        const long long tile = w / p.nchunks;
-        const int chunk = (int)(w - tile * p.nchunks);
-        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+        const int tile = (int)div_c.div((uint32_t)w);
+        const int chunk = w - tile * p.nchunks;
+        const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
 
         cp_async_wait<0>();
@@ -184,13 +197,13 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
         }
 
         if (warp < p.crb && row0 + warp * 16 < L) {
-            const T* Ks = st[s].K;
-            const T* Vs = st[s].V;
-            const T* Qs = st[s].Q;
+            const T* Ks = stage(s).K;
+            const T* Vs = stage(s).V;
+            const T* Qs = stage(s).Q;
             const int la = warp * 16 + g, lb = la + 8;               // local rows
             const int ra = row0 + la, rbb = row0 + lb;                // global rows
-            TP* srow_a = st[s].slab + la * G::STRIDE;
-            TP* srow_b = st[s].slab + lb * G::STRIDE;
+            TP* srow_a = stage(s).slab + la * G::STRIDE;
+            TP* srow_b = stage(s).slab + lb * G::STRIDE;
             float sc[NKB][4];
 
             // ---- S = Q K^T
@@ -262,17 +275,32 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
                 suma += sc[kb][0] + sc[kb][1];
                 sumb += sc[kb][2] + sc[kb][3];
             }
+            // dropout: per-halfword keep masks (0xFFFF = keep), applied to the packed bf16 probabilities below
+            uint32_t mka[NKB], mkb[NKB];
             if (do_drop) {
                 const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
 #pragma unroll
-                for (int kb = 0; kb < NKB; ++kb) {
-                    const int col = kb * 8 + 2 * q4;
-                    const uint32_t ba = rng_pair_bits(rkey, ra, col), bb = rng_pair_bits(rkey, rbb, col);
-                    if (!rng_keep(ba, 0, p.thresh16)) sc[kb][0] = 0.f;
-                    if (!rng_keep(ba, 1, p.thresh16)) sc[kb][1] = 0.f;
-                    if (!rng_keep(bb, 0, p.thresh16)) sc[kb][2] = 0.f;
-                    if (!rng_keep(bb, 1, p.thresh16)) sc[kb][3] = 0.f;
+                for (int kb = 0; kb < NKB; kb += 2) {
+                    const uint2 wa = rng_quad_bits(rkey, ra, kb * 8 + 2 * q4), wb = rng_quad_bits(rkey, rbb, kb * 8 + 2 * q4);
+                    mka[kb] = rng_keep_mask2(wa.x, thresh2);
+                    mkb[kb] = rng_keep_mask2(wb.x, thresh2);
+                    if (kb + 1 < NKB) {
+                        mka[kb + 1] = rng_keep_mask2(wa.y, thresh2);
+                        mkb[kb + 1] = rng_keep_mask2(wb.y, thresh2);
+                    }
                 }
+                if constexpr (F32) {
+#pragma unroll
+                    for (int kb = 0; kb < NKB; ++kb) {
+                        if (!(mka[kb] & 0xffffu)) sc[kb][0] = 0.f;
+                        if (!(mka[kb] >> 16)) sc[kb][1] = 0.f;
+                        if (!(mkb[kb] & 0xffffu)) sc[kb][2] = 0.f;
+                        if (!(mkb[kb] >> 16)) sc[kb][3] = 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb) mka[kb] = mkb[kb] = 0xffffffffu;
             }
             suma = quad_sum(suma);
             sumb = quad_sum(sumb);
@@ -291,12 +319,12 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
                     for (int jj = 0; jj < 2; ++jj) {
                         if (j + jj < G::NKB16) {
                             const int kb0 = 2 * (j + jj), kb1 = kb0 + 1;
-                            const uint32_t a0 = pack_bf16(sc[kb0][0], sc[kb0][1]);
-                            const uint32_t a1 = pack_bf16(sc[kb0][2], sc[kb0][3]);
+                            const uint32_t a0 = pack_bf16(sc[kb0][0], sc[kb0][1]) & mka[kb0];
+                            const uint32_t a1 = pack_bf16(sc[kb0][2], sc[kb0][3]) & mkb[kb0];
                             uint32_t a2 = 0u, a3 = 0u;
                             if (kb1 < NKB) {
-                                a2 = pack_bf16(sc[kb1][0], sc[kb1][1]);
-                                a3 = pack_bf16(sc[kb1][2], sc[kb1][3]);
+                                a2 = pack_bf16(sc[kb1][0], sc[kb1][1]) & mka[kb1];
+                                a3 = pack_bf16(sc[kb1][2], sc[kb1][3]) & mkb[kb1];
                             }
                             mma_bf16_16816(o, a0, a1, a2, a3, jj ? b2 : b0, jj ? b3 : b1);
                         }
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(256) pair_attn_fwd_kernel(const FwdParams p) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            bulk_s2g(static_cast<TP*>(p.pout) + tile * tile_elems + (size_t)row0 * G::STRIDE, st[s].slab,
+            bulk_s2g(static_cast<TP*>(p.pout) + tile * tile_elems + (size_t)row0 * G::STRIDE, stage(s).slab,
                      (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP)));
             bulk_commit();
         }
@@ -393,10 +421,12 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
     const int L = p.L, NR = p.crb * 16;
     const int nkb16 = (L + 15) >> 4;
 
-    BwdStage<T, TP, TG, NKB> st[NSTAGE];
     const size_t stage_bytes = (BwdStage<T, TP, TG, NKB>::bytes(NR) + 127) & ~size_t(127);
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) st[s].carve(smem_raw + s * stage_bytes, NR);
+    auto stage = [&](int s) {
+        BwdStage<T, TP, TG, NKB> x;
+        x.carve(smem_raw + (size_t)s * stage_bytes, NR);
+        return x;
+    };
     unsigned char* extra = smem_raw + NSTAGE * stage_bytes;
     T* Apt = reinterpret_cast<T*>(extra);                            // [NR][STRIDE] dropped probabilities
     T* dSt_own = Apt + NR * G::STRIDE;                               // [NR][STRIDE] (only when !ALIAS_DS)
@@ -416,24 +446,25 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
     }
     __syncthreads();
 
-    const long long ntiles = (long long)p.B * p.H;
-    const long long t0 = ntiles * blockIdx.x / gridDim.x, t1 = ntiles * (blockIdx.x + 1) / gridDim.x;
-    const long long w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
+    const int ntiles = p.B * p.H;
+    const int t0 = (int)((long long)ntiles * blockIdx.x / gridDim.x), t1 = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+    const int w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
+    const FastDiv div_h((uint32_t)p.H), div_c((uint32_t)p.nchunks);
     const size_t tile_elems = (size_t)L * G::STRIDE;
     const bool has_dpo = p.dpout != nullptr;
 
-    auto prefetch = [&](long long w, int s) {
-        const long long tile = w / p.nchunks;
-        const int chunk = (int)(w - tile * p.nchunks);
-        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+    auto prefetch = [&](int w, int s) {
+        const int tile = (int)div_c.div((uint32_t)w);
+        const int chunk = w - tile * p.nchunks;
+        const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
         if (tid == 0) {
             const uint32_t bs = (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP));
             const uint32_t bg = has_dpo ? (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TG)) : 0u;
             mbar_arrive_expect_tx(&full_bar[s], bs + bg);
-            bulk_g2s(st[s].sS, static_cast<const TP*>(p.s) + tile * tile_elems + (size_t)row0 * G::STRIDE, bs, &full_bar[s]);
+            bulk_g2s(stage(s).sS, static_cast<const TP*>(p.s) + (size_t)tile * tile_elems + (size_t)row0 * G::STRIDE, bs, &full_bar[s]);
             if (has_dpo)
-                bulk_g2s(st[s].sG, static_cast<const TG*>(p.dpout) + tile * tile_elems + (size_t)row0 * G::STRIDE, bg,
+                bulk_g2s(stage(s).sG, static_cast<const TG*>(p.dpout) + (size_t)tile * tile_elems + (size_t)row0 * G::STRIDE, bg,
                          &full_bar[s]);
         }
         const size_t tok = (size_t)b * L;
@@ -443,13 +474,13 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
         const T* og = static_cast<const T*>(p.o) + tok * p.lddo + h * HD;
         const T* dog = static_cast<const T*>(p.d_o) + tok * p.lddo + h * HD;
         for (int i = tid; i < 2 * L + 3 * nrows; i += nthr) {
-            if (i < L) cp_head_row(st[s].K + i * HD, kg + (size_t)i * p.ldqkv);
-            else if (i < 2 * L) cp_head_row(st[s].V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
+            if (i < L) cp_head_row(stage(s).K + i * HD, kg + (size_t)i * p.ldqkv);
+            else if (i < 2 * L) cp_head_row(stage(s).V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
             else {
                 const int j = i - 2 * L, which = j / nrows, r = j - which * nrows;
-                if (which == 0) cp_head_row(st[s].Q + r * HD, qg + (size_t)(row0 + r) * p.ldqkv);
-                else if (which == 1) cp_head_row(st[s].dO + r * HD, dog + (size_t)(row0 + r) * p.lddo);
-                else cp_head_row(st[s].O + r * HD, og + (size_t)(row0 + r) * p.lddo);
+                if (which == 0) cp_head_row(stage(s).Q + r * HD, qg + (size_t)(row0 + r) * p.ldqkv);
+                else if (which == 1) cp_head_row(stage(s).dO + r * HD, dog + (size_t)(row0 + r) * p.lddo);
+                else cp_head_row(stage(s).O + r * HD, og + (size_t)(row0 + r) * p.lddo);
             }
         }
         cp_async_commit();
@@ -460,11 +491,11 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
 
     if (w0 < w1) prefetch(w0, 0);
     int it = 0;
-    for (long long w = w0; w < w1; ++w, ++it) {
+    for (int w = w0; w < w1; ++w, ++it) {
         const int s = it & 1;
-        const long long tile = w / p.nchunks;
-        const int chunk = (int)(w - tile * p.nchunks);
-        const int b = (int)(tile / p.H), h = (int)(tile - (long long)b * p.H);
+        const int tile = (int)div_c.div((uint32_t)w);
+        const int chunk = w - tile * p.nchunks;
+        const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
         const int nrb_chunk = (nrows + 15) >> 4;
 
@@ -486,21 +517,21 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             }
         }
 
-        const T* Ks = st[s].K;
-        const T* Vs = st[s].V;
-        const T* Qs = st[s].Q;
-        const T* dOs = st[s].dO;
-        const T* Os = st[s].O;
-        T* dSt = ALIAS_DS ? reinterpret_cast<T*>(st[s].sG) : dSt_own;
+        const T* Ks = stage(s).K;
+        const T* Vs = stage(s).V;
+        const T* Qs = stage(s).Q;
+        const T* dOs = stage(s).dO;
+        const T* Os = stage(s).O;
+        T* dSt = ALIAS_DS ? reinterpret_cast<T*>(stage(s).sG) : dSt_own;
 
         // ================= phase 1: per 16-row block: A, dA, dS, dQ
         if (warp < nrb_chunk) {
             const int la = warp * 16 + g, lb = la + 8;
             const int ra = row0 + la, rbb = row0 + lb;
-            const TP* srow_a = st[s].sS + la * G::STRIDE;
-            const TP* srow_b = st[s].sS + lb * G::STRIDE;
-            TG* grow_a = st[s].sG + la * G::STRIDE;
-            TG* grow_b = st[s].sG + lb * G::STRIDE;
+            const TP* srow_a = stage(s).sS + la * G::STRIDE;
+            const TP* srow_b = stage(s).sS + lb * G::STRIDE;
+            TG* grow_a = stage(s).sG + la * G::STRIDE;
+            TG* grow_b = stage(s).sG + lb * G::STRIDE;
             T* ap_a = Apt + la * G::STRIDE;
             T* ap_b = Apt + lb * G::STRIDE;
             T* ds_a = dSt + la * G::STRIDE;
@@ -577,6 +608,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
             const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
             const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
+            uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 const int col = kb * 8 + 2 * q4;
@@ -597,7 +629,8 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 }
                 float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
                 if (do_drop) {
-                    const uint32_t ba = rng_pair_bits(rkey, ra, col), bb = rng_pair_bits(rkey, rbb, col);
+                    if ((kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
+                    const uint32_t ba = (kb & 1) ? qwa.y : qwa.x, bb = (kb & 1) ? qwb.y : qwb.x;
                     k0 = rng_keep(ba, 0, p.thresh16) ? p.keep_scale : 0.f;
                     k1 = rng_keep(ba, 1, p.thresh16) ? p.keep_scale : 0.f;
                     k2 = rng_keep(bb, 0, p.thresh16) ? p.keep_scale : 0.f;
@@ -698,7 +731,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            bulk_s2g(static_cast<TG*>(p.dpin) + tile * tile_elems + (size_t)row0 * G::STRIDE, st[s].sG,
+            bulk_s2g(static_cast<TG*>(p.dpin) + (size_t)tile * tile_elems + (size_t)row0 * G::STRIDE, stage(s).sG,
                      (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TG)));
             bulk_commit();
         }
