@@ -11,7 +11,8 @@
 //                                                       shared-memory tile read transposed)  phase 2 only
 //               issued software-pipelined: MMA1(t+1) goes out before MMA2(t), so the tensor pipe
 //               computes the next similarity tile while the epilogue warps turn tile t into H
-//   warps 2..5  epilogue: thread r owns anchor row r (TMEM lane r): tcgen05.ld the S row, apply the
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant, half of the tile columns each): thread owns anchor
+//               row r (TMEM lane r): tcgen05.ld the S row segment, apply the
 //               per-pair functor of sim_common.cuh (masks / exp / weights),
 //                 phase 1: accumulate the row statistics in registers
 //                 phase 2: write H (bf16, swizzled K-major) to shared memory for MMA2
@@ -37,8 +38,7 @@ constexpr int BM = 128;
 constexpr int CHUNK_K = 64;                 // bf16 elements per 128-byte swizzled row
 constexpr int A_CHUNK_BYTES = BM * 128;     // one K-chunk of the A stripe
 constexpr int H_ATOM_BYTES = BM * 128;      // one [128][64] bf16 swizzle atom of H
-constexpr int NUM_THREADS = 192;
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_DA_COL = 256;
 
@@ -104,13 +104,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout; version 1)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout << 61;          // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
     return d;
 }
 // instruction descriptor: bf16 x bf16 -> f32, M = 128, N = n; b_mn = 1: B operand is MN-major
@@ -125,23 +125,126 @@ struct TcParams {
     int M, D, nkc, nstage, tiles_per_split, use_atomics;
 };
 
+constexpr int NUM_EPI_WARPS = 8;            // two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;
+constexpr int META_F = 6;                   // staged per-column floats: y, yhat, wrow, wcol, rs0, rs1
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+// H (the bf16 gradient-coefficient tile, A operand of MMA2): [128 rows][BN] K-major.  BN >= 64: 128-byte rows,
+// 128B swizzle, one 16 KB atom per 64 columns.  BN == 32: 64-byte rows, 64B swizzle (8 KB).
+__host__ __device__ constexpr uint32_t h_buf_bytes(int bn) { return bn == 32 ? 128u * 64u : (uint32_t)((bn + 63) / 64) * H_ATOM_BYTES; }
+
 struct SmemLayout {
-    uint32_t a_off, b_off, h_off, bar_off, total;
-    uint32_t b_stage_bytes;
+    uint32_t a_off, b_off, h_off, meta_off, bar_off, total;
+    uint32_t b_stage_bytes, meta_buf_bytes;
 };
 __host__ __device__ inline SmemLayout smem_layout(int nkc, int bn, int nstage, int phase) {
     SmemLayout s;
     s.a_off = 0;
     s.b_off = nkc * A_CHUNK_BYTES;
-    s.b_stage_bytes = nkc * bn * 128;
+    s.b_stage_bytes = (phase == 1 ? 1 : nkc) * bn * 128;      // phase 1 streams single 64-wide K chunks, phase 2 whole key tiles
     s.h_off = s.b_off + nstage * s.b_stage_bytes;
-    const uint32_t h_bytes = phase == 2 ? 2u * ((bn + 63) / 64) * H_ATOM_BYTES : 0u;
-    s.bar_off = s.h_off + h_bytes;
+    const uint32_t h_bytes = phase == 2 ? 2u * h_buf_bytes(bn) : 0u;
+    s.meta_off = s.h_off + h_bytes;
+    s.meta_buf_bytes = bn * (META_F * 4 + 8);
+    s.bar_off = s.meta_off + 2 * s.meta_buf_bytes;
     s.total = s.bar_off + 256;
     return s;
 }
 
-template <int PHASE, int BN>
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// per-row constants of an epilogue thread (registers) and per-column constants of a tile (shared memory)
+struct RowCtx {
+    float y, yh, wr, wc, ri0, ri1;
+    long long key;
+    int gi;
+};
+struct ColMeta {
+    const float *y, *yh, *wr, *wc, *rs0, *rs1;
+    const long long* key;
+};
+struct TcConst {
+    float inv_t, k2, k2t, w_thr, e_push;    // k2 = log2(e)/t, k2t = k2 (exponent shift of InfoNCE: exp(z - 1/t))
+};
+
+// ---- phase 1, one similarity value (column c of the tile, global key j)
+template <int MODE>
+__device__ __forceinline__ void p1_elem(const TcConst& k, const RowCtx& r, const ColMeta& m, RowAcc& acc, float dot, int j, int c) {
+    if (MODE == SIM_INFONCE) {
+        acc.v[0] += ex2f(fmaf(dot, k.k2, -k.k2t));
+        if (r.gi == j) acc.v[1] += dot * k.inv_t;
+    } else {
+        bool pos, neg;
+        float w = r.wr * m.wc[c];
+        if (MODE == SIM_REGRESS) {
+            const float l = fabsf(__fsub_rn(r.y, m.y[c])), pd = fabsf(__fsub_rn(r.yh, m.yh[c]));
+            const bool close = l <= k.w_thr;
+            pos = close && (r.gi != j);
+            neg = (!close) && (pd <= k.w_thr);
+            w = l * w * k.e_push;
+        } else {
+            const bool same = r.key == m.key[c];
+            pos = same && (r.gi != j);
+            neg = !same;
+        }
+        const float e = ex2f(dot * k.k2);
+        if (pos) {
+            acc.v[0] += e;
+            acc.v[2] += 1.f;
+            acc.v[4] = fmaf(dot, k.inv_t, acc.v[4]);
+        } else if (neg) {
+            acc.v[1] = fmaf(w, e, acc.v[1]);
+            acc.v[3] += 1.f;
+        }
+    }
+}
+// ---- phase 2, gradient coefficient H_ij
+template <int MODE>
+__device__ __forceinline__ float p2_elem(const TcConst& k, const RowCtx& r, const ColMeta& m, float dot, int j, int c) {
+    if (MODE == SIM_INFONCE) {       // ri0 / rs0 hold lse * log2(e)
+        float h = ex2f(fmaf(dot, k.k2, -r.ri0)) + ex2f(fmaf(dot, k.k2, -m.rs0[c]));
+        if (r.gi == j) h -= 2.f;
+        return h;
+    }
+    bool pos, neg;
+    float wij = r.wr * m.wc[c], wji = m.wr[c] * r.wc;
+    if (MODE == SIM_REGRESS) {
+        const float l = fabsf(__fsub_rn(r.y, m.y[c])), pd = fabsf(__fsub_rn(r.yh, m.yh[c]));
+        const bool close = l <= k.w_thr;
+        pos = close && (r.gi != j);
+        neg = (!close) && (pd <= k.w_thr);
+        wij = l * wij * k.e_push;
+        wji = l * wji * k.e_push;
+    } else {
+        const bool same = r.key == m.key[c];
+        pos = same && (r.gi != j);
+        neg = !same;
+    }
+    const float e = ex2f(dot * k.k2);
+    const float cj = m.rs0[c], aj = m.rs1[c];
+    float h = 0.f;
+    if (pos) h = fmaf(r.ri1 + aj, e, -(r.ri0 + cj));
+    else if (neg) h = fmaf(r.ri1, wij, aj * wji) * e;
+    return h;
+}
+
+template <int PHASE, int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -154,6 +257,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     unsigned char* sA = smem + lay.a_off;
     unsigned char* sB = smem + lay.b_off;
     unsigned char* sH = smem + lay.h_off;
+    unsigned char* sMeta = smem + lay.meta_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
     uint64_t* a_full = bars + 0;
     uint64_t* d_full = bars + 1;
@@ -162,8 +266,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint64_t* h_full = bars + 6;      // [2]
     uint64_t* h_empty = bars + 8;     // [2]
     uint64_t* full = bars + 10;       // [MAX_STAGES]
-    uint64_t* empty = bars + 16;      // [MAX_STAGES]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* empty = bars + 18;      // [MAX_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int i0 = blockIdx.x * BM;
     const int ntiles_all = (aux.N + BN - 1) / BN;
@@ -177,8 +281,8 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_init(d_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_empty[i], 128);
-            mbar_init(&h_full[i], 128);
+            mbar_init(&s_empty[i], NUM_EPI_THREADS);
+            mbar_init(&h_full[i], NUM_EPI_THREADS);
             mbar_init(&h_empty[i], 1);
         }
         for (int i = 0; i < MAX_STAGES; ++i) {
@@ -202,13 +306,27 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (lane == 0) {
             mbar_arrive_expect_tx(a_full, (uint32_t)(nkc * A_CHUNK_BYTES));
             for (int kc = 0; kc < nkc; ++kc) tma_load_2d(sA + kc * A_CHUNK_BYTES, &tmA, kc * CHUNK_K, i0, a_full);
-            for (int t = 0; t < T; ++t) {
-                const int st = t % nstage, use = t / nstage;
-                if (use > 0) mbar_wait_g(&empty[st], (use - 1) & 1);
-                mbar_arrive_expect_tx(&full[st], lay.b_stage_bytes);
-                unsigned char* dst = sB + (size_t)st * lay.b_stage_bytes;
-                const int j0 = (t_begin + t) * BN;
-                for (int kc = 0; kc < nkc; ++kc) tma_load_2d(dst + kc * BN * 128, &tmB, kc * CHUNK_K, j0, &full[st]);
+            if (PHASE == 1) {
+                // K-chunk ring: every stage holds one (BN keys x 64) chunk; many small loads in flight
+                int idx = 0;
+                for (int t = 0; t < T; ++t) {
+                    const int j0 = (t_begin + t) * BN;
+                    for (int kc = 0; kc < nkc; ++kc, ++idx) {
+                        const int st = idx % nstage, use = idx / nstage;
+                        if (use > 0) mbar_wait_g(&empty[st], (use - 1) & 1);
+                        mbar_arrive_expect_tx(&full[st], lay.b_stage_bytes);
+                        tma_load_2d(sB + (size_t)st * lay.b_stage_bytes, &tmB, kc * CHUNK_K, j0, &full[st]);
+                    }
+                }
+            } else {
+                for (int t = 0; t < T; ++t) {
+                    const int st = t % nstage, use = t / nstage;
+                    if (use > 0) mbar_wait_g(&empty[st], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&full[st], lay.b_stage_bytes);
+                    unsigned char* dst = sB + (size_t)st * lay.b_stage_bytes;
+                    const int j0 = (t_begin + t) * BN;
+                    for (int kc = 0; kc < nkc; ++kc) tma_load_2d(dst + kc * BN * 128, &tmB, kc * CHUNK_K, j0, &full[st]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -222,10 +340,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 mbar_wait_g(&h_full[hb], (u >> 1) & 1);
                 tc_fence_after();
                 const uint32_t bst = b_addr + st * lay.b_stage_bytes + (dcol0 / CHUNK_K) * BN * 128;
-                const uint32_t hst = h_addr + hb * ((BN + 63) / 64) * H_ATOM_BYTES;
+                const uint32_t hst = h_addr + hb * h_buf_bytes(BN);
 #pragma unroll
                 for (int ks = 0; ks < BN / 16; ++ks) {
-                    const uint64_t ad = smem_desc(hst + (ks >> 2) * H_ATOM_BYTES + (ks & 3) * 32, 16, 1024);
+                    const uint64_t ad = BN == 32 ? smem_desc(hst + ks * 32, 16, 512, 4)
+                                                 : smem_desc(hst + (ks >> 2) * H_ATOM_BYTES + (ks & 3) * 32, 16, 1024);
                     const uint64_t bd = smem_desc(bst + ks * 16 * 128, BN * 128, 1024);
                     tc_mma(tmem_base + TMEM_DA_COL, ad, bd, idesc_d, (u > 0 || ks > 0) ? 1u : 0u);
                 }
@@ -233,23 +352,41 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 tc_commit(&empty[st]);
             };
             mbar_wait_g(a_full, 0);
+            int idx = 0;
             for (int t = 0; t < T; ++t) {
-                const int buf = t & 1, st = t % nstage;
+                const int buf = t & 1;
                 if (t >= 2) mbar_wait_g(&s_empty[buf], ((t >> 1) - 1) & 1);
-                mbar_wait_g(&full[st], (t / nstage) & 1);
-                tc_fence_after();
-                const uint32_t bst = b_addr + st * lay.b_stage_bytes;
-                for (int kc = 0; kc < nkc; ++kc) {
+                if (PHASE == 1) {
+                    for (int kc = 0; kc < nkc; ++kc, ++idx) {
+                        const int st = idx % nstage;
+                        mbar_wait_g(&full[st], (idx / nstage) & 1);
+                        tc_fence_after();
+                        const uint32_t bst = b_addr + st * lay.b_stage_bytes;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t ad = smem_desc(a_addr + kc * A_CHUNK_BYTES + k4 * 32, 16, 1024);
-                        const uint64_t bd = smem_desc(bst + kc * BN * 128 + k4 * 32, 16, 1024);
-                        tc_mma(tmem_base + buf * BN, ad, bd, idesc_s, (kc > 0 || k4 > 0) ? 1u : 0u);
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint64_t ad = smem_desc(a_addr + kc * A_CHUNK_BYTES + k4 * 32, 16, 1024);
+                            const uint64_t bd = smem_desc(bst + k4 * 32, 16, 1024);
+                            tc_mma(tmem_base + buf * BN, ad, bd, idesc_s, (kc > 0 || k4 > 0) ? 1u : 0u);
+                        }
+                        tc_commit(&empty[st]);
                     }
+                    tc_commit(&s_full[buf]);
+                } else {
+                    const int st = t % nstage;
+                    mbar_wait_g(&full[st], (t / nstage) & 1);
+                    tc_fence_after();
+                    const uint32_t bst = b_addr + st * lay.b_stage_bytes;
+                    for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            const uint64_t ad = smem_desc(a_addr + kc * A_CHUNK_BYTES + k4 * 32, 16, 1024);
+                            const uint64_t bd = smem_desc(bst + kc * BN * 128 + k4 * 32, 16, 1024);
+                            tc_mma(tmem_base + buf * BN, ad, bd, idesc_s, (kc > 0 || k4 > 0) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&s_full[buf]);
+                    if (t > 0) mma2(t - 1);
                 }
-                tc_commit(&s_full[buf]);
-                if (PHASE == 1) tc_commit(&empty[st]);
-                if (PHASE == 2 && t > 0) mma2(t - 1);
             }
             if (PHASE == 2) {
                 mma2(T - 1);
@@ -257,41 +394,99 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
         }
     } else {
-        // ================================================= epilogue warps (TMEM lane quadrant = warp % 4)
-        const int quad = warp & 3;
+        // ================================================= epilogue warps
+        // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the tile's columns
+        constexpr int HC = BN / 2;                       // columns per epilogue thread and tile
+        const int ew = warp - 2;
+        const int quad = warp & 3, half = ew >> 2;
+        const int et = ew * 32 + lane;                   // 0..255
         const int r = quad * 32 + lane;                  // anchor row of this thread inside the stripe
         const bool row_ok = (i0 + r) < p.M;
-        const int gi = aux.row_offset + i0 + r;          // global anchor index
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        TcConst kc;
+        kc.inv_t = aux.inv_t;
+        kc.k2 = aux.inv_t * LOG2E_F;
+        kc.k2t = kc.k2;
+        kc.w_thr = aux.w_thr;
+        kc.e_push = aux.e_push;
+        RowCtx rc;
+        rc.gi = aux.row_offset + i0 + r;
+        rc.y = rc.yh = 0.f;
+        rc.wr = rc.wc = 1.f;
+        rc.ri0 = rc.ri1 = 0.f;
+        rc.key = 0;
+        if (row_ok) {
+            const int gi = rc.gi;
+            if (MODE == SIM_REGRESS) { rc.y = aux.y[gi]; rc.yh = aux.yhat[gi]; }
+            if (MODE == SIM_SINGLE) rc.key = aux.key[gi];
+            if (MODE != SIM_INFONCE) {
+                if (aux.wrow) rc.wr = aux.wrow[gi];
+                if (aux.wcol) rc.wc = aux.wcol[gi];
+            }
+            if (PHASE == 2) {
+                if (MODE == SIM_INFONCE) rc.ri0 = aux.rs_row[i0 + r] * LOG2E_F;
+                else { rc.ri0 = aux.rs_row[2 * (i0 + r)]; rc.ri1 = aux.rs_row[2 * (i0 + r) + 1]; }
+            }
+        }
         RowAcc racc;
         racc.clear();
-        float ri0 = 0.f, ri1 = 0.f;
+        float gri0 = 0.f, gri1 = 0.f;                    // un-scaled row statistics for the generic (tail / multi) path
         if (PHASE == 2 && row_ok) {
-            if (aux.mode == SIM_INFONCE) ri0 = aux.rs_row[i0 + r];
-            else { ri0 = aux.rs_row[2 * (i0 + r)]; ri1 = aux.rs_row[2 * (i0 + r) + 1]; }
+            if (MODE == SIM_INFONCE) gri0 = aux.rs_row[i0 + r];
+            else { gri0 = rc.ri0; gri1 = rc.ri1; }
         }
         for (int t = 0; t < T; ++t) {
             const int buf = t & 1;
             const int j0 = (t_begin + t) * BN;
+            const bool fast = (MODE != SIM_MULTI) && (j0 + BN <= aux.N);
+            // ---- stage the per-column constants of this tile (overlaps the MMA of the tile)
+            ColMeta cm;
+            {
+                float* mf = reinterpret_cast<float*>(sMeta + buf * lay.meta_buf_bytes);
+                long long* mk = reinterpret_cast<long long*>(mf + META_F * BN);
+                cm.y = mf; cm.yh = mf + BN; cm.wr = mf + 2 * BN; cm.wc = mf + 3 * BN; cm.rs0 = mf + 4 * BN; cm.rs1 = mf + 5 * BN;
+                cm.key = mk;
+                if (fast && et < BN) {
+                    const int j = j0 + et;
+                    if (MODE == SIM_REGRESS) { mf[et] = aux.y[j]; mf[BN + et] = aux.yhat[j]; }
+                    if (MODE == SIM_SINGLE) mk[et] = aux.key[j];
+                    if (MODE != SIM_INFONCE) {
+                        mf[2 * BN + et] = aux.wrow ? aux.wrow[j] : 1.f;
+                        mf[3 * BN + et] = aux.wcol ? aux.wcol[j] : 1.f;
+                    }
+                    if (PHASE == 2) {
+                        if (MODE == SIM_INFONCE) mf[4 * BN + et] = aux.rs_col[j] * LOG2E_F;
+                        else { mf[4 * BN + et] = aux.rs_col[2 * j]; mf[5 * BN + et] = aux.rs_col[2 * j + 1]; }
+                    }
+                }
+                epi_bar();
+            }
             mbar_wait_g(&s_full[buf], (t >> 1) & 1);
             tc_fence_after();
             if (PHASE == 2 && t >= 2) mbar_wait_g(&h_empty[buf], ((t >> 1) - 1) & 1);
-            unsigned char* hrow = sH + buf * ((BN + 63) / 64) * H_ATOM_BYTES + r * 128;
+            unsigned char* hrow = sH + buf * h_buf_bytes(BN) + r * (BN == 32 ? 64 : 128);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
                 uint32_t v[32];
-                tc_ld32(lane_addr + buf * BN + c0, v);
+                constexpr int NC = HC < 32 ? HC : 32;    // columns per TMEM load
+                if (NC == 16) tc_ld16(lane_addr + buf * BN + c0, v);
+                else tc_ld32(lane_addr + buf * BN + c0, v);
                 if (PHASE == 1) {
                     if (row_ok) {
+                        if (fast) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const int j = j0 + c0 + c;
-                            if (j < aux.N) sim_stats_accum(aux, racc, gi, j, __uint_as_float(v[c]));
+                            for (int c = 0; c < NC; ++c) p1_elem<MODE>(kc, rc, cm, racc, __uint_as_float(v[c]), j0 + c0 + c, c0 + c);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                const int j = j0 + c0 + c;
+                                if (j < aux.N) sim_stats_accum(aux, racc, rc.gi, j, __uint_as_float(v[c]));
+                            }
                         }
                     }
                 } else {
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
+                    for (int g8 = 0; g8 < NC / 8; ++g8) {
                         uint32_t w[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -300,12 +495,18 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                             for (int u = 0; u < 2; ++u) {
                                 const int c = g8 * 8 + e * 2 + u;
                                 const int j = j0 + c0 + c;
-                                h2[u] = (row_ok && j < aux.N) ? sim_grad_coeff(aux, gi, j, __uint_as_float(v[c]), ri0, ri1) : 0.f;
+                                float h = 0.f;
+                                if (row_ok) {
+                                    if (fast) h = p2_elem<MODE>(kc, rc, cm, __uint_as_float(v[c]), j, c0 + c);
+                                    else if (j < aux.N) h = sim_grad_coeff(aux, rc.gi, j, __uint_as_float(v[c]), gri0, gri1);
+                                }
+                                h2[u] = h;
                             }
                             w[e] = pack_bf16(h2[0], h2[1]);
                         }
                         const int col8 = (c0 >> 3) + g8;                   // 16-byte chunk index along K
-                        unsigned char* dst = hrow + (col8 >> 3) * H_ATOM_BYTES + (((col8 & 7) ^ (r & 7)) << 4);
+                        unsigned char* dst = BN == 32 ? hrow + ((col8 ^ ((r >> 1) & 3)) << 4)
+                                                      : hrow + (col8 >> 3) * H_ATOM_BYTES + (((col8 & 7) ^ (r & 7)) << 4);
                         *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
@@ -321,15 +522,14 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (row_ok) {
                 float* dst = p.out + (long long)(i0 + r) * SIM_NSTAT;
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    if (p.use_atomics) atomicAdd(dst + k, racc.v[k]);
-                    else dst[k] = racc.v[k];
-                }
+                for (int k = 0; k < 5; ++k)
+                    if (racc.v[k] != 0.f) atomicAdd(dst + k, racc.v[k]);      // two threads per row (+ key splits)
             }
         } else {
             mbar_wait_g(d_full, 0);
             tc_fence_after();
-            for (int c0 = 0; c0 < ND; c0 += 32) {
+            const int ndh = ND / 2;                      // ND is a multiple of 64
+            for (int c0 = half * ndh; c0 < (half + 1) * ndh; c0 += 32) {
                 uint32_t v[32];
                 tc_ld32(lane_addr + TMEM_DA_COL + c0, v);
                 if (row_ok) {
@@ -411,12 +611,22 @@ int launch_bn(const void* A, const void* B, int M, int N, int Dp, int D, const S
     p.aux = aux; p.out = out; p.ldout = ldout; p.M = M; p.D = D; p.nkc = nkc; p.nstage = nstage;
     p.tiles_per_split = per; p.use_atomics = jsplit > 1;
     const size_t outbytes = PHASE == 1 ? (size_t)M * SIM_NSTAT * sizeof(float) : (size_t)M * ldout * sizeof(float);
-    if (jsplit > 1 || PHASE == 1) MMDTI_CUDA_OK(cudaMemsetAsync(out, 0, outbytes, st));
-    auto kern = sim_tc_kernel<PHASE, BN>;
+    if (jsplit > 1 || PHASE == 1) MMDTI_CUDA_OK(cudaMemsetAsync(out, 0, outbytes, st));      // phase 1 always accumulates with atomics
     const int smem_bytes = (int)lay.total + 1024;
-    MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     dim3 grid(stripes, jsplit, halves);
-    kern<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);
+#define SIM_GO(MODE)                                                                                                    \
+    do {                                                                                                                \
+        auto kern = sim_tc_kernel<PHASE, BN, MODE>;                                                                     \
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));             \
+        kern<<<grid, NUM_THREADS, smem_bytes, st>>>(tmA, tmB, p);                                                       \
+    } while (0)
+    switch (aux.mode) {
+        case SIM_INFONCE: SIM_GO(SIM_INFONCE); break;
+        case SIM_REGRESS: SIM_GO(SIM_REGRESS); break;
+        case SIM_SINGLE: SIM_GO(SIM_SINGLE); break;
+        default: SIM_GO(SIM_MULTI); break;
+    }
+#undef SIM_GO
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }
@@ -425,7 +635,7 @@ template <int PHASE>
 int launch(const void* A, const void* B, int M, int N, int Dp, int D, const SimAux& aux, float* out, long long ldout, cudaStream_t st) {
     MMDTI_REQUIRE(Dp >= 64 && Dp <= 512 && Dp % 64 == 0, "sim_tc: Dp must be a multiple of 64 in [64, 512] (got %d)", Dp);
     MMDTI_REQUIRE(mmdti_aligned(A, 16) && mmdti_aligned(B, 16), "sim_tc: operands must be 16-byte aligned");
-    if (Dp <= 128) return launch_bn<PHASE, 128>(A, B, M, N, Dp, D, aux, out, ldout, st);
+    if (PHASE == 1 || Dp <= 128) return launch_bn<PHASE, 128>(A, B, M, N, Dp, D, aux, out, ldout, st);
     if (Dp <= 256) return launch_bn<PHASE, 64>(A, B, M, N, Dp, D, aux, out, ldout, st);
     return launch_bn<PHASE, 32>(A, B, M, N, Dp, D, aux, out, ldout, st);
 }
