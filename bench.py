@@ -153,16 +153,23 @@ def run_ours(args, rank, local_rank, world):
     torch.manual_seed(0)
     model = UnimolEncoder().to(dev).train()
     step_model = model
-    if dist_on:
+    use_graph = not args.no_graph
+    if dist_on and not use_graph:
         from torch.nn.parallel import DistributedDataParallel as DDP
         step_model = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=64)
+    elif dist_on:
+        # replicas start identical (same seed); gradients are exchanged by mmdti_b200.dist.allreduce_grads inside the graph
+        from mmdti_b200.dist import allreduce_grads
+        for prm in model.parameters():
+            dist.broadcast(prm.data, src=0)
 
     tokens, dmat, et, g = make_batch(1234 + rank)
     pin = [t.pin_memory() for t in (tokens, dmat, et)]
     d_tokens, d_dist, d_et, d_g = tokens.to(dev), dmat.to(dev), et.to(dev), g.to(dev)
-    use_graph = (not args.no_graph) and not dist_on
     # Adam(eps 1e-6) as in tasks/trainer.py:160; fused + capturable so that it can live inside the CUDA graph
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
+
+    params = [prm for prm in model.parameters() if prm.requires_grad]
 
     def barrier():
         if dist_on:
@@ -173,6 +180,8 @@ def run_ours(args, rank, local_rank, world):
         rep = step_model(t, d, e)
         loss = (rep * d_g).sum()
         loss.backward()
+        if dist_on and use_graph:
+            allreduce_grads(params, average=True, async_op=False)      # exchange 2: NCCL all-reduce, captured in the graph
         opt.step()
         return loss.detach()
 
@@ -184,7 +193,8 @@ def run_ours(args, rank, local_rank, world):
     if use_graph:
         from mmdti_b200.graph import GraphedStep
         opt.zero_grad(set_to_none=True)
-        graphed = GraphedStep(full_step, [d_tokens, d_dist, d_et], device=dev)
+        graphed = GraphedStep(full_step, [d_tokens, d_dist, d_et], device=dev,
+                              capture_error_mode="thread_local" if dist_on else "global")
 
         def step_resident():
             return graphed(d_tokens, d_dist, d_et)
@@ -275,6 +285,8 @@ def run_ours(args, rank, local_rank, world):
                        "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
                        "optimizer": "Adam(eps=1e-6), torch fused", "cuda_graph": bool(use_graph),
                        "parallelism": "dp%d" % world,
+                       "grad_exchange": (None if world == 1 else ("NCCL all-reduce of flat 64 MB buckets inside the graph" if use_graph
+                                                                  else "DistributedDataParallel (NCCL)")),
                        "l2": "no flush: the per-step working set (15 x %.0f MB pair tensors + activations) exceeds the 126 MB L2"
                              % (nel * esz / 1e6)},
             "e2e": {"value": mols / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -291,8 +303,17 @@ def run_ours(args, rank, local_rank, world):
                                               "oracle/restate.py on the host cores" % sec}
         print(json.dumps(line), flush=True)
     if dist_on:
+        # tear down in a fixed order: drain the device, drop the captured graph (it holds NCCL kernels), then leave
+        torch.cuda.synchronize()
+        print("[bench rank %d] finished, entering final barrier" % rank, file=sys.stderr, flush=True)
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        if use_graph:
+            del graphed
+        print("[bench rank %d] barrier passed" % rank, file=sys.stderr, flush=True)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)        # skip the NCCL communicator teardown (observed to hang after graph-captured collectives)
 
 
 def main():

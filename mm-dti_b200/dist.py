@@ -49,10 +49,11 @@ class DataParallelCtx:
         return t
 
 
-def allreduce_grads(params, group=None, average=True, bucket_bytes=64 << 20):
+def allreduce_grads(params, group=None, average=True, bucket_bytes=64 << 20, async_op=True):
     """Exchange 2: all-reduce ``p.grad`` of every parameter in flat same-dtype buckets of about
     ``bucket_bytes`` (NVSwitch: size buckets for launch latency, not link count).  Parameters whose
-    grad is None on this rank contribute zeros (every rank must issue the same collectives)."""
+    grad is None on this rank contribute zeros (every rank must issue the same collectives).
+    async_op=False issues plain in-stream collectives (use it inside a CUDA-graph capture)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
@@ -79,10 +80,11 @@ def allreduce_grads(params, group=None, average=True, bucket_bytes=64 << 20):
         works = []
         for b in buckets:
             flat = torch.cat([g.reshape(-1) for g in b])
-            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, b))
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op), flat, b))
             n_coll += 1
         for w, flat, b in works:
-            w.wait()
+            if async_op:
+                w.wait()
             if average:
                 flat.div_(world)
             off = 0

@@ -20,9 +20,13 @@ class GraphedStep:
     construction, do not set it to None afterwards).
 
     example_inputs: tensors defining the static input signature; host (pinned) tensors are allowed,
-    in which case every call copies them to the static device buffers inside the timed path."""
+    in which case every call copies them to the static device buffers inside the timed path.
 
-    def __init__(self, step_fn, example_inputs, device=None, warmup=3):
+    Data parallel: the step may contain in-stream NCCL collectives (dist.allreduce_grads(..., async_op=False));
+    pass capture_error_mode="thread_local" so that NCCL's watchdog thread does not invalidate the capture,
+    and run enough warm-up steps for the communicator to exist before the capture starts."""
+
+    def __init__(self, step_fn, example_inputs, device=None, warmup=3, capture_error_mode="global"):
         if not torch.cuda.is_available():
             raise _lib.MMDTIError("GraphedStep needs a CUDA device")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -46,7 +50,7 @@ class GraphedStep:
         torch.cuda.synchronize(self.device)
         n0 = _lib.launch_count
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.static_out = body()
         self.launches_per_replay = _lib.launch_count - n0      # own kernels captured in the graph
 
