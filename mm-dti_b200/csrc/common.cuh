@@ -54,13 +54,14 @@ template <> __device__ __forceinline__ float from_f<float>(float x) { return x; 
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float x) { return __float2bfloat16_rn(x); }
 template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
 
+// one F2FP (cvt.rn.bf16x2.f32) / one shift + one mask: the cuda_bf16.hpp helpers cost 3 instructions per pair
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-    return __bfloat1622float2(v);
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);

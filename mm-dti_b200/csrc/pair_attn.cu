@@ -24,7 +24,8 @@
 namespace {
 
 constexpr int HD = MMDTI_HEAD_DIM;  // 8
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 2;      // backward ring
+constexpr int NSTAGE_F = 3;    // forward ring: the bulk store of item w-1 may still be reading its stage while w+1 loads
 constexpr float LOG2E = 1.4426950408889634f;
 
 template <int NKB> struct Geo {
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
     using G = Geo<NKB>;
     constexpr bool F32 = std::is_same<T, float>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[NSTAGE];
+    __shared__ __align__(8) uint64_t full_bar[NSTAGE_F];
 
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, q4 = lane & 3;
@@ -140,10 +141,10 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
 
     // one-time init: zero the whole ring (K/V rows beyond L stay zero for ever; slab rows the TMA never
     // writes must hold finite bit patterns, not NaNs), barriers
-    for (size_t i = tid; i < NSTAGE * stage_bytes / 4; i += nthr) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    for (size_t i = tid; i < NSTAGE_F * stage_bytes / 4; i += nthr) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[s], 1);
+        for (int s = 0; s < NSTAGE_F; ++s) mbar_init(&full_bar[s], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -153,7 +154,6 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
     const int w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
     const size_t tile_elems = (size_t)L * G::STRIDE;
     const FastDiv div_h((uint32_t)p.H), div_c((uint32_t)p.nchunks);
-    const uint32_t thresh2 = p.thresh16 | (p.thresh16 << 16);
 
     auto prefetch = [&](int w, int s) {
         const int tile = (int)div_c.div((uint32_t)w);
@@ -181,19 +181,21 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
     if (w0 < w1) prefetch(w0, 0);
 
     int it = 0;
+    int s = 0, par = 0;                 // ring position of item w and the phase parity of its mbarrier
     for (int w = w0; w < w1; ++w, ++it) {
-        const int s = it & 1;
         const int tile = (int)div_c.div((uint32_t)w);
         const int chunk = w - tile * p.nchunks;
         const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
 
         cp_async_wait<0>();
-        mbar_wait(&full_bar[s], (it >> 1) & 1);
+        mbar_wait(&full_bar[s], par);
         __syncthreads();                    // item w is resident; everyone is done with item w-1
+        const int sn = s + 1 == NSTAGE_F ? 0 : s + 1;
         if (w + 1 < w1) {
-            if (tid == 0) bulk_wait_read<0>();       // the store that last read stage s^1 has drained it
-            prefetch(w + 1, s ^ 1);
+            // stage sn was last read by the bulk store of item w-2: allow the store of item w-1 to stay in flight
+            if (tid == 0) bulk_wait_read<1>();
+            prefetch(w + 1, sn);
         }
 
         if (warp < p.crb && row0 + warp * 16 < L) {
@@ -275,32 +277,25 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                 suma += sc[kb][0] + sc[kb][1];
                 sumb += sc[kb][2] + sc[kb][3];
             }
-            // dropout: per-halfword keep masks (0xFFFF = keep), applied to the packed bf16 probabilities below
-            uint32_t mka[NKB], mkb[NKB];
+            // dropout: one hash per 4 elements; the odd column's 16 bits are compared in place (bits >= t << 16),
+            // the even column's after one shift
             if (do_drop) {
                 const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
+                const uint32_t thi = p.thresh16 << 16;
 #pragma unroll
                 for (int kb = 0; kb < NKB; kb += 2) {
                     const uint2 wa = rng_quad_bits(rkey, ra, kb * 8 + 2 * q4), wb = rng_quad_bits(rkey, rbb, kb * 8 + 2 * q4);
-                    mka[kb] = rng_keep_mask2(wa.x, thresh2);
-                    mkb[kb] = rng_keep_mask2(wb.x, thresh2);
+                    if ((wa.x << 16) < thi) sc[kb][0] = 0.f;
+                    if (wa.x < thi) sc[kb][1] = 0.f;
+                    if ((wb.x << 16) < thi) sc[kb][2] = 0.f;
+                    if (wb.x < thi) sc[kb][3] = 0.f;
                     if (kb + 1 < NKB) {
-                        mka[kb + 1] = rng_keep_mask2(wa.y, thresh2);
-                        mkb[kb + 1] = rng_keep_mask2(wb.y, thresh2);
+                        if ((wa.y << 16) < thi) sc[kb + 1][0] = 0.f;
+                        if (wa.y < thi) sc[kb + 1][1] = 0.f;
+                        if ((wb.y << 16) < thi) sc[kb + 1][2] = 0.f;
+                        if (wb.y < thi) sc[kb + 1][3] = 0.f;
                     }
                 }
-                if constexpr (F32) {
-#pragma unroll
-                    for (int kb = 0; kb < NKB; ++kb) {
-                        if (!(mka[kb] & 0xffffu)) sc[kb][0] = 0.f;
-                        if (!(mka[kb] >> 16)) sc[kb][1] = 0.f;
-                        if (!(mkb[kb] & 0xffffu)) sc[kb][2] = 0.f;
-                        if (!(mkb[kb] >> 16)) sc[kb][3] = 0.f;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int kb = 0; kb < NKB; ++kb) mka[kb] = mkb[kb] = 0xffffffffu;
             }
             suma = quad_sum(suma);
             sumb = quad_sum(sumb);
@@ -319,12 +314,12 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                     for (int jj = 0; jj < 2; ++jj) {
                         if (j + jj < G::NKB16) {
                             const int kb0 = 2 * (j + jj), kb1 = kb0 + 1;
-                            const uint32_t a0 = pack_bf16(sc[kb0][0], sc[kb0][1]) & mka[kb0];
-                            const uint32_t a1 = pack_bf16(sc[kb0][2], sc[kb0][3]) & mkb[kb0];
+                            const uint32_t a0 = pack_bf16(sc[kb0][0], sc[kb0][1]);
+                            const uint32_t a1 = pack_bf16(sc[kb0][2], sc[kb0][3]);
                             uint32_t a2 = 0u, a3 = 0u;
                             if (kb1 < NKB) {
-                                a2 = pack_bf16(sc[kb1][0], sc[kb1][1]) & mka[kb1];
-                                a3 = pack_bf16(sc[kb1][2], sc[kb1][3]) & mkb[kb1];
+                                a2 = pack_bf16(sc[kb1][0], sc[kb1][1]);
+                                a3 = pack_bf16(sc[kb1][2], sc[kb1][3]);
                             }
                             mma_bf16_16816(o, a0, a1, a2, a3, jj ? b2 : b0, jj ? b3 : b1);
                         }
@@ -376,6 +371,8 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                      (uint32_t)((size_t)nrows * G::STRIDE * sizeof(TP)));
             bulk_commit();
         }
+        if (sn == 0) par ^= 1;
+        s = sn;
     }
     if (tid == 0) bulk_wait_all<0>();
 }
@@ -631,10 +628,11 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 if (do_drop) {
                     if ((kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
                     const uint32_t ba = (kb & 1) ? qwa.y : qwa.x, bb = (kb & 1) ? qwb.y : qwb.x;
-                    k0 = rng_keep(ba, 0, p.thresh16) ? p.keep_scale : 0.f;
-                    k1 = rng_keep(ba, 1, p.thresh16) ? p.keep_scale : 0.f;
-                    k2 = rng_keep(bb, 0, p.thresh16) ? p.keep_scale : 0.f;
-                    k3 = rng_keep(bb, 1, p.thresh16) ? p.keep_scale : 0.f;
+                    const uint32_t thi = p.thresh16 << 16;
+                    k0 = (ba << 16) >= thi ? p.keep_scale : 0.f;
+                    k1 = ba >= thi ? p.keep_scale : 0.f;
+                    k2 = (bb << 16) >= thi ? p.keep_scale : 0.f;
+                    k3 = bb >= thi ? p.keep_scale : 0.f;
                 }
                 const float A0 = sc[kb][0] * inva, A1 = sc[kb][1] * inva, A2 = sc[kb][2] * invb, A3 = sc[kb][3] * invb;
                 if constexpr (F32) {
@@ -855,7 +853,7 @@ inline void pick_chunks(int L, int& crb, int& nchunks) {
 template <typename T, typename TP, int NKB>
 int launch_fwd(FwdParams p, cudaStream_t st) {
     pick_chunks(p.L, p.crb, p.nchunks);
-    auto smem_of = [](int crb) { return NSTAGE * ((FwdStage<T, TP, NKB>::bytes(crb * 16) + 127) & ~size_t(127)); };
+    auto smem_of = [](int crb) { return NSTAGE_F * ((FwdStage<T, TP, NKB>::bytes(crb * 16) + 127) & ~size_t(127)); };
     while (p.crb > 1 && smem_of(p.crb) > SMEM_CAP) --p.crb;
     p.nchunks = ((p.L + 15) / 16 + p.crb - 1) / p.crb;
     const size_t smem = smem_of(p.crb);
