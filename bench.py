@@ -270,8 +270,16 @@ def run_ours(args, rank, local_rank, world):
             # the last layer's backward reads no dP' (MM-DTI discards the pair output): 1 of 15 launches
             bytes_per_launch = alg[dom] - (nel * esz / LAYERS if dom.endswith("bwd") else 0)
             ach = bytes_per_launch / (s / n) / 1e9
+            traffic = None
+            try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+                with open(os.path.join(ROOT, "profiles", "k2_dram_traffic.json")) as fh:
+                    tr = json.load(fh)[dom]
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            except Exception:
+                pass
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "traffic": traffic, "traffic_source": "profiles/k2_dram_traffic.json (ncu --set full, bytes per launch)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                     "avg_launch_us": 1e6 * s / n, "share_of_step": (s / tl_steps) / (t_res / args.steps),
                     "timing": "CUDA events around each launch on the launching stream"
                               + (" (separate eager pass: the timed region replays a CUDA graph)" if use_graph else "")}

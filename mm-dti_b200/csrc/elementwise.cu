@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace {
@@ -560,6 +561,18 @@ __global__ void ew_mask_kernel(uint8_t* keep, long long n, uint32_t key, const u
         keep[i] = ew_keep(key, (unsigned long long)i, thresh16) ? 1 : 0;
 }
 
+// CTAs per SM of the row-reduction kernels (LayerNorm backward): every CTA ends with D..3D vector atomics, so
+// fewer, longer-running CTAs win over occupancy.  MMDTI_LN_CTAS_PER_SM overrides for tuning.
+inline int ln_ctas_per_sm() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("MMDTI_LN_CTAS_PER_SM");
+        v = e ? atoi(e) : 2;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
 inline int ew_grid(long long work_items, int per_block) {
     return (int)std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, (long long)num_sms() * 8));
 }
@@ -594,7 +607,7 @@ extern "C" int mmdti_layernorm_bwd(const void* dy, const float* x, const float* 
                   "layernorm_bwd: bad arguments (D=%d)", D);
     MMDTI_REQUIRE(dy_dtype == MMDTI_F32 || dy_dtype == MMDTI_BF16, "layernorm_bwd: dy_dtype must be f32 or bf16");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = std::min(ew_grid(rows, 8), num_sms() * 4);
+    const int grid = std::min(ew_grid(rows, 8), num_sms() * ln_ctas_per_sm());
     const size_t smem = (size_t)8 * 2 * D * sizeof(float);
 #define CALL(NV)                                                                                                         \
     if (dy_dtype == MMDTI_F32) {                                                                                         \
@@ -649,7 +662,7 @@ extern "C" int mmdti_layernorm_bwd_dropout(const void* dy, const float* x, const
     drop_params(p, th, ks);
     const uint32_t key = mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = std::min(ew_grid(rows, 8), num_sms() * 4);
+    const int grid = std::min(ew_grid(rows, 8), num_sms() * ln_ctas_per_sm());
     const size_t smem = (size_t)8 * 3 * D * sizeof(float);
 #define CALL(NV)                                                                                                         \
     if (dy_dtype == MMDTI_F32) {                                                                                         \
