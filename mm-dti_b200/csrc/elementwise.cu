@@ -573,6 +573,16 @@ inline int ln_ctas_per_sm() {
     return v;
 }
 
+inline int rowmap_ctas_per_sm() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("MMDTI_ROWMAP_CTAS_PER_SM");
+        v = e ? atoi(e) : 2;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
 inline int ew_grid(long long work_items, int per_block) {
     return (int)std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, (long long)num_sms() * 8));
 }
@@ -703,7 +713,7 @@ static int launch_rowmap(const void* in0, const void* in1, void* out, float* col
     const int tpr = C / 8;
     const int rpp = 256 / tpr;
     const size_t smem = rpp > 1 ? (size_t)rpp * C * sizeof(float) : 0;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 4 * rpp - 1) / (4 * rpp), (long long)num_sms() * 2));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 4 * rpp - 1) / (4 * rpp), (long long)num_sms() * rowmap_ctas_per_sm()));
     rowmap_colsum_kernel<TIN0, TIO, OP><<<grid, 256, smem, st>>>(static_cast<const TIN0*>(in0), static_cast<const TIO*>(in1),
                                                                   static_cast<TIO*>(out), colsum, rows, C, key, mmdti_seed_offset_ptr(), th, ks);
     return 0;

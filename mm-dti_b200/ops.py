@@ -301,6 +301,17 @@ def _mm_f32(a, b):
         return torch.mm(a, b).float()
 
 
+_side_streams = {}
+overlap_wgrad = True      # run weight-gradient GEMMs / bias column sums of a layer on a side stream (off the critical path)
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
+
+
 def layernorm_fwd(x2d, w, b, out_dtype, eps=1e-5):
     rows, D = x2d.shape
     y = torch.empty((rows, D), device=x2d.device, dtype=out_dtype)
@@ -379,33 +390,53 @@ class EncoderLayerFn(torch.autograd.Function):
         db_out, db_fc2 = red[4 * D:5 * D], red[5 * D:6 * D]
         db_fc1 = red[6 * D:6 * D + F_]
         db_in = red[6 * D + F_:]
+        # Weight gradients (and the in_proj bias column sums) are not on the critical path of the backward
+        # chain: they go to a side stream and overlap the latency-bound kernels of the main stream (in a CUDA
+        # graph they become parallel branches).  The layer joins the side stream before it returns.
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if overlap_wgrad else None
+
+        def off_path(fn):
+            if side is None:
+                return fn()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = fn()
+            out.record_stream(main)
+            return out
+
         # ---- feed-forward block
         df = torch.empty((rows, D), device=dev, dtype=dt)
         call("mmdti_dropout_bwd", dx2, df, db_fc2, i32(rows), i32(D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+        dW_fc2 = off_path(lambda: _mm_f32(df.t(), u))
         du = torch.mm(df, w_fc2_l)
-        dW_fc2 = _mm_f32(df.t(), u)
         dz = torch.empty_like(z)
         call("mmdti_gelu_bwd", du, z, dz, db_fc1, i32(rows), i32(F_), i32(code), sp)
+        dW_fc1 = off_path(lambda: _mm_f32(dz.t(), h2))
         dh2 = torch.mm(dz, w_fc1_l)
-        dW_fc1 = _mm_f32(dz.t(), h2)
         dx1 = torch.empty_like(x2d)
         # ---- attention block (LayerNorm-2 backward fused with the dropout backward of the attention output)
         da = torch.empty((rows, D), device=dev, dtype=dt)
         call("mmdti_layernorm_bwd_dropout", dh2, x1, ln2_w, st2[0], st2[1], dx2, dx1, dw_ln2, db_ln2, da, db_out, i32(rows),
              i32(D), f32(p_drop), u64(seeds[1]), i32(code), sp)
+        dW_out = off_path(lambda: _mm_f32(da.t(), o))
         d_o = torch.mm(da, w_out_l)
-        dW_out = _mm_f32(da.t(), o)
         dqkv = torch.empty_like(qkv)
         dpair_in = torch.empty_like(pair_out)
         call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_out, o, d_o, i64(D),
              dpair_out, dpair_in, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L),
              f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_out.dtype]),
              i32(DTYPE_CODE[pair_out.dtype]), sp)
-        call("mmdti_colsum", dqkv, db_in, i32(rows), i32(3 * D), i32(code), sp)
+        def in_proj_grads():
+            call("mmdti_colsum", dqkv, db_in, i32(rows), i32(3 * D), i32(code), stream_ptr())
+            return _mm_f32(dqkv.t(), h1)
+
+        dW_in = off_path(in_proj_grads)
         dh1 = torch.mm(dqkv, w_in_l)
-        dW_in = _mm_f32(dqkv.t(), h1)
         dx = dx1          # in place: dx = dx1 + dLN1
         call("mmdti_layernorm_bwd", dh1, x2d, ln1_w, st1[0], st1[1], dx1, dx, dw_ln1, db_ln1, i32(rows), i32(D), i32(code), sp)
+        if side is not None:
+            main.wait_stream(side)
         return (dx.view(B, L, D), dpair_in, dw_ln1, db_ln1, dW_in, db_in, dW_out, db_out, dw_ln2, db_ln2, dW_fc1, db_fc1,
                 dW_fc2, db_fc2, None, None)
 
