@@ -69,9 +69,10 @@ struct BwdSmem {
     float* db2;                                  // [64]
     float *s_u, *s_d;                            // [128] per-pair u, dist
     int* s_e;                                    // [128] per-pair edge type (-1: no pair)
+    long long* s_off;                            // [128] element offset of (b, h=0, i, j) in d_out (-1: no pair)
     static size_t bytes(int E) {
         return sizeof(bf16) * WS * (size_t)(128 + 64 + 64 + 3 * 128) + sizeof(float) * (size_t)(5 * 128 + 4 * E + 3 * 128 + 64 + 2 * 128) +
-               sizeof(int) * 128 + 64;
+               sizeof(int) * 128 + sizeof(long long) * 128 + 64;
     }
     __device__ void carve(unsigned char* base, int E) {
         W1s = reinterpret_cast<bf16*>(base);
@@ -86,6 +87,8 @@ struct BwdSmem {
         dmu = dbias + E; dsd = dmu + 128; db1 = dsd + 128; db2 = db1 + 128;
         s_u = db2 + 64; s_d = s_u + 128;
         s_e = reinterpret_cast<int*>(s_d + 128);
+        // 8-byte aligned: everything before is a multiple of 8 bytes when E is odd or even? keep it safe:
+        s_off = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(s_e + 128) + 7) & ~uintptr_t(7));
     }
 };
 
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) pair_bias_bwd_kernel(const BwdB
             const long long P = P0 + tid;
             int e = -1;
             float u = 0.f, d = 0.f;
+            long long off = -1;
             if (P < p.npairs) {
                 long long ee = p.et[P];
                 if (ee < 0) ee = 0;
@@ -147,23 +151,30 @@ __global__ void __launch_bounds__(NWARP * 32, 1) pair_bias_bwd_kernel(const BwdB
                 e = (int)ee;
                 d = p.dist[P];
                 u = fmaf(S.muls[e], d, S.biass[e]);
+                const long long bidx = P / LL;
+                const int pp = (int)(P - bidx * LL), irow = pp / p.L, j = pp - irow * p.L;
+                off = bidx * NH * tile_elems + (long long)irow * p.Lp + j;
             }
             S.s_e[tid] = e;
             S.s_u[tid] = u;
             S.s_d[tid] = d;
+            S.s_off[tid] = off;
         }
-        // ---- dO^T tile [head][pair] (non-finite entries -> 0: they sit at masked keys / padding)
-        for (int idx = tid; idx < NH * TPR; idx += blockDim.x) {
-            const int h = idx >> 7, i = idx & (TPR - 1);
-            const long long P = P0 + i;
-            float v = 0.f;
-            if (P < p.npairs) {
-                const long long bidx = P / LL;
-                const int pp = (int)(P - bidx * LL), irow = pp / p.L, j = pp - irow * p.L;
-                v = to_f(dout[(bidx * NH + h) * tile_elems + (long long)irow * p.Lp + j]);
-                if (!(fabsf(v) <= 3.0e38f)) v = 0.f;
+        __syncthreads();
+        // ---- dO^T tile [head][pair] (non-finite entries -> 0: they sit at masked keys / padding).  Thread t owns
+        //      pair t & 127 and every other head: 32 independent 2-byte loads in flight per thread, no index math
+        {
+            const int i = tid & (TPR - 1), h0 = tid >> 7;
+            const long long off = S.s_off[i];
+            float v[NH / 2];
+#pragma unroll
+            for (int k = 0; k < NH / 2; ++k) v[k] = off >= 0 ? to_f(dout[off + (long long)(h0 + 2 * k) * tile_elems]) : 0.f;
+#pragma unroll
+            for (int k = 0; k < NH / 2; ++k) {
+                float x = v[k];
+                if (!(fabsf(x) <= 3.0e38f)) x = 0.f;
+                S.dOt[(h0 + 2 * k) * WS + i] = __float2bfloat16_rn(x);
             }
-            S.dOt[h * WS + i] = __float2bfloat16_rn(v);
         }
         __syncthreads();
 
