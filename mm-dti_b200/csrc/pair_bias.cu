@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
     int* s_off = s_mol + TM;                                         // [TM] irow*Lp + j inside the (b,h) tile
     TP* Ot = reinterpret_cast<TP*>(s_off + TM);                      // [64][OT_STRIDE]
     unsigned char* negf = reinterpret_cast<unsigned char*>(Ot + NH * OT_STRIDE);   // [TM] bit0: -inf key, bit1: row end
+    long long* s_base = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(negf + TM) + 7) & ~uintptr_t(7));   // [TM] offset of (b, h=0, i, j)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
 
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
             s_mol[warp * 16 + lane] = mol;
             s_off[warp * 16 + lane] = off;
             negf[warp * 16 + lane] = fl;
+            s_base[warp * 16 + lane] = mol >= 0 ? (long long)mol * NH * ((long long)p.L * p.Lp) + off : -1;
         }
         __syncwarp();
         const float ua = __shfl_sync(0xffffffffu, u, g), ub = __shfl_sync(0xffffffffu, u, g + 8);
@@ -180,14 +182,38 @@ __global__ void __launch_bounds__(128) pair_bias_fwd_tc_kernel(const BiasParams 
         TP* out = static_cast<TP*>(p.out);
         const long long tile_elems = (long long)p.L * p.Lp;
         const TP ninf = from_f<TP>(-INFINITY);
-        for (int idx = tid; idx < NH * TM; idx += blockDim.x) {
-            const int h = idx >> 6, i = idx & (TM - 1);
-            const int mol = s_mol[i];
-            if (mol >= 0) {
-                TP* dst = out + ((long long)mol * NH + h) * tile_elems + s_off[i];
-                *dst = Ot[h * OT_STRIDE + i];
-                if (negf[i] & 2) {                       // last key of its row: write the -inf padding columns
-                    for (int c = 1; c <= p.Lp - p.L; ++c) dst[c] = ninf;
+        if (sizeof(TP) == 2 && (p.L & 1) == 0) {
+            // even L, 16-bit output: pairs (P even, P+1) are adjacent keys of the same row and 4-byte aligned ->
+            // one 32-bit store per two pairs; the row's -inf padding follows the odd pair of a row end
+            const int npad2 = (p.Lp - p.L) >> 1;
+            uint32_t ninf2;
+            {
+                const TP t2[2] = {ninf, ninf};
+                ninf2 = *reinterpret_cast<const uint32_t*>(t2);
+            }
+            for (int idx = tid; idx < NH * (TM / 2); idx += blockDim.x) {
+                const int h = idx >> 5, i = (idx & (TM / 2 - 1)) * 2;
+                const long long b0 = s_base[i];
+                if (b0 < 0) continue;
+                TP* dst = out + b0 + (long long)h * tile_elems;
+                if (s_base[i + 1] >= 0) {
+                    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(Ot + h * OT_STRIDE + i);
+                    if (negf[i + 1] & 2)
+                        for (int c = 1; c <= npad2; ++c) reinterpret_cast<uint32_t*>(dst)[c] = ninf2;
+                } else {
+                    *dst = Ot[h * OT_STRIDE + i];
+                }
+            }
+        } else {
+            for (int idx = tid; idx < NH * TM; idx += blockDim.x) {
+                const int h = idx >> 6, i = idx & (TM - 1);
+                const long long b0 = s_base[i];
+                if (b0 >= 0) {
+                    TP* dst = out + b0 + (long long)h * tile_elems;
+                    *dst = Ot[h * OT_STRIDE + i];
+                    if (negf[i] & 2) {                       // last key of its row: write the -inf padding columns
+                        for (int c = 1; c <= p.Lp - p.L; ++c) dst[c] = ninf;
+                    }
                 }
             }
         }
@@ -465,7 +491,7 @@ extern "C" int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, 
     } else {
         const size_t esz = pair_dtype == MMDTI_F32 ? 4 : 2;
         const size_t smem = (size_t)(KB + NH) * WS * sizeof(bf16) + (size_t)(KB * 4 + NH + 2 * E) * sizeof(float) +
-                            (size_t)2 * TM * sizeof(int) + (size_t)NH * OT_STRIDE * esz + TM + 16;
+                            (size_t)2 * TM * sizeof(int) + (size_t)NH * OT_STRIDE * esz + TM + 16 + (size_t)TM * sizeof(long long) + 8;
         const long long ntiles = (p.npairs + TM - 1) / TM;
         const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * 3);
 #define LAUNCH_TC(TP)                                                                                              \

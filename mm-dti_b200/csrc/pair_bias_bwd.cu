@@ -70,9 +70,10 @@ struct BwdSmem {
     float *s_u, *s_d;                            // [128] per-pair u, dist
     int* s_e;                                    // [128] per-pair edge type (-1: no pair)
     long long* s_off;                            // [128] element offset of (b, h=0, i, j) in d_out (-1: no pair)
+    float* wacc;                                 // [NWARP][2][128] per-warp private d_means / d_stds partials (no atomics)
     static size_t bytes(int E) {
         return sizeof(bf16) * WS * (size_t)(128 + 64 + 64 + 3 * 128) + sizeof(float) * (size_t)(5 * 128 + 4 * E + 3 * 128 + 64 + 2 * 128) +
-               sizeof(int) * 128 + sizeof(long long) * 128 + 64;
+               sizeof(int) * 128 + sizeof(long long) * 128 + sizeof(float) * NWARP * 256 + 64;
     }
     __device__ void carve(unsigned char* base, int E) {
         W1s = reinterpret_cast<bf16*>(base);
@@ -89,6 +90,7 @@ struct BwdSmem {
         s_e = reinterpret_cast<int*>(s_d + 128);
         // 8-byte aligned: everything before is a multiple of 8 bytes when E is odd or even? keep it safe:
         s_off = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(s_e + 128) + 7) & ~uintptr_t(7));
+        wacc = reinterpret_cast<float*>(s_off + 128);
     }
 };
 
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(NWARP * 32, 1) pair_bias_bwd_kernel(const BwdB
         S.dmu[i] = S.dsd[i] = S.db1[i] = 0.f;
     }
     for (int i = tid; i < NH; i += blockDim.x) S.db2[i] = 0.f;
+    for (int i = tid; i < NWARP * 256; i += blockDim.x) S.wacc[i] = 0.f;
     for (int i = tid; i < p.E; i += blockDim.x) {
         S.muls[i] = p.mul[i];
         S.biass[i] = p.bias[i];
@@ -298,11 +301,12 @@ __global__ void __launch_bounds__(NWARP * 32, 1) pair_bias_bwd_kernel(const BwdB
                         ds[e] += __shfl_xor_sync(0xffffffffu, ds[e], o);
                     }
                 }
-                if (g == 0) {
-                    atomicAdd(S.dmu + c0, dm[0]);
-                    atomicAdd(S.dmu + c0 + 1, dm[1]);
-                    atomicAdd(S.dsd + c0, ds[0]);
-                    atomicAdd(S.dsd + c0 + 1, ds[1]);
+                if (g == 0) {                 // lanes 0..3 own distinct columns of this warp's private row: plain read-modify-write
+                    float* pm = S.wacc + warp * 256;
+                    float2 a = *reinterpret_cast<float2*>(pm + c0), b = *reinterpret_cast<float2*>(pm + 128 + c0);
+                    a.x += dm[0]; a.y += dm[1]; b.x += ds[0]; b.y += ds[1];
+                    *reinterpret_cast<float2*>(pm + c0) = a;
+                    *reinterpret_cast<float2*>(pm + 128 + c0) = b;
                 }
             }
             dua = quad_sum(dua);
@@ -385,8 +389,10 @@ __global__ void __launch_bounds__(NWARP * 32, 1) pair_bias_bwd_kernel(const BwdB
     }
     if (tid < KB) {
         atomicAdd(p.d_b1 + tid, colacc);
-        atomicAdd(p.d_means + tid, S.dmu[tid]);
-        atomicAdd(p.d_stds + tid, S.dsd[tid]);
+        float sm = 0.f, ss = 0.f;
+        for (int w = 0; w < NWARP; ++w) { sm += S.wacc[w * 256 + tid]; ss += S.wacc[w * 256 + 128 + tid]; }
+        atomicAdd(p.d_means + tid, sm);
+        atomicAdd(p.d_stds + tid, ss);
     } else if (tid < KB + NH) {
         atomicAdd(p.d_b2 + (tid - KB), colacc);
     }
