@@ -79,6 +79,39 @@ template <typename TP> __device__ __forceinline__ float2 unpack2(uint32_t u);
 template <> __device__ __forceinline__ float2 unpack2<bf16>(uint32_t u) { return unpack_bf16(u); }
 template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) { return unpack_f16(u); }
 
+// ---------------------------------------------------------------- fast math (bf16 paths)
+// exp2f / __expf / __fdividef carry range fix-ups (FSETP + predicated FMULs around the MUFU); the flush-to-zero
+// approximations are a single MUFU each, accurate to 2 ulp — far below the bf16 rounding of what consumes them.
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+// exact-erf GELU and its derivative with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7); exp(-x^2/2) is shared
+// between erf and the normal density.  value = x Phi(x), grad = Phi(x) + x phi(x).
+__device__ __forceinline__ void gelu_fast_both(float x, float& val, float& grad) {
+    const float e = fast_ex2(x * x * -0.72134752044448170368f);                      // exp(-x^2/2)
+    const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erfa = fmaf(-poly * t, e, 1.f);                                      // erf(|x| / sqrt 2)
+    const float cdf = 0.5f + copysignf(0.5f * erfa, x);
+    val = x * cdf;
+    grad = fmaf(x * e, 0.3989422804014327f, cdf);
+}
+__device__ __forceinline__ float gelu_fast_val(float x) {
+    float v, g;
+    gelu_fast_both(x, v, g);
+    return v;
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) dropres_layernorm_fwd_kernel(const float*
 // dx = dx_add + dLN/dx (f32, stored: the residual gradient);  da = dropout'(dx) (TDA);  dbias += colsum(da);
 // dw, db += LayerNorm parameter gradients.  Same mask as dropout_bwd (key, flat index).
 template <typename TI, typename TDA, int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_dropout_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_dropout_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ w, const float* __restrict__ mean,
                                                                     const float* __restrict__ rstd, const float* __restrict__ dx_add,
                                                                     float* __restrict__ dx, float* __restrict__ dw,
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dropout_kernel(const TI* __
 // dx_out = (add ? dx_add : 0) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*w
 // dw += sum_rows dy*xhat, db += sum_rows dy   (warp partials -> smem -> atomics)
 template <typename TI, int NV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const TI* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ dx_add,
                                                             float* __restrict__ dx, float* __restrict__ dw,
@@ -393,18 +393,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 // bf16 tensors: exact-erf GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the bf16
 // rounding of the result): 2 MUFU + ~10 FMA-class instructions instead of erff + expf (~50); exp(-x^2/2) is
 // shared between erf and the normal density of the gradient.
-__device__ __forceinline__ void gelu_fast_pair(float x, float& val, float& grad) {
-    const float e = __expf(-0.5f * x * x);
-    const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float erfa = fmaf(-poly * t, e, 1.f);
-    const float cdf = 0.5f + copysignf(0.5f * erfa, x);
-    val = x * cdf;
-    grad = fmaf(x * e, 0.3989422804014327f, cdf);
-}
+__device__ __forceinline__ void gelu_fast_pair(float x, float& val, float& grad) { gelu_fast_both(x, val, grad); }
 template <typename T> __device__ __forceinline__ float gelu_t(float x) {
     if constexpr (sizeof(T) == 4) return gelu_f(x);
     float v, g;

@@ -266,10 +266,10 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                 const float ka = ma * LOG2E, kbm = mb * LOG2E;
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
-                    sc[kb][0] = exp2f(fmaf(sc[kb][0], LOG2E, -ka));
-                    sc[kb][1] = exp2f(fmaf(sc[kb][1], LOG2E, -ka));
-                    sc[kb][2] = exp2f(fmaf(sc[kb][2], LOG2E, -kbm));
-                    sc[kb][3] = exp2f(fmaf(sc[kb][3], LOG2E, -kbm));
+                    sc[kb][0] = fast_ex2(fmaf(sc[kb][0], LOG2E, -ka));
+                    sc[kb][1] = fast_ex2(fmaf(sc[kb][1], LOG2E, -ka));
+                    sc[kb][2] = fast_ex2(fmaf(sc[kb][2], LOG2E, -kbm));
+                    sc[kb][3] = fast_ex2(fmaf(sc[kb][3], LOG2E, -kbm));
                 }
             }
 #pragma unroll
@@ -561,10 +561,10 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 const float ka = ma * LOG2E, kbm = mb * LOG2E;
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
-                    sc[kb][0] = exp2f(fmaf(sc[kb][0], LOG2E, -ka));
-                    sc[kb][1] = exp2f(fmaf(sc[kb][1], LOG2E, -ka));
-                    sc[kb][2] = exp2f(fmaf(sc[kb][2], LOG2E, -kbm));
-                    sc[kb][3] = exp2f(fmaf(sc[kb][3], LOG2E, -kbm));
+                    sc[kb][0] = fast_ex2(fmaf(sc[kb][0], LOG2E, -ka));
+                    sc[kb][1] = fast_ex2(fmaf(sc[kb][1], LOG2E, -ka));
+                    sc[kb][2] = fast_ex2(fmaf(sc[kb][2], LOG2E, -kbm));
+                    sc[kb][3] = fast_ex2(fmaf(sc[kb][3], LOG2E, -kbm));
                 }
             }
 #pragma unroll

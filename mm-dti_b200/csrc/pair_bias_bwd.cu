@@ -43,18 +43,7 @@ struct BwdBiasParams {
 
 // gelu(x) = x Phi(x) and gelu'(x) = Phi(x) + x phi(x); erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7),
 // sharing exp(-x^2/2) between erf and phi.
-__device__ __forceinline__ void gelu_and_grad(float x, float& h, float& gp) {
-    const float e = __expf(-0.5f * x * x);
-    const float t = __fdividef(1.f, fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.f));
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float erfa = fmaf(-poly * t, e, 1.f);                 // erf(|x|/sqrt2)
-    const float cdf = 0.5f + copysignf(0.5f * erfa, x);
-    h = x * cdf;
-    gp = fmaf(x * e, 0.3989422804014327f, cdf);
-}
+__device__ __forceinline__ void gelu_and_grad(float x, float& h, float& gp) { gelu_fast_both(x, h, gp); }
 
 struct BwdSmem {
     bf16* W1s;      // [128][WS]   W1[hidden][k]
@@ -200,8 +189,8 @@ __global__ void __launch_bounds__(NWARP * 32, 1) pair_bias_bwd_kernel(const BwdB
                     for (int e = 0; e < 2; ++e) {
                         const float m = S.mus[k0 + e], is = S.isg[k0 + e], c = S.cof[k0 + e];
                         const float ra = (ua - m) * is, rb = (ub - m) * is;
-                        ga[e] = __expf(-0.5f * ra * ra) * c;
-                        gb[e] = __expf(-0.5f * rb * rb) * c;
+                        ga[e] = fast_ex2(ra * ra * -0.72134752044448170368f) * c;
+                        gb[e] = fast_ex2(rb * rb * -0.72134752044448170368f) * c;
                     }
                     a[hf * 2 + 0] = pack_bf16(ga[0], ga[1]);
                     a[hf * 2 + 1] = pack_bf16(gb[0], gb[1]);
