@@ -470,11 +470,11 @@ template <typename T> __device__ __forceinline__ void store8(T* p, float (&v)[8]
 }
 
 template <typename TIN0, typename TIO, int OP>
-__global__ void __launch_bounds__(256) rowmap_colsum_kernel(const TIN0* __restrict__ in0, const TIO* __restrict__ in1,
+__global__ void __launch_bounds__(256, 4) rowmap_colsum_kernel(const TIN0* __restrict__ in0, const TIO* __restrict__ in1,
                                                             TIO* __restrict__ out, float* __restrict__ colsum, int rows, int C,
                                                             uint32_t key, const unsigned long long* seed_off, uint32_t thresh16, float keep_scale) {
     key = rng_effective_key(key, seed_off);
-    constexpr int UNROLL = 4;
+    constexpr int UNROLL = 2;         // 4 CTAs/SM x 8 warps with 2 row passes in flight each beat 2 CTAs x 4 passes (latency-bound)
     extern __shared__ float part[];                   // [rpp][C] when rpp > 1
     const int tpr = C >> 3;                           // threads per row (8 columns each); host guarantees tpr <= 256
     const int rpp = blockDim.x / tpr;                 // rows per pass
@@ -566,7 +566,7 @@ inline int rowmap_ctas_per_sm() {
     static int v = 0;
     if (!v) {
         const char* e = getenv("MMDTI_ROWMAP_CTAS_PER_SM");
-        v = e ? atoi(e) : 2;
+        v = e ? atoi(e) : 4;
         if (v < 1) v = 1;
     }
     return v;
@@ -702,7 +702,7 @@ static int launch_rowmap(const void* in0, const void* in1, void* out, float* col
     const int tpr = C / 8;
     const int rpp = 256 / tpr;
     const size_t smem = rpp > 1 ? (size_t)rpp * C * sizeof(float) : 0;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 4 * rpp - 1) / (4 * rpp), (long long)num_sms() * rowmap_ctas_per_sm()));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 4 * rpp - 1) / (4 * rpp), (long long)num_sms() * (OP == OP_COLSUM ? std::min(2, rowmap_ctas_per_sm()) : rowmap_ctas_per_sm())));
     rowmap_colsum_kernel<TIN0, TIO, OP><<<grid, 256, smem, st>>>(static_cast<const TIN0*>(in0), static_cast<const TIO*>(in1),
                                                                   static_cast<TIO*>(out), colsum, rows, C, key, mmdti_seed_offset_ptr(), th, ks);
     return 0;
