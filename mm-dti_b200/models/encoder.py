@@ -174,7 +174,7 @@ class UnimolEncoder(nn.Module):
         host sync on ``padding_mask.any()``); with no padding it is all-false and the result is
         identical to the reference's padding_mask=None branch (Q15)."""
         padding_mask = src_tokens.eq(self.padding_idx)
-        x = self.embed_tokens(src_tokens)
+        x = ops.TokenEmbeddingFn.apply(src_tokens, self.embed_tokens.weight, self.padding_idx)
         g, pj = self.gbf, self.gbf_proj
         # K1 straight into the padded (B,H,L,Lp) layout with the key-padding mask merged
         bias = ops.pair_bias(src_distance, src_edge_type, g.means.weight, g.stds.weight, g.mul.weight, g.bias.weight,

@@ -321,6 +321,56 @@ def layernorm_fwd(x2d, w, b, out_dtype, eps=1e-5):
     return y, stats
 
 
+class LayerNormFn(torch.autograd.Function):
+    """Stand-alone LayerNorm (unicore.modules.LayerNorm, eps 1e-5) on the mmdti kernels: fp32 in / fp32 out.
+    Used for the encoder's emb_layer_norm / final_layer_norm (models/transformers.py:69-78,114,160)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        _lib.require_cuda(x)
+        D = x.shape[-1]
+        x2d = x.detach().reshape(-1, D).contiguous().float()
+        wd, bd = w.detach().float().contiguous(), b.detach().float().contiguous()
+        y = torch.empty_like(x2d)
+        st = torch.empty((2, x2d.shape[0]), device=x.device, dtype=torch.float32)
+        call("mmdti_layernorm_fwd", x2d, wd, bd, y, st[0], st[1], i32(x2d.shape[0]), i32(D), f32(eps), i32(_lib.F32), stream_ptr())
+        ctx.save_for_backward(x2d, wd, st)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2d, w, st = ctx.saved_tensors
+        rows, D = x2d.shape
+        dy2 = dy.reshape(rows, D).contiguous().float()
+        dx = torch.empty_like(x2d)
+        dwb = torch.zeros(2 * D, device=x2d.device, dtype=torch.float32)
+        call("mmdti_layernorm_bwd", dy2, x2d, w, st[0], st[1], None, dx, dwb[:D], dwb[D:], i32(rows), i32(D), i32(_lib.F32),
+             stream_ptr())
+        return dx.view(ctx.shape), dwb[:D], dwb[D:], None
+
+
+class TokenEmbeddingFn(torch.autograd.Function):
+    """nn.Embedding lookup whose backward is one index_add (atomics) instead of torch's sort-based path:
+    the Uni-Mol dictionary has 31 rows, so the sorted segmented reduction is pure overhead."""
+
+    @staticmethod
+    def forward(ctx, tokens, weight, padding_idx):
+        ctx.save_for_backward(tokens)
+        ctx.meta = (weight.shape, padding_idx)
+        return weight[tokens]
+
+    @staticmethod
+    def backward(ctx, g):
+        (tokens,) = ctx.saved_tensors
+        shape, padding_idx = ctx.meta
+        gw = torch.zeros(shape, device=g.device, dtype=g.dtype)
+        gw.index_add_(0, tokens.reshape(-1), g.reshape(-1, shape[1]))
+        if padding_idx is not None:
+            gw[padding_idx].zero_()
+        return None, gw, None
+
+
 class EncoderLayerFn(torch.autograd.Function):
     """One pre-LN Uni-Core TransformerEncoderLayer with return_attn=True (SURVEY.md Appendix A;
     call site models/transformers.py:136-139) as a single autograd node with a hand-written
