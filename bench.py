@@ -166,8 +166,13 @@ def run_ours(args, rank, local_rank, world):
     tokens, dmat, et, g = make_batch(1234 + rank)
     pin = [t.pin_memory() for t in (tokens, dmat, et)]
     d_tokens, d_dist, d_et, d_g = tokens.to(dev), dmat.to(dev), et.to(dev), g.to(dev)
-    # Adam(eps 1e-6) as in tasks/trainer.py:160; fused + capturable so that it can live inside the CUDA graph
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
+    # Adam(eps 1e-6) as in tasks/trainer.py:160: mmdti_b200.optim.FusedAdam = one launch per step that also refreshes
+    # the bf16 shadows of the encoder's GEMM weights (--torch-adam: torch.optim.Adam(fused=True) + per-step cast pass)
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
+    else:
+        from mmdti_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=1e-4, eps=1e-6, shadows=model.encoder.use_external_lowp())
 
     params = [prm for prm in model.parameters() if prm.requires_grad]
 
@@ -291,7 +296,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms", "per_gpu_batch": B_PER_GPU,
                        "global_batch": B_PER_GPU * world, "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS,
                        "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
-                       "optimizer": "Adam(eps=1e-6), torch fused", "cuda_graph": bool(use_graph),
+                       "optimizer": "Adam(eps=1e-6), " + ("torch fused" if args.torch_adam else "mmdti FusedAdam (one launch, writes bf16 weight shadows)"),
+                       "cuda_graph": bool(use_graph),
                        "parallelism": "dp%d" % world,
                        "grad_exchange": (None if world == 1 else ("NCCL all-reduce of flat 64 MB buckets inside the graph" if use_graph
                                                                   else "DistributedDataParallel (NCCL)")),
@@ -331,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of mmdti_b200.optim.FusedAdam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

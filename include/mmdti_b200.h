@@ -304,6 +304,19 @@ int mmdti_fds_ema(const float* count, const float* sum1, const float* m2, float*
 int mmdti_fds_window(const float* in, const float* window, float* out, int nb, int D, int ks,
                      void* stream);
 
+/* ---------------------------------------------------------------- fused multi-tensor Adam
+ * torch.optim.Adam as the reference configures it (tasks/trainer.py:160-162: Adam(lr, eps=1e-6); no weight decay,
+ * no amsgrad) in ONE launch over every parameter tensor:
+ *   table  (ntensors, 6) int64 on the device: {p, g, m, v, lowp, numel}; p,g,m,v f32 device pointers, lowp a bf16
+ *          device pointer or 0 — when given, the bf16 copy of the updated weight is written in the same pass;
+ *   chunks (nchunks, 2) int32 on the device: {tensor index, first element}; one CTA per chunk of
+ *          mmdti_adam_chunk() elements;
+ *   step   device int64: the 1-based step count t (kept on the device so that CUDA-graph replays advance it);
+ *   grad_scale multiplies every gradient first (1/world for summed data-parallel gradients). */
+int mmdti_adam_chunk(void);
+int mmdti_adam_step(const int64_t* table, const int32_t* chunks, int nchunks, const int64_t* step, double lr,
+                    double beta1, double beta2, double eps, double grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -765,3 +765,78 @@ extern "C" int mmdti_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t se
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }
+
+// ------------------------------------------------------------------ fused multi-tensor Adam
+// torch.optim.Adam semantics (tasks/trainer.py:160-162: Adam(lr, eps=1e-6), no weight decay, no amsgrad):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// ONE launch over every parameter: `table` holds per tensor {p, g, m, v, lowp, numel} (device pointers as int64),
+// `chunks` maps a CTA to (tensor, first element).  The step count t lives on the device (CUDA-graph replays).
+// When lowp != 0 the bf16 shadow of the updated weight is written in the same pass (the encoder's GEMM operands),
+// which removes the separate fp32 -> bf16 cast pass of every step.
+namespace {
+constexpr int ADAM_CHUNK = 16384;        // elements per CTA
+__global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ chunks,
+                                                         const long long* __restrict__ step_ptr, float lr, float beta1,
+                                                         float beta2, float omb1, float omb2, float eps, float grad_scale) {
+    const int ti = chunks[2 * blockIdx.x], start = chunks[2 * blockIdx.x + 1];
+    const long long* row = table + 6LL * ti;
+    float* p = reinterpret_cast<float*>(row[0]);
+    const float* g = reinterpret_cast<const float*>(row[1]);
+    float* m = reinterpret_cast<float*>(row[2]);
+    float* v = reinterpret_cast<float*>(row[3]);
+    bf16* lp = reinterpret_cast<bf16*>(row[4]);
+    const long long n = row[5];
+    const float t = (float)(*step_ptr);
+    const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const long long end = min(n, (long long)start + ADAM_CHUNK);
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (!lp || (reinterpret_cast<uintptr_t>(lp) & 7) == 0);
+    if (vec) {
+        for (long long i = start + threadIdx.x * 4LL; i + 3 < end; i += 256 * 4) {
+            float4 pv = *reinterpret_cast<float4*>(p + i), mv = *reinterpret_cast<float4*>(m + i), vv = *reinterpret_cast<float4*>(v + i);
+            const float4 gv = *reinterpret_cast<const float4*>(g + i);
+            float pe[4] = {pv.x, pv.y, pv.z, pv.w}, me[4] = {mv.x, mv.y, mv.z, mv.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
+            const float ge[4] = {gv.x * grad_scale, gv.y * grad_scale, gv.z * grad_scale, gv.w * grad_scale};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                me[e] = fmaf(beta1, me[e], omb1 * ge[e]);
+                ve[e] = fmaf(beta2, ve[e], omb2 * ge[e] * ge[e]);
+                pe[e] -= step_size * me[e] / (sqrtf(ve[e]) * inv_sqrt_bc2 + eps);
+            }
+            *reinterpret_cast<float4*>(p + i) = make_float4(pe[0], pe[1], pe[2], pe[3]);
+            *reinterpret_cast<float4*>(m + i) = make_float4(me[0], me[1], me[2], me[3]);
+            *reinterpret_cast<float4*>(v + i) = make_float4(ve[0], ve[1], ve[2], ve[3]);
+            if (lp) {
+                uint2 u;
+                u.x = pack_bf16(pe[0], pe[1]);
+                u.y = pack_bf16(pe[2], pe[3]);
+                *reinterpret_cast<uint2*>(lp + i) = u;
+            }
+        }
+    }
+    // scalar path: unaligned tensors, and the (< 4 element) tail of an aligned chunk
+    const long long tail0 = vec ? start + ((end - start) / 4) * 4 : start;
+    for (long long i = tail0 + threadIdx.x; i < end; i += 256) {
+        const float ge = g[i] * grad_scale;
+        const float me = fmaf(beta1, m[i], omb1 * ge), ve = fmaf(beta2, v[i], omb2 * ge * ge);
+        const float pe = p[i] - step_size * me / (sqrtf(ve) * inv_sqrt_bc2 + eps);
+        p[i] = pe; m[i] = me; v[i] = ve;
+        if (lp) lp[i] = __float2bfloat16_rn(pe);
+    }
+}
+}  // namespace
+
+extern "C" int mmdti_adam_chunk(void) { return ADAM_CHUNK; }
+
+extern "C" int mmdti_adam_step(const int64_t* table, const int32_t* chunks, int nchunks, const int64_t* step, double lr, double beta1,
+                               double beta2, double eps, double grad_scale, void* stream) {
+    MMDTI_REQUIRE(table && chunks && step && nchunks > 0, "adam_step: bad arguments");
+    MMDTI_REQUIRE(lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps > 0., "adam_step: bad hyper-parameters");
+    adam_multi_kernel<<<nchunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(table), chunks,
+                                                                           reinterpret_cast<const long long*>(step), (float)lr, (float)beta1,
+                                                                           (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                                           (float)eps, (float)grad_scale);
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}

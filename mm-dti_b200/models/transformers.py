@@ -60,11 +60,31 @@ class TransformerEncoderWithPair(nn.Module):
         pair = ops.PairPadFn.apply(attn_mask.reshape(bsz * H, seq_len, seq_len), bsz, H, seq_len, config.pair_dtype())
         return self.forward_padded(emb, pair, padding_mask)
 
+    def _gemm_params(self):
+        src = []
+        for layer in self.layers:
+            sa = layer.self_attn
+            src += [sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias, layer.fc1.weight,
+                    layer.fc1.bias, layer.fc2.weight, layer.fc2.bias]
+        return src
+
+    def use_external_lowp(self):
+        """Hand the bf16 shadows of the GEMM operands to an optimizer that refreshes them while it updates the
+        fp32 master weights (mmdti_b200.optim.FusedAdam(shadows=...)): forward then skips its per-step cast pass.
+        Returns {parameter: bf16 shadow}.  Call again after loading new weights."""
+        src = self._gemm_params()
+        shadows = [p.detach().to(torch.bfloat16) for p in src]
+        self._lowp_cache = shadows
+        self._lowp_external = True
+        return dict(zip(src, shadows))
+
     def _lowp_weights(self):
         """bf16 copies of every layer's GEMM operands, refreshed with one multi-tensor copy per step."""
         dt = config.act_dtype()
         if dt == torch.float32:
             return None
+        if getattr(self, "_lowp_external", False) and dt == torch.bfloat16:
+            return self._lowp_cache
         src = []
         for layer in self.layers:
             sa = layer.self_attn
