@@ -147,6 +147,9 @@ def run_ours(args, rank, local_rank, world):
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
+        # keep stdout to the ONE JSON line: NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     mmdti_b200.set_precision(act="bf16", pair=os.environ.get("MMDTI_PAIR", "bf16"))
