@@ -95,6 +95,88 @@ def allreduce_grads(params, group=None, average=True, bucket_bytes=64 << 20, asy
     return n_coll
 
 
+class OverlappedGradReducer:
+    """Exchange 2 overlapped with the backward pass: parameters are grouped into buckets of about ``bucket_bytes``
+    in REVERSE registration order (the order their gradients become ready); a post-accumulate-grad hook counts a
+    bucket down and, when it is complete, all-reduces it on a communication stream while the main stream keeps
+    running the rest of the backward.  ``finish()`` (call it after ``loss.backward()``) reduces whatever is left
+    (parameters that received no gradient contribute zeros) and joins the streams.  Every rank issues the same
+    collectives in the same order.  Works inside a CUDA-graph capture (the communication stream becomes a parallel
+    branch of the graph); on CPU tensors (gloo tests) the reduction runs synchronously."""
+
+    def __init__(self, params, group=None, average=True, bucket_bytes=32 << 20):
+        self.group, self.average = group, average
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(self.params):
+            nb = p.numel() * p.element_size()
+            if cur and (size + nb > bucket_bytes or p.dtype != cur[0].dtype):
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nb
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {p: i for i, b in enumerate(self.buckets) for p in b}
+        self.comm = torch.cuda.Stream(device=self.params[0].device) if self.params[0].is_cuda else None
+        self._reset()
+        self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        self.collectives = 0
+
+    def _reset(self):
+        self.pending = [len(b) for b in self.buckets]
+        self.done = [False] * len(self.buckets)
+
+    def _hook(self, p):
+        if self.world == 1:
+            return
+        i = self.bucket_of[p]
+        self.pending[i] -= 1
+        if self.pending[i] == 0 and not self.done[i]:
+            self._reduce(i)
+
+    def _reduce(self, i):
+        bucket = self.buckets[i]
+        for p in bucket:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+
+        def run():
+            flat = torch.cat([p.grad.reshape(-1) for p in bucket])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                flat.div_(self.world)
+            off = 0
+            for p in bucket:
+                n = p.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+
+        if self.comm is not None:
+            main = torch.cuda.current_stream(bucket[0].device)
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                run()
+        else:
+            run()
+        self.done[i] = True
+        self.collectives += 1
+
+    def finish(self):
+        if self.world > 1:
+            for i in range(len(self.buckets)):
+                if not self.done[i]:
+                    self._reduce(i)
+            if self.comm is not None:
+                torch.cuda.current_stream(self.params[0].device).wait_stream(self.comm)
+        self._reset()
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
 def shard_rows(n_total, rank, world):
     """[start, stop) of the rows a rank owns when n_total samples are split evenly."""
     if n_total % world:

@@ -52,6 +52,32 @@ def _worker(rank, world, port, q):
         for i, p in enumerate(net.parameters()):
             parts = [g[i] if g[i] is not None else torch.zeros_like(p) for g in gathered]
             assert torch.allclose(p.grad, sum(parts) / world, atol=1e-6), i
+        # overlapped (hook-driven) reducer: same averaged gradients, buckets launched from gradient hooks
+        from mmdti_b200.dist import OverlappedGradReducer
+        torch.manual_seed(0)
+        net2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4), torch.nn.Linear(4, 2))
+        red = OverlappedGradReducer(net2.parameters(), average=True, bucket_bytes=256)
+        assert len(red.buckets) >= 2
+        for it in range(2):                                       # two steps: the reducer re-arms itself
+            for prm in net2.parameters():
+                prm.grad = None
+            net2[1](net2[0](x * (it + 1))).sum().backward()       # net2[2] gets no gradient: finish() sends zeros
+            g_loc = [None if prm.grad is None else None for prm in net2.parameters()]
+            red.finish()
+            ref_net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4), torch.nn.Linear(4, 2))
+            ref_net.load_state_dict(net2.state_dict())
+            tot = [torch.zeros_like(prm) for prm in ref_net.parameters()]
+            for r in range(world):
+                xr = torch.randn(5, 8, generator=torch.Generator().manual_seed(r)) * (it + 1)
+                for prm in ref_net.parameters():
+                    prm.grad = None
+                ref_net[1](ref_net[0](xr)).sum().backward()
+                for t_, prm in zip(tot, ref_net.parameters()):
+                    if prm.grad is not None:
+                        t_ += prm.grad
+            for t_, prm in zip(tot, net2.parameters()):
+                assert torch.allclose(prm.grad, t_ / world, atol=1e-6)
+        assert red.collectives == 2 * len(red.buckets)
         q.put((rank, "ok"))
     except Exception as e:                                       # noqa: BLE001
         q.put((rank, "fail: %r" % (e,)))
