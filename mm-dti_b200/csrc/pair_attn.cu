@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
     };
 
     const bool do_drop = p.thresh16 != 0;
+    const unsigned long long eff_seed = do_drop ? rng_effective_seed(p.seed, p.seed_off) : 0ull;      // once per kernel
     if (w0 < w1) prefetch(w0, 0);
 
     int it = 0;
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
             // dropout: one hash per 4 elements; the odd column's 16 bits are compared in place (bits >= t << 16),
             // the even column's after one shift
             if (do_drop) {
-                const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
+                const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
                 const uint32_t thi = p.thresh16 << 16;
 #pragma unroll
                 for (int kb = 0; kb < NKB; kb += 2) {
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
             }
             suma = quad_sum(suma);
             sumb = quad_sum(sumb);
-            const float inva = p.keep_scale / suma, invb = p.keep_scale / sumb;
+            const float inva = F32 ? p.keep_scale / suma : p.keep_scale * fast_rcp(suma);
+            const float invb = F32 ? p.keep_scale / sumb : p.keep_scale * fast_rcp(sumb);
             T* og = static_cast<T*>(p.o) + (size_t)b * L * p.ldo + h * HD;
 
             // ---- O = A' V
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             if (i < L) cp_head_row(stage(s).K + i * HD, kg + (size_t)i * p.ldqkv);
             else if (i < 2 * L) cp_head_row(stage(s).V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
             else {
-                const int j = i - 2 * L, which = j / nrows, r = j - which * nrows;
+                const int j = i - 2 * L, which = j >= 2 * nrows ? 2 : (j >= nrows ? 1 : 0), r = j - which * nrows;
                 if (which == 0) cp_head_row(stage(s).Q + r * HD, qg + (size_t)(row0 + r) * p.ldqkv);
                 else if (which == 1) cp_head_row(stage(s).dO + r * HD, dog + (size_t)(row0 + r) * p.lddo);
                 else cp_head_row(stage(s).O + r * HD, og + (size_t)(row0 + r) * p.lddo);
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
     };
 
     const bool do_drop = p.thresh16 != 0;
+    const unsigned long long eff_seed = do_drop ? rng_effective_seed(p.seed, p.seed_off) : 0ull;      // once per kernel
     float dk_acc[MAXKB16][4], dv_acc[MAXKB16][4];
 
     if (w0 < w1) prefetch(w0, 0);
@@ -575,8 +578,8 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             suma = quad_sum(suma);
             sumb = quad_sum(sumb);
             // rows beyond L (stale slab rows) get A = 0
-            const float inva = (va_ok && suma > 0.f) ? 1.f / suma : 0.f;
-            const float invb = (vb_ok && sumb > 0.f) ? 1.f / sumb : 0.f;
+            const float inva = (va_ok && suma > 0.f) ? (F32 ? 1.f / suma : fast_rcp(suma)) : 0.f;
+            const float invb = (vb_ok && sumb > 0.f) ? (F32 ? 1.f / sumb : fast_rcp(sumb)) : 0.f;
 
             // ---- delta = dO . O per row; dO fragments
             float dela, delb;
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             delb = quad_sum(delb);
 
             // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
-            const uint32_t rkey = rng_stream_key(rng_effective_seed(p.seed, p.seed_off), (uint32_t)tile);
+            const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
             const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
             uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
 #pragma unroll
