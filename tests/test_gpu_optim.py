@@ -40,7 +40,8 @@ def test_fused_adam_under_cuda_graph():
     pa, pb = _params(3), _params(3)
     ref = torch.optim.Adam(pa, lr=1e-3, eps=1e-6)
     mine = FusedAdam(pb, lr=1e-3, eps=1e-6)
-    grads = [torch.randn_like(p) for p in pb]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    grads = [torch.randn(p.shape, device="cuda", generator=gen) for p in pb]
     for p, g in zip(pb, grads):
         p.grad = g                              # static gradient buffers, as in a captured training step
     s = torch.cuda.Stream()
@@ -60,4 +61,4 @@ def test_fused_adam_under_cuda_graph():
     torch.cuda.synchronize()
     assert int(mine.step_count.item()) == 4
     for a, b in zip(pa, pb):
-        assert rel_err(b, a) < 1e-5
+        assert (b - a).abs().max().item() < 1e-6 + 1e-5 * a.abs().max().item()      # lr = 1e-3: updates are O(1e-3)
