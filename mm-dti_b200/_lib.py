@@ -64,10 +64,12 @@ def call(name, *args):
     """Invoke an `int mmdti_*(...)` entry point; tensors -> device pointers; raises on error."""
     global launch_count
     fn = getattr(lib(), name)
+    cargs = [_arg(a_) for a_ in args]
     if _timeline is not None:
+        # events hug the launch: arguments are marshalled first so that host-side work is not inside the bracket
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-    rc = fn(*[_arg(a_) for a_ in args])
+    rc = fn(*cargs)
     if rc != 0:
         raise MMDTIError("%s failed (%d): %s" % (name, rc, lib().mmdti_last_error().decode()))
     if _timeline is not None:
