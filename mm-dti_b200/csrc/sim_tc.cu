@@ -56,6 +56,7 @@ int num_sms() {
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void mbar_wait_g(uint64_t* bar, uint32_t parity) {
     // bounded wait: a pipeline bug traps instead of hanging the GPU
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         uint32_t done;
         asm volatile(
@@ -183,35 +184,38 @@ struct TcConst {
     float inv_t, k2, k2t, w_thr, e_push;    // k2 = log2(e)/t, k2t = k2 (exponent shift of InfoNCE: exp(z - 1/t))
 };
 
-// ---- phase 1, one similarity value (column c of the tile, global key j)
+// ---- phase 1, one similarity value (column c of the tile, global key j).  Branch-free: every update is a
+// select + accumulate, so a warp whose lanes see different masks does not serialise (the epilogue warps are the
+// pacing stage for SupCon / ConR).  Counts are integers, the positive logits are summed un-scaled.
+struct P1Acc {
+    float e_pos, e_neg, sdot;
+    int n_pos, n_neg;
+};
 template <int MODE>
-__device__ __forceinline__ void p1_elem(const TcConst& k, const RowCtx& r, const ColMeta& m, RowAcc& acc, float dot, int j, int c) {
+__device__ __forceinline__ void p1_elem(const TcConst& k, const RowCtx& r, const ColMeta& m, P1Acc& a, float dot, int j, int c) {
     if (MODE == SIM_INFONCE) {
-        acc.v[0] += ex2f(fmaf(dot, k.k2, -k.k2t));
-        if (r.gi == j) acc.v[1] += dot * k.inv_t;
+        a.e_pos += ex2f(fmaf(dot, k.k2, -k.k2t));
+        a.sdot += (r.gi == j) ? dot : 0.f;
     } else {
         bool pos, neg;
-        float w = r.wr * m.wc[c];
+        float w = r.wr * m.wc[c];                 // r.wr carries e_push in the regression mode
         if (MODE == SIM_REGRESS) {
             const float l = fabsf(__fsub_rn(r.y, m.y[c])), pd = fabsf(__fsub_rn(r.yh, m.yh[c]));
             const bool close = l <= k.w_thr;
             pos = close && (r.gi != j);
             neg = (!close) && (pd <= k.w_thr);
-            w = l * w * k.e_push;
+            w *= l;
         } else {
             const bool same = r.key == m.key[c];
             pos = same && (r.gi != j);
             neg = !same;
         }
         const float e = ex2f(dot * k.k2);
-        if (pos) {
-            acc.v[0] += e;
-            acc.v[2] += 1.f;
-            acc.v[4] = fmaf(dot, k.inv_t, acc.v[4]);
-        } else if (neg) {
-            acc.v[1] = fmaf(w, e, acc.v[1]);
-            acc.v[3] += 1.f;
-        }
+        a.e_pos += pos ? e : 0.f;
+        a.sdot += pos ? dot : 0.f;
+        a.n_pos += pos ? 1 : 0;
+        a.e_neg = fmaf(neg ? w : 0.f, e, a.e_neg);
+        a.n_neg += neg ? 1 : 0;
     }
 }
 // ---- phase 2, gradient coefficient H_ij
@@ -306,26 +310,28 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (lane == 0) {
             mbar_arrive_expect_tx(a_full, (uint32_t)(nkc * A_CHUNK_BYTES));
             for (int kc = 0; kc < nkc; ++kc) tma_load_2d(sA + kc * A_CHUNK_BYTES, &tmA, kc * CHUNK_K, i0, a_full);
+            // ring positions are carried as (slot, parity) counters: no runtime divisions in the single-thread loops
+            int st = 0, par = 1;                    // par = parity of the PREVIOUS use of the slot (first pass: nothing to wait for)
+            bool wrapped = false;
             if (PHASE == 1) {
                 // K-chunk ring: every stage holds one (BN keys x 64) chunk; many small loads in flight
-                int idx = 0;
                 for (int t = 0; t < T; ++t) {
                     const int j0 = (t_begin + t) * BN;
-                    for (int kc = 0; kc < nkc; ++kc, ++idx) {
-                        const int st = idx % nstage, use = idx / nstage;
-                        if (use > 0) mbar_wait_g(&empty[st], (use - 1) & 1);
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        if (wrapped) mbar_wait_g(&empty[st], par);
                         mbar_arrive_expect_tx(&full[st], lay.b_stage_bytes);
                         tma_load_2d(sB + (size_t)st * lay.b_stage_bytes, &tmB, kc * CHUNK_K, j0, &full[st]);
+                        if (++st == nstage) { st = 0; par ^= 1; wrapped = true; }
                     }
                 }
             } else {
                 for (int t = 0; t < T; ++t) {
-                    const int st = t % nstage, use = t / nstage;
-                    if (use > 0) mbar_wait_g(&empty[st], (use - 1) & 1);
+                    if (wrapped) mbar_wait_g(&empty[st], par);
                     mbar_arrive_expect_tx(&full[st], lay.b_stage_bytes);
                     unsigned char* dst = sB + (size_t)st * lay.b_stage_bytes;
                     const int j0 = (t_begin + t) * BN;
                     for (int kc = 0; kc < nkc; ++kc) tma_load_2d(dst + kc * BN * 128, &tmB, kc * CHUNK_K, j0, &full[st]);
+                    if (++st == nstage) { st = 0; par ^= 1; wrapped = true; }
                 }
             }
         }
@@ -335,56 +341,66 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             constexpr uint32_t idesc_s = instr_desc(BN, 0);
             const uint32_t idesc_d = instr_desc(ND > 0 ? ND : 16, 1);
             const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB), h_addr = smem_u32(sH);
+            // descriptors are built once; the loops only add (byte offset >> 4) to the 14-bit start-address field
+            // (the issuing thread is a single dependent instruction stream: every ALU op here delays the tensor pipe)
+            const uint64_t adesc0 = smem_desc(a_addr, 16, 1024);
+            const uint64_t bdesc0 = smem_desc(b_addr, 16, 1024);                                               // K-major keys (MMA1)
+            const uint64_t bdesc2 = smem_desc(b_addr + (dcol0 / CHUNK_K) * BN * 128, BN * 128, 1024);          // MN-major keys (MMA2)
+            const uint64_t hdesc0 = BN == 32 ? smem_desc(h_addr, 16, 512, 4) : smem_desc(h_addr, 16, 1024);
+            const uint32_t stage16 = lay.b_stage_bytes >> 4;
+            int st2 = 0;                            // ring slot of the tile whose MMA2 is issued next
             auto mma2 = [&](int u) {
-                const int hb = u & 1, st = u % nstage;
+                const int hb = u & 1;
                 mbar_wait_g(&h_full[hb], (u >> 1) & 1);
                 tc_fence_after();
-                const uint32_t bst = b_addr + st * lay.b_stage_bytes + (dcol0 / CHUNK_K) * BN * 128;
-                const uint32_t hst = h_addr + hb * h_buf_bytes(BN);
+                const uint64_t bst = bdesc2 + (uint64_t)(st2 * stage16);
+                const uint64_t hst = hdesc0 + (uint64_t)(hb * (h_buf_bytes(BN) >> 4));
 #pragma unroll
                 for (int ks = 0; ks < BN / 16; ++ks) {
-                    const uint64_t ad = BN == 32 ? smem_desc(hst + ks * 32, 16, 512, 4)
-                                                 : smem_desc(hst + (ks >> 2) * H_ATOM_BYTES + (ks & 3) * 32, 16, 1024);
-                    const uint64_t bd = smem_desc(bst + ks * 16 * 128, BN * 128, 1024);
+                    const uint64_t ad = BN == 32 ? hst + (uint64_t)(ks * 2) : hst + (uint64_t)((ks >> 2) * (H_ATOM_BYTES >> 4) + (ks & 3) * 2);
+                    const uint64_t bd = bst + (uint64_t)(ks * 16 * 128 >> 4);
                     tc_mma(tmem_base + TMEM_DA_COL, ad, bd, idesc_d, (u > 0 || ks > 0) ? 1u : 0u);
                 }
                 tc_commit(&h_empty[hb]);
-                tc_commit(&empty[st]);
+                tc_commit(&empty[st2]);
+                if (++st2 == nstage) st2 = 0;
             };
             mbar_wait_g(a_full, 0);
-            int idx = 0;
+            int st = 0;
+            uint32_t par = 0;
             for (int t = 0; t < T; ++t) {
                 const int buf = t & 1;
+                const uint32_t d_s = tmem_base + buf * BN;
                 if (t >= 2) mbar_wait_g(&s_empty[buf], ((t >> 1) - 1) & 1);
                 if (PHASE == 1) {
-                    for (int kc = 0; kc < nkc; ++kc, ++idx) {
-                        const int st = idx % nstage;
-                        mbar_wait_g(&full[st], (idx / nstage) & 1);
+                    uint64_t ad = adesc0;
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        mbar_wait_g(&full[st], par);
                         tc_fence_after();
-                        const uint32_t bst = b_addr + st * lay.b_stage_bytes;
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint64_t ad = smem_desc(a_addr + kc * A_CHUNK_BYTES + k4 * 32, 16, 1024);
-                            const uint64_t bd = smem_desc(bst + k4 * 32, 16, 1024);
-                            tc_mma(tmem_base + buf * BN, ad, bd, idesc_s, (kc > 0 || k4 > 0) ? 1u : 0u);
-                        }
+                        const uint64_t bd = bdesc0 + (uint64_t)(st * stage16);
+                        tc_mma(d_s, ad, bd, idesc_s, kc > 0 ? 1u : 0u);
+                        tc_mma(d_s, ad + 2, bd + 2, idesc_s, 1u);
+                        tc_mma(d_s, ad + 4, bd + 4, idesc_s, 1u);
+                        tc_mma(d_s, ad + 6, bd + 6, idesc_s, 1u);
                         tc_commit(&empty[st]);
+                        ad += A_CHUNK_BYTES >> 4;
+                        if (++st == nstage) { st = 0; par ^= 1u; }
                     }
                     tc_commit(&s_full[buf]);
                 } else {
-                    const int st = t % nstage;
-                    mbar_wait_g(&full[st], (t / nstage) & 1);
+                    mbar_wait_g(&full[st], par);
                     tc_fence_after();
-                    const uint32_t bst = b_addr + st * lay.b_stage_bytes;
+                    uint64_t ad = adesc0, bd = bdesc0 + (uint64_t)(st * stage16);
                     for (int kc = 0; kc < nkc; ++kc) {
-#pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {
-                            const uint64_t ad = smem_desc(a_addr + kc * A_CHUNK_BYTES + k4 * 32, 16, 1024);
-                            const uint64_t bd = smem_desc(bst + kc * BN * 128 + k4 * 32, 16, 1024);
-                            tc_mma(tmem_base + buf * BN, ad, bd, idesc_s, (kc > 0 || k4 > 0) ? 1u : 0u);
-                        }
+                        tc_mma(d_s, ad, bd, idesc_s, kc > 0 ? 1u : 0u);
+                        tc_mma(d_s, ad + 2, bd + 2, idesc_s, 1u);
+                        tc_mma(d_s, ad + 4, bd + 4, idesc_s, 1u);
+                        tc_mma(d_s, ad + 6, bd + 6, idesc_s, 1u);
+                        ad += A_CHUNK_BYTES >> 4;
+                        bd += (uint64_t)(BN * 128 >> 4);
                     }
                     tc_commit(&s_full[buf]);
+                    if (++st == nstage) { st = 0; par ^= 1u; }
                     if (t > 0) mma2(t - 1);
                 }
             }
@@ -430,6 +446,11 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         RowAcc racc;
         racc.clear();
+        P1Acc pacc;
+        pacc.e_pos = pacc.e_neg = pacc.sdot = 0.f;
+        pacc.n_pos = pacc.n_neg = 0;
+        RowCtx rc1 = rc;                                 // phase-1 view of the row constants
+        if (MODE == SIM_REGRESS) rc1.wr = rc.wr * aux.e_push;
         float gri0 = 0.f, gri1 = 0.f;                    // un-scaled row statistics for the generic (tail / multi) path
         if (PHASE == 2 && row_ok) {
             if (MODE == SIM_INFONCE) gri0 = aux.rs_row[i0 + r];
@@ -475,7 +496,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     if (row_ok) {
                         if (fast) {
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) p1_elem<MODE>(kc, rc, cm, racc, __uint_as_float(v[c]), j0 + c0 + c, c0 + c);
+                            for (int c = 0; c < NC; ++c) p1_elem<MODE>(kc, rc1, cm, pacc, __uint_as_float(v[c]), j0 + c0 + c, c0 + c);
                         } else {
 #pragma unroll
                             for (int c = 0; c < NC; ++c) {
@@ -519,6 +540,16 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
         }
         if (PHASE == 1) {
+            if (MODE == SIM_INFONCE) {
+                racc.v[0] += pacc.e_pos;
+                racc.v[1] = fmaf(pacc.sdot, kc.inv_t, racc.v[1]);
+            } else {
+                racc.v[0] += pacc.e_pos;
+                racc.v[1] += pacc.e_neg;
+                racc.v[2] += (float)pacc.n_pos;
+                racc.v[3] += (float)pacc.n_neg;
+                racc.v[4] = fmaf(pacc.sdot, kc.inv_t, racc.v[4]);
+            }
             if (row_ok) {
                 float* dst = p.out + (long long)(i0 + r) * SIM_NSTAT;
 #pragma unroll
@@ -594,6 +625,7 @@ int launch_bn(const void* A, const void* B, int M, int N, int Dp, int D, const S
               cudaStream_t st) {
     const int nkc = Dp / CHUNK_K;
     int nstage = MAX_STAGES;
+    if (const char* e = getenv("MMDTI_SIM_STAGES")) nstage = std::max(2, std::min(MAX_STAGES, atoi(e)));      // tuning knob
     SmemLayout lay = smem_layout(nkc, BN, nstage, PHASE);
     while (nstage > 2 && lay.total + 1024 > 227 * 1024) lay = smem_layout(nkc, BN, --nstage, PHASE);
     if (lay.total + 1024 > 227 * 1024) { mmdti_set_error("sim_tc: shared memory budget exceeded (Dp=%d BN=%d)", Dp, BN); return MMDTI_ERR_ARG; }
@@ -635,7 +667,13 @@ template <int PHASE>
 int launch(const void* A, const void* B, int M, int N, int Dp, int D, const SimAux& aux, float* out, long long ldout, cudaStream_t st) {
     MMDTI_REQUIRE(Dp >= 64 && Dp <= 512 && Dp % 64 == 0, "sim_tc: Dp must be a multiple of 64 in [64, 512] (got %d)", Dp);
     MMDTI_REQUIRE(mmdti_aligned(A, 16) && mmdti_aligned(B, 16), "sim_tc: operands must be 16-byte aligned");
-    if (PHASE == 1 || Dp <= 128) return launch_bn<PHASE, 128>(A, B, M, N, Dp, D, aux, out, ldout, st);
+    if constexpr (PHASE == 1) {
+        // 256-key tiles halve the MMA instructions per flop (the single issuing thread, not the tensor pipe, paces
+        // 128-key tiles); small N keeps 128-key tiles for parallelism
+        if (N >= 4096 && !getenv("MMDTI_SIM_BN128")) return launch_bn<PHASE, 256>(A, B, M, N, Dp, D, aux, out, ldout, st);
+        return launch_bn<PHASE, 128>(A, B, M, N, Dp, D, aux, out, ldout, st);
+    }
+    if (Dp <= 128) return launch_bn<PHASE, 128>(A, B, M, N, Dp, D, aux, out, ldout, st);
     if (Dp <= 256) return launch_bn<PHASE, 64>(A, B, M, N, Dp, D, aux, out, ldout, st);
     return launch_bn<PHASE, 32>(A, B, M, N, Dp, D, aux, out, ldout, st);
 }

@@ -112,6 +112,33 @@ def test_losses_vs_oracle_ragged_sizes(N, D, mode, ltol, gtol, report):
         assert e[0] < ltol * 2 and all(v < gtol * 2 for v in e[1:]), (name, e)
 
 
+@pytest.mark.parametrize("N,D", [(4096, 512), (4396, 136)])
+def test_large_n_tensor_core_tiles_match_fp32_kernels(N, D, report):
+    """N >= 4096 switches phase 1 to 256-key tiles (sim_tc.cu); the fp32 validation kernels, themselves checked against
+    the oracle at small N above, are the reference here (the oracle would need an N x N fp32 matrix per loss)"""
+    f, y, yhat, w, cls = _rand_case(N, D, 11 + N)
+    f2 = torch.randn(N, D, generator=torch.Generator().manual_seed(N))
+    out = {}
+    for mode in ("fp32", "bf16"):
+        res = []
+        for name in ("infonce", "conr", "supcon"):
+            ac, bc = f.cuda().requires_grad_(True), (0.5 * f + f2).cuda().requires_grad_(True)
+            with mmdti_b200.precision(act=mode):
+                if name == "infonce":
+                    loss = infm.info_nce(ac, bc, temperature=0.1)
+                elif name == "conr":
+                    loss = ctm.CT_Regress(ac, y.cuda(), yhat.cuda(), weights=w.cuda(), w=0.2)
+                else:
+                    loss = ctm.CT_Single(ac, cls.cuda(), None)
+                loss.backward()
+            res.append((name, loss.detach(), ac.grad.clone(), bc.grad.clone() if name == "infonce" else None))
+        out[mode] = res
+    for (name, l32, g32, gb32), (_, l16, g16, gb16) in zip(out["fp32"], out["bf16"]):
+        e = [rel_err(l16, l32), norm_err(g16, g32)] + ([norm_err(gb16, gb32)] if gb32 is not None else [])
+        report("sim-large-n", name, N, D, *("%.2e" % v for v in e))
+        assert e[0] < 4e-3 and all(v < 4e-2 for v in e[1:]), (name, e)
+
+
 def test_infonce_value_errors():
     for bad in ((torch.randn(4), torch.randn(4, 3)), (torch.randn(4, 3), torch.randn(5, 3)),
                 (torch.randn(4, 3), torch.randn(4, 2))):
