@@ -252,6 +252,17 @@ int mmdti_sim_grad_tc(const void* A, const void* B, int M, int N, int Dp, int ro
                       const int64_t* key, int C, float coef_multi, const float* wrow,
                       const float* wcol, const float* rs_row, const float* rs_col, float* dA,
                       int64_t lddA, void* stream);
+
+/* Gradient coefficients alone (tensor cores): H (M, ldh) bf16, H_ij as in mmdti_sim_grad_*; columns [N, ldh) of a row are
+ * written as zeros or left untouched.  With dA = H . B (a plain GEMM) this is the two-step form of phase 2 that large
+ * N x 512-d problems use: the 512-column TMEM cannot hold the dA accumulators (512 columns at D = 512) next to a
+ * similarity tile, so the fused kernel has to evaluate every H_ij once per 128/256-column slice of dA.
+ * Same argument meaning as mmdti_sim_grad_tc; ldh >= N, ldh % 8 == 0.  Replaces the autograd backward of
+ * models/infonce.py:91-98 and models/contrastive.py:55-60,110-115 up to the final H . B product. */
+int mmdti_sim_coef_tc(const void* A, const void* B, int M, int N, int Dp, int row_offset, int mode, float temperature,
+                      const float* y, const float* yhat, float w_thr, float e_push, const int64_t* key, int C,
+                      float coef_multi, const float* wrow, const float* wcol, const float* rs_row, const float* rs_col,
+                      void* H, int64_t ldh, void* stream);
 /* InfoNCE: stats (M,8) -> lse (M) = log sum_j exp(z_ij); *loss += scale * sum_i (lse_i - z_ii). */
 int mmdti_infonce_finalize(const float* stats, float* lse, float* loss, int M, float temperature,
                            float scale, void* stream);

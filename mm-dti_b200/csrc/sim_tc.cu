@@ -124,6 +124,8 @@ struct TcParams {
     float* out;          // phase 1: stats (M, 8); phase 2: dA (M, ldout)
     long long ldout;
     int M, D, nkc, nstage, tiles_per_split, use_atomics;
+    __nv_bfloat16* hout; // phase 3: H tiles (M, ldh) bf16
+    long long ldh;
 };
 
 constexpr int NUM_EPI_WARPS = 8;            // two warps per TMEM lane quadrant, each takes half of the tile's columns
@@ -144,7 +146,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nkc, int bn, int nstage, i
     SmemLayout s;
     s.a_off = 0;
     s.b_off = nkc * A_CHUNK_BYTES;
-    s.b_stage_bytes = (phase == 1 ? 1 : nkc) * bn * 128;      // phase 1 streams single 64-wide K chunks, phase 2 whole key tiles
+    s.b_stage_bytes = (phase != 2 ? 1 : nkc) * bn * 128;      // phases 1 / 3 stream single 64-wide K chunks, phase 2 whole key tiles
     s.h_off = s.b_off + nstage * s.b_stage_bytes;
     const uint32_t h_bytes = phase == 2 ? 2u * h_buf_bytes(bn) : 0u;
     s.meta_off = s.h_off + h_bytes;
@@ -218,34 +220,31 @@ __device__ __forceinline__ void p1_elem(const TcConst& k, const RowCtx& r, const
         a.n_neg += neg ? 1 : 0;
     }
 }
-// ---- phase 2, gradient coefficient H_ij
+// ---- phases 2 / 3, gradient coefficient H_ij (branch-free).  Row constants are pre-combined by the caller:
+//   r.ri0 = c_i, r.ri1 = alpha_i, r.wr = alpha_i * wrow_i (* e_push), r.wc = wcol_i (* e_push);
+//   per column: m.rs0 = c_j, m.rs1 = alpha_j, m.wr = alpha_j * wrow_j, m.wc = wcol_j.
 template <int MODE>
 __device__ __forceinline__ float p2_elem(const TcConst& k, const RowCtx& r, const ColMeta& m, float dot, int j, int c) {
     if (MODE == SIM_INFONCE) {       // ri0 / rs0 hold lse * log2(e)
-        float h = ex2f(fmaf(dot, k.k2, -r.ri0)) + ex2f(fmaf(dot, k.k2, -m.rs0[c]));
-        if (r.gi == j) h -= 2.f;
-        return h;
+        const float h = ex2f(fmaf(dot, k.k2, -r.ri0)) + ex2f(fmaf(dot, k.k2, -m.rs0[c]));
+        return h - ((r.gi == j) ? 2.f : 0.f);
     }
     bool pos, neg;
-    float wij = r.wr * m.wc[c], wji = m.wr[c] * r.wc;
+    float e = ex2f(dot * k.k2);
+    const float hp = fmaf(r.ri1 + m.rs1[c], e, -(r.ri0 + m.rs0[c]));
     if (MODE == SIM_REGRESS) {
         const float l = fabsf(__fsub_rn(r.y, m.y[c])), pd = fabsf(__fsub_rn(r.yh, m.yh[c]));
         const bool close = l <= k.w_thr;
         pos = close && (r.gi != j);
         neg = (!close) && (pd <= k.w_thr);
-        wij = l * wij * k.e_push;
-        wji = l * wji * k.e_push;
+        e *= l;
     } else {
         const bool same = r.key == m.key[c];
         pos = same && (r.gi != j);
         neg = !same;
     }
-    const float e = ex2f(dot * k.k2);
-    const float cj = m.rs0[c], aj = m.rs1[c];
-    float h = 0.f;
-    if (pos) h = fmaf(r.ri1 + aj, e, -(r.ri0 + cj));
-    else if (neg) h = fmaf(r.ri1, wij, aj * wji) * e;
-    return h;
+    const float hn = fmaf(r.wr, m.wc[c], r.wc * m.wr[c]) * e;
+    return pos ? hp : (neg ? hn : 0.f);
 }
 
 template <int PHASE, int BN, int MODE>
@@ -279,6 +278,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int T = min(ntiles_all, t_begin + p.tiles_per_split) - t_begin;      // tiles of this CTA (>= 1)
     const int dcol0 = PHASE == 2 ? blockIdx.z * 256 : 0;
     const int ND = PHASE == 2 ? min(nkc * CHUNK_K - dcol0, 256) : 0;          // output columns of this CTA
+    constexpr uint32_t da_col = TMEM_DA_COL;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -313,7 +313,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // ring positions are carried as (slot, parity) counters: no runtime divisions in the single-thread loops
             int st = 0, par = 1;                    // par = parity of the PREVIOUS use of the slot (first pass: nothing to wait for)
             bool wrapped = false;
-            if (PHASE == 1) {
+            if (PHASE != 2) {
                 // K-chunk ring: every stage holds one (BN keys x 64) chunk; many small loads in flight
                 for (int t = 0; t < T; ++t) {
                     const int j0 = (t_begin + t) * BN;
@@ -359,7 +359,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 for (int ks = 0; ks < BN / 16; ++ks) {
                     const uint64_t ad = BN == 32 ? hst + (uint64_t)(ks * 2) : hst + (uint64_t)((ks >> 2) * (H_ATOM_BYTES >> 4) + (ks & 3) * 2);
                     const uint64_t bd = bst + (uint64_t)(ks * 16 * 128 >> 4);
-                    tc_mma(tmem_base + TMEM_DA_COL, ad, bd, idesc_d, (u > 0 || ks > 0) ? 1u : 0u);
+                    tc_mma(tmem_base + da_col, ad, bd, idesc_d, (u > 0 || ks > 0) ? 1u : 0u);
                 }
                 tc_commit(&h_empty[hb]);
                 tc_commit(&empty[st2]);
@@ -372,7 +372,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 const int buf = t & 1;
                 const uint32_t d_s = tmem_base + buf * BN;
                 if (t >= 2) mbar_wait_g(&s_empty[buf], ((t >> 1) - 1) & 1);
-                if (PHASE == 1) {
+                if (PHASE != 2) {
                     uint64_t ad = adesc0;
                     for (int kc = 0; kc < nkc; ++kc) {
                         mbar_wait_g(&full[st], par);
@@ -439,10 +439,16 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 if (aux.wrow) rc.wr = aux.wrow[gi];
                 if (aux.wcol) rc.wc = aux.wcol[gi];
             }
-            if (PHASE == 2) {
+            if (PHASE >= 2) {
                 if (MODE == SIM_INFONCE) rc.ri0 = aux.rs_row[i0 + r] * LOG2E_F;
                 else { rc.ri0 = aux.rs_row[2 * (i0 + r)]; rc.ri1 = aux.rs_row[2 * (i0 + r) + 1]; }
             }
+        }
+        RowCtx rc2 = rc;                                 // phase-2 view: pre-combined factors of p2_elem
+        if (PHASE >= 2 && MODE != SIM_INFONCE) {
+            const float ep = MODE == SIM_REGRESS ? aux.e_push : 1.f;
+            rc2.wr = rc.ri1 * rc.wr * ep;
+            rc2.wc = rc.wc * ep;
         }
         RowAcc racc;
         racc.clear();
@@ -452,7 +458,7 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         RowCtx rc1 = rc;                                 // phase-1 view of the row constants
         if (MODE == SIM_REGRESS) rc1.wr = rc.wr * aux.e_push;
         float gri0 = 0.f, gri1 = 0.f;                    // un-scaled row statistics for the generic (tail / multi) path
-        if (PHASE == 2 && row_ok) {
+        if (PHASE >= 2 && row_ok) {
             if (MODE == SIM_INFONCE) gri0 = aux.rs_row[i0 + r];
             else { gri0 = rc.ri0; gri1 = rc.ri1; }
         }
@@ -475,9 +481,14 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         mf[2 * BN + et] = aux.wrow ? aux.wrow[j] : 1.f;
                         mf[3 * BN + et] = aux.wcol ? aux.wcol[j] : 1.f;
                     }
-                    if (PHASE == 2) {
+                    if (PHASE >= 2) {
                         if (MODE == SIM_INFONCE) mf[4 * BN + et] = aux.rs_col[j] * LOG2E_F;
-                        else { mf[4 * BN + et] = aux.rs_col[2 * j]; mf[5 * BN + et] = aux.rs_col[2 * j + 1]; }
+                        else {
+                            const float aj = aux.rs_col[2 * j + 1];
+                            mf[4 * BN + et] = aux.rs_col[2 * j];
+                            mf[5 * BN + et] = aj;
+                            mf[2 * BN + et] = aj * (aux.wrow ? aux.wrow[j] : 1.f);       // alpha_j * wrow_j
+                        }
                     }
                 }
                 epi_bar();
@@ -506,29 +517,42 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         }
                     }
                 } else {
+                    const bool lean = fast && row_ok;
+                    __nv_bfloat16* grow = PHASE == 3 ? p.hout + (long long)(i0 + r) * p.ldh + j0 + c0 : nullptr;
 #pragma unroll
                     for (int g8 = 0; g8 < NC / 8; ++g8) {
                         uint32_t w[4];
+                        if (lean) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            float h2[2];
-#pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const int c = g8 * 8 + e * 2 + u;
-                                const int j = j0 + c0 + c;
-                                float h = 0.f;
-                                if (row_ok) {
-                                    if (fast) h = p2_elem<MODE>(kc, rc, cm, __uint_as_float(v[c]), j, c0 + c);
-                                    else if (j < aux.N) h = sim_grad_coeff(aux, rc.gi, j, __uint_as_float(v[c]), gri0, gri1);
-                                }
-                                h2[u] = h;
+                            for (int e = 0; e < 4; ++e) {
+                                const int c = g8 * 8 + e * 2;
+                                const float h0 = p2_elem<MODE>(kc, rc2, cm, __uint_as_float(v[c]), j0 + c0 + c, c0 + c);
+                                const float h1 = p2_elem<MODE>(kc, rc2, cm, __uint_as_float(v[c + 1]), j0 + c0 + c + 1, c0 + c + 1);
+                                w[e] = pack_bf16(h0, h1);
                             }
-                            w[e] = pack_bf16(h2[0], h2[1]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float h2[2];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    const int c = g8 * 8 + e * 2 + u;
+                                    const int j = j0 + c0 + c;
+                                    h2[u] = (row_ok && j < aux.N) ? sim_grad_coeff(aux, rc.gi, j, __uint_as_float(v[c]), gri0, gri1) : 0.f;
+                                }
+                                w[e] = pack_bf16(h2[0], h2[1]);
+                            }
                         }
-                        const int col8 = (c0 >> 3) + g8;                   // 16-byte chunk index along K
-                        unsigned char* dst = BN == 32 ? hrow + ((col8 ^ ((r >> 1) & 3)) << 4)
-                                                      : hrow + (col8 >> 3) * H_ATOM_BYTES + (((col8 & 7) ^ (r & 7)) << 4);
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                        if (PHASE == 3) {
+                            // 16 bytes = 8 consecutive keys of this thread's row (ldh is a multiple of 8, tiles start at
+                            // multiples of 32): columns at or beyond ldh are never written
+                            if (row_ok && j0 + c0 + g8 * 8 < p.ldh) *reinterpret_cast<uint4*>(grow + g8 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                        } else {
+                            const int col8 = (c0 >> 3) + g8;                   // 16-byte chunk index along K
+                            unsigned char* dst = BN == 32 ? hrow + ((col8 ^ ((r >> 1) & 3)) << 4)
+                                                          : hrow + (col8 >> 3) * H_ATOM_BYTES + (((col8 & 7) ^ (r & 7)) << 4);
+                            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
                     }
                 }
             }
@@ -556,13 +580,13 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 for (int k = 0; k < 5; ++k)
                     if (racc.v[k] != 0.f) atomicAdd(dst + k, racc.v[k]);      // two threads per row (+ key splits)
             }
-        } else {
+        } else if (PHASE == 2) {
             mbar_wait_g(d_full, 0);
             tc_fence_after();
             const int ndh = ND / 2;                      // ND is a multiple of 64
             for (int c0 = half * ndh; c0 < (half + 1) * ndh; c0 += 32) {
                 uint32_t v[32];
-                tc_ld32(lane_addr + TMEM_DA_COL + c0, v);
+                tc_ld32(lane_addr + da_col + c0, v);
                 if (row_ok) {
                     float* dst = p.out + (long long)(i0 + r) * p.ldout + dcol0 + c0;
 #pragma unroll
@@ -642,8 +666,10 @@ int launch_bn(const void* A, const void* B, int M, int N, int Dp, int D, const S
     TcParams p;
     p.aux = aux; p.out = out; p.ldout = ldout; p.M = M; p.D = D; p.nkc = nkc; p.nstage = nstage;
     p.tiles_per_split = per; p.use_atomics = jsplit > 1;
+    p.hout = PHASE == 3 ? reinterpret_cast<__nv_bfloat16*>(out) : nullptr;
+    p.ldh = PHASE == 3 ? ldout : 0;
     const size_t outbytes = PHASE == 1 ? (size_t)M * SIM_NSTAT * sizeof(float) : (size_t)M * ldout * sizeof(float);
-    if (jsplit > 1 || PHASE == 1) MMDTI_CUDA_OK(cudaMemsetAsync(out, 0, outbytes, st));      // phase 1 always accumulates with atomics
+    if (PHASE != 3 && (jsplit > 1 || PHASE == 1)) MMDTI_CUDA_OK(cudaMemsetAsync(out, 0, outbytes, st));      // phase 1 always accumulates with atomics
     const int smem_bytes = (int)lay.total + 1024;
     dim3 grid(stripes, jsplit, halves);
 #define SIM_GO(MODE)                                                                                                    \
@@ -667,7 +693,7 @@ template <int PHASE>
 int launch(const void* A, const void* B, int M, int N, int Dp, int D, const SimAux& aux, float* out, long long ldout, cudaStream_t st) {
     MMDTI_REQUIRE(Dp >= 64 && Dp <= 512 && Dp % 64 == 0, "sim_tc: Dp must be a multiple of 64 in [64, 512] (got %d)", Dp);
     MMDTI_REQUIRE(mmdti_aligned(A, 16) && mmdti_aligned(B, 16), "sim_tc: operands must be 16-byte aligned");
-    if constexpr (PHASE == 1) {
+    if constexpr (PHASE != 2) {
         // 256-key tiles halve the MMA instructions per flop (the single issuing thread, not the tensor pipe, paces
         // 128-key tiles); small N keeps 128-key tiles for parallelism
         if (N >= 4096 && !getenv("MMDTI_SIM_BN128")) return launch_bn<PHASE, 256>(A, B, M, N, Dp, D, aux, out, ldout, st);
@@ -697,4 +723,15 @@ extern "C" int mmdti_sim_grad_tc(const void* A, const void* B, int M, int N, int
     const SimAux aux = sim_make_aux(mode, N, row_offset, temperature, y, yhat, w_thr, e_push, key, C, coef_multi, wrow, wcol, rs_row, rs_col);
     if (int rc = sim_check_aux(aux, 2)) return rc;
     return launch<2>(A, B, M, N, Dp, (int)lddA, aux, dA, lddA, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mmdti_sim_coef_tc(const void* A, const void* B, int M, int N, int Dp, int row_offset, int mode, float temperature,
+                                 const float* y, const float* yhat, float w_thr, float e_push, const int64_t* key, int C,
+                                 float coef_multi, const float* wrow, const float* wcol, const float* rs_row, const float* rs_col,
+                                 void* H, int64_t ldh, void* stream) {
+    MMDTI_REQUIRE(A && B && H && M > 0 && ldh >= N && ldh % 8 == 0 && mmdti_aligned(H, 16),
+                  "sim_coef_tc: bad arguments (need ldh >= N, ldh %% 8 == 0, 16-byte aligned H)");
+    const SimAux aux = sim_make_aux(mode, N, row_offset, temperature, y, yhat, w_thr, e_push, key, C, coef_multi, wrow, wcol, rs_row, rs_col);
+    if (int rc = sim_check_aux(aux, 2)) return rc;
+    return launch<3>(A, B, M, N, Dp, Dp, aux, static_cast<float*>(H), ldh, static_cast<cudaStream_t>(stream));
 }

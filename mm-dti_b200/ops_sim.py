@@ -4,7 +4,8 @@ two-phase similarity engine of the C ABI (include/mmdti_b200.h, "contrastive sim
     forward : F.normalize -> phase 1 (row statistics over the similarity tiles) -> finalize
     backward: phase 2 (recompute tiles, gradient coefficients, dA) -> normalisation backward
 
-The N x N similarity matrix never exists.  Two arithmetic modes (config.fp32_mode()):
+The N x N similarity matrix never exists in the forward; the backward of large problems (see _two_step) materialises
+bounded row blocks of the bf16 gradient coefficients H and finishes with one plain GEMM.  Two arithmetic modes (config.fp32_mode()):
   bf16 (production)  bf16 unit vectors on the tcgen05 tensor cores, fp32 accumulation/statistics
   fp32 (validation)  plain fp32 FMA kernels (1e-5 parity with the reference)
 
@@ -14,6 +15,8 @@ the exact gradient of the global loss w.r.t. its own rows (see dist.py).  The re
 global loss on every rank.
 
 Reference: models/infonce.py:42-98, models/contrastive.py:3-169; closed forms SURVEY.md Appendix B."""
+import os
+
 import torch
 
 from . import _lib, config
@@ -69,9 +72,47 @@ def sim_stats(mode, A, B, row_offset, temperature, lab, use_tc):
     return stats
 
 
+H_BLOCK_BYTES = 512 << 20        # bound of the bf16 coefficient block of the two-step backward
+
+
+def _two_step(A, B):
+    """Two-step phase 2 (coefficient tiles to HBM, then one plain GEMM) or the fused kernel?  The fused kernel keeps dA
+    in TMEM: at Dp > 256 its 512 columns force two 256-column slices (each re-evaluates all H_ij) and the 128 KB anchor
+    stripe leaves shared memory for 32-key tiles only, so the two-step form is ~3x faster once the N x N coefficient work
+    dominates the launch overheads (measured: profiles/r1_sim_bwd_fused_vs_twostep.log); at Dp <= 256 the fused kernel
+    wins.  MMDTI_SIM_BWD=fused|twostep overrides."""
+    forced = os.environ.get("MMDTI_SIM_BWD", "auto")
+    if forced in ("fused", "twostep"):
+        return forced == "twostep"
+    return A.Dp > 256 and A.N * B.N >= (1 << 23)
+
+
+def _sim_grad_two_step(mode, A, B, row_offset, temperature, lab, rs_row, rs_col):
+    M, N = A.N, B.N
+    dev = B.inv_norm.device
+    ldh = (N + 7) // 8 * 8
+    rb = max(128, min((M + 127) // 128 * 128, H_BLOCK_BYTES // (2 * ldh) // 128 * 128))
+    hbuf = torch.empty((min(rb, M), ldh), device=dev, dtype=torch.bfloat16)
+    out = None
+    for r0 in range(0, M, rb):
+        m = min(rb, M - r0)
+        call("mmdti_sim_coef_tc", A.bf16[r0:], B.bf16, i32(m), i32(N), i32(A.Dp), i32(row_offset + r0), i32(mode),
+             f32(temperature), *_label_args(mode, lab), rs_row[r0:], rs_col, hbuf, i64(ldh), stream_ptr())
+        blk = torch.mm(hbuf[:m, :N], B.bf16, out_dtype=torch.float32)            # (m, Dp), fp32 accumulate and result
+        if m == M:
+            out = blk
+        else:
+            if out is None:
+                out = torch.empty((M, A.Dp), device=dev, dtype=torch.float32)
+            out[r0:r0 + m] = blk
+    return out if A.D == A.Dp else out[:, :A.D].contiguous()
+
+
 def sim_grad(mode, A, B, row_offset, temperature, lab, rs_row, rs_col, use_tc):
     """phase 2: dA (M, D) f32 = sum_j H_ij b_j"""
     M, N = A.N, B.N
+    if use_tc and _two_step(A, B):
+        return _sim_grad_two_step(mode, A, B, row_offset, temperature, lab, rs_row, rs_col)
     dA = torch.empty((M, A.D), device=B.inv_norm.device, dtype=torch.float32)
     if use_tc:
         call("mmdti_sim_grad_tc", A.bf16, B.bf16, i32(M), i32(N), i32(A.Dp), i32(row_offset), i32(mode), f32(temperature),
