@@ -81,9 +81,9 @@ class ClockSampler:
 
 def make_batch(seed):
     from mmdti_b200.data import synthetic_molecules
-    tokens, dist, et, _ = synthetic_molecules(B_PER_GPU, N_ATOMS, seed=seed)
+    tokens, dist, et, coord = synthetic_molecules(B_PER_GPU, N_ATOMS, seed=seed)
     g = torch.randn(B_PER_GPU, L, DIM, generator=torch.Generator().manual_seed(seed + 7)) * 0.05
-    return tokens, dist, et, g
+    return tokens, dist, et, g, coord
 
 
 # ------------------------------------------------------------------ CPU arm (oracle port of the reference)
@@ -171,9 +171,13 @@ def run_ours(args, rank, local_rank, world):
             dist.broadcast(prm.data, src=0)
         reducer = OverlappedGradReducer(model.parameters(), average=True)
 
-    tokens, dmat, et, g = make_batch(1234 + rank)
-    pin = [t.pin_memory() for t in (tokens, dmat, et)]
-    d_tokens, d_dist, d_et, d_g = tokens.to(dev), dmat.to(dev), et.to(dev), g.to(dev)
+    tokens, dmat, et, g, coord = make_batch(1234 + rank)
+    # --inputs pair (default): the reference's batch format (src_tokens, src_distance, src_edge_type);
+    # --inputs coords: tokens + coordinates only, the pair features are computed on the device
+    host_inputs = (tokens, dmat, et) if args.inputs == "pair" else (tokens, coord)
+    pin = [t.pin_memory() for t in host_inputs]
+    dev_inputs = [t.to(dev) for t in host_inputs]
+    d_g = g.to(dev)
     # Adam(eps 1e-6) as in tasks/trainer.py:160: mmdti_b200.optim.FusedAdam = one launch per step that also refreshes
     # the bf16 shadows of the encoder's GEMM weights (--torch-adam: torch.optim.Adam(fused=True) + per-step cast pass)
     if args.torch_adam:
@@ -189,8 +193,8 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def full_step(t, d, e):
-        rep = step_model(t, d, e)
+    def full_step(*inp):
+        rep = step_model(*inp) if args.inputs == "pair" else step_model(inp[0], src_coord=inp[1])
         loss = (rep * d_g).sum()
         loss.backward()
         if dist_on and use_graph:
@@ -199,18 +203,18 @@ def run_ours(args, rank, local_rank, world):
         return loss.detach()
 
     def step_eager():
-        loss = full_step(d_tokens, d_dist, d_et)
+        loss = full_step(*dev_inputs)
         opt.zero_grad(set_to_none=True)
         return loss
 
     if use_graph:
         from mmdti_b200.graph import GraphedStep
         opt.zero_grad(set_to_none=True)
-        graphed = GraphedStep(full_step, [d_tokens, d_dist, d_et], device=dev,
+        graphed = GraphedStep(full_step, dev_inputs, device=dev,
                               capture_error_mode="thread_local" if dist_on else "global")
 
         def step_resident():
-            return graphed(d_tokens, d_dist, d_et)
+            return graphed(*dev_inputs)
 
         def step_e2e():
             # pinned host inputs -> static device buffers (H2D inside the timed path), replay, D2H read of the loss
@@ -219,8 +223,7 @@ def run_ours(args, rank, local_rank, world):
         step_resident = step_eager
 
         def step_e2e():
-            t, d, e = (x.to(dev, non_blocking=True) for x in pin)
-            loss = full_step(t, d, e)
+            loss = full_step(*(x.to(dev, non_blocking=True) for x in pin))
             opt.zero_grad(set_to_none=True)
             return float(loss.item())                  # device -> host read of the step's result
 
@@ -306,6 +309,8 @@ def run_ours(args, rank, local_rank, world):
                        "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
                        "optimizer": "Adam(eps=1e-6), " + ("torch fused" if args.torch_adam else "mmdti FusedAdam (one launch, writes bf16 weight shadows)"),
                        "cuda_graph": bool(use_graph),
+                       "inputs": ("src_tokens + src_distance + src_edge_type (reference batch format)" if args.inputs == "pair"
+                                  else "src_tokens + src_coord (pair features computed on the device, mmdti_featurise)"),
                        "parallelism": "dp%d" % world,
                        "grad_exchange": (None if world == 1 else ("bucketed NCCL all-reduce (32 MB) overlapped with the backward, inside the graph" if use_graph
                                                                   else "DistributedDataParallel (NCCL)")),
@@ -346,6 +351,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of mmdti_b200.optim.FusedAdam")
+    ap.add_argument("--inputs", default="pair", choices=["pair", "coords"],
+                    help="host batch format of the e2e path: the reference's (tokens, distance, edge_type) or (tokens, coordinates)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -88,6 +88,13 @@ int mmdti_pair_bias_bwd(const void* d_out, const float* dist, const int64_t* edg
                         float* d_w2, float* d_b2, int B, int L, int K, int H, int E, int gpair_dtype,
                         void* stream);
 
+/* Pair featurisation on the device: src_distance (B,L,L) f32 and src_edge_type (B,L,L) int64 of
+ * a padded batch from src_tokens (B,L) int64 and src_coord (B,L,3) f32; both outputs are 0 wherever either position
+ * holds pad_idx.  Bit-exact with data/conformer.py:205-212,216-218 (float64 scipy distance_matrix cast to float32,
+ * tok_i * n_dict + tok_j) followed by the zero padding of utils/util.py:41-105. */
+int mmdti_featurise(const float* coord, const int64_t* tokens, int B, int L, int n_dict, int64_t pad_idx,
+                    float* dist, int64_t* edge_type, void* stream);
+
 /* Pieces of the fp32 validation-mode backward (the 128-wide GEMMs in between run as fp32 library
  * GEMMs on the host side, see mm-dti_b200/ops.py:PairBiasFn.backward):
  *  - mmdti_gauss_basis: the (npairs,128) basis g (out_dtype f32|bf16), i.e. GaussianLayer.forward

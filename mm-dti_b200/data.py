@@ -4,6 +4,9 @@ data/conformer.py:204-212: tokens with [CLS]/[SEP], centred coordinates, Euclide
 distance matrix, edge_type = tok_i*|dict| + tok_j; pad token 0, pad distance 0)."""
 import torch
 
+from . import _lib
+from ._lib import call, i32, i64, stream_ptr
+
 
 def _pad_size(values, pad_to_length, pad_to_multiple):
     size = max(v.size(0) for v in values)
@@ -65,3 +68,20 @@ def synthetic_molecules(B, n_atoms, seed=1234, ragged=False, n_dict=31):
     dist = torch.cdist(coord, coord) * (valid[:, :, None] & valid[:, None, :])
     et = (tokens[:, :, None] * n_dict + tokens[:, None, :]) * (valid[:, :, None] & valid[:, None, :])
     return tokens, dist.float().contiguous(), et.contiguous(), coord
+
+
+def featurise(src_tokens, src_coord, n_dict=31, pad_idx=0):
+    """src_distance (B,L,L) f32 and src_edge_type (B,L,L) int64 computed ON THE DEVICE from the tokens (B,L) and the
+    centred coordinates (B,L,3) of a padded batch -- bit-exact with data/conformer.py:205-218 + the zero padding of
+    utils/util.py:41-105, so a step uploads B*L*20 bytes instead of B*L*L*12.  n_dict is
+    len(dictionary) (31 with [MASK], models/mm_model.py:435-437)."""
+    _lib.require_cuda(src_tokens)
+    tok = src_tokens.long().contiguous()
+    xyz = src_coord.float().contiguous()
+    B, L = tok.shape
+    if xyz.shape != (B, L, 3):
+        raise ValueError("featurise: src_coord must be (B, L, 3) matching src_tokens (B, L)")
+    dist = torch.empty((B, L, L), device=tok.device, dtype=torch.float32)
+    et = torch.empty((B, L, L), device=tok.device, dtype=torch.int64)
+    call("mmdti_featurise", xyz, tok, i32(B), i32(L), i32(n_dict), i64(pad_idx), dist, et, stream_ptr())
+    return dist, et

@@ -169,10 +169,18 @@ class UnimolEncoder(nn.Module):
     def build_model(cls, args):
         return cls(args)
 
-    def forward(self, src_tokens, src_distance, src_edge_type):
+    def forward(self, src_tokens, src_distance=None, src_edge_type=None, src_coord=None):
         """-> all_repr (B,L,512).  The key-padding mask is always handed to the kernels (no
         host sync on ``padding_mask.any()``); with no padding it is all-false and the result is
-        identical to the reference's padding_mask=None branch (Q15)."""
+        identical to the reference's padding_mask=None branch (Q15).
+
+        New: when src_distance / src_edge_type are omitted they are computed on the device from ``src_coord``
+        (data.featurise, bit-exact with data/conformer.py:205-218), so only tokens and coordinates cross PCIe."""
+        if src_distance is None or src_edge_type is None:
+            if src_coord is None:
+                raise ValueError("UnimolEncoder.forward needs src_distance and src_edge_type, or src_coord")
+            from ..data import featurise
+            src_distance, src_edge_type = featurise(src_tokens, src_coord, n_dict=len(self.dictionary), pad_idx=self.padding_idx)
         padding_mask = src_tokens.eq(self.padding_idx)
         x = ops.TokenEmbeddingFn.apply(src_tokens, self.embed_tokens.weight, self.padding_idx)
         g, pj = self.gbf, self.gbf_proj

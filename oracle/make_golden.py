@@ -398,6 +398,53 @@ def gold_fds(ref):
     _save("fds", d)
 
 
+def gold_featurise(ref):
+    """data/conformer.py coords2unimol executed from the reference tree (rdkit / config / logger stubbed: the function
+    itself only needs numpy + scipy + the dictionary), batched with the reference's own padding helpers."""
+    import importlib.util
+    import types
+    stubs = {}
+    for name in ("rdkit", "rdkit.Chem", "rdkit.Chem.AllChem", "rdkit.RDLogger", "config"):
+        if name not in sys.modules:
+            stubs[name] = sys.modules[name] = types.ModuleType(name)
+    sys.modules["rdkit"].Chem = sys.modules["rdkit.Chem"]
+    sys.modules["rdkit"].RDLogger = sys.modules["rdkit.RDLogger"]
+    sys.modules["rdkit.Chem"].AllChem = sys.modules["rdkit.Chem.AllChem"]
+    sys.modules["rdkit.RDLogger"].DisableLog = lambda *a, **k: None
+    sys.modules["config"].MODEL_CONFIG = {}
+    spec = importlib.util.spec_from_file_location("_ref_conformer", os.path.join(ref_loader.REF_ROOT, "data", "conformer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    with ref_loader._tmp_cwd():
+        spec.loader.exec_module(mod)
+    for name in stubs:
+        sys.modules.pop(name, None)
+    from unicore.data import Dictionary
+    symbols = ["[PAD]", "[CLS]", "[SEP]", "[UNK]", "C", "N", "O", "S", "H", "Cl", "F", "Br", "I", "Si", "P", "B", "Na", "K",
+               "Al", "Ca", "Sn", "As", "Hg", "Fe", "Zn", "Cr", "Se", "Gd", "Au", "Li"]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "mol.dict.txt")
+        open(path, "w").write("\n".join(symbols) + "\n")
+        dictionary = Dictionary.load(path)
+    dictionary.add_symbol("[MASK]", is_special=True)
+    assert len(dictionary) == 31
+    rng = np.random.RandomState(11)
+    samples = []
+    for n in (5, 12, 30, 64, 3, 20, 1):
+        atoms = [symbols[i] for i in rng.randint(4, 30, size=n)]
+        atoms = [a if a != "H" else "C" for a in atoms]            # remove_hs would drop hydrogens
+        xyz = (rng.randn(n, 3) * 2.0 + rng.randn(1, 3) * 5.0).astype(np.float64)
+        samples.append(mod.coords2unimol(atoms, xyz, dictionary, max_atoms=256, remove_hs=True))
+    util = ref["util"]
+    tok = util.pad_1d_tokens([torch.as_tensor(s["src_tokens"]).long() for s in samples], pad_idx=0)
+    dist = util.pad_2d([torch.as_tensor(s["src_distance"]).float() for s in samples], pad_idx=0)
+    et = util.pad_2d([torch.as_tensor(s["src_edge_type"]).long() for s in samples], pad_idx=0)
+    coord = util.pad_coords([torch.as_tensor(s["src_coord"]).float() for s in samples], pad_idx=0.0)
+    d2, e2 = restate.featurise(tok, coord, n_dict=len(dictionary), pad_idx=0)
+    assert torch.equal(d2, dist), "featurise: distances differ from the reference (max %g)" % (d2 - dist).abs().max()
+    assert torch.equal(e2, et), "featurise: edge types differ from the reference"
+    _save("featurise", {"in.src_tokens": tok, "in.src_coord": coord, "out.src_distance": dist, "out.src_edge_type": et})
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
@@ -407,6 +454,7 @@ def main():
     gold_infonce(ref)
     gold_ct(ref)
     gold_fds(ref)
+    gold_featurise(ref)
     print("all fixtures written and the restatement reproduces each of them")
 
 

@@ -16,6 +16,24 @@ import torch.nn.functional as F
 GAUSS_PI = 3.14159  # truncated on purpose: models/mm_model.py:222
 
 
+def featurise(src_tokens, src_coord, n_dict=31, pad_idx=0):
+    """Pair features of a PADDED batch from tokens (B,L) and centred coordinates (B,L,3) f32:
+    src_distance (B,L,L) f32 and src_edge_type (B,L,L) int64, zero wherever either position is padding.
+    Follows data/conformer.py:205-212,216-218 (scipy distance_matrix = float64 (sum |d|^2)^(1/2) of the
+    float32-valued coordinates, cast to float32; edge type = tok_i * len(dictionary) + tok_j) and the
+    zero padding of utils/util.py:41-105 / models/mm_model.py:656-661."""
+    import numpy as np
+    tok = np.asarray(src_tokens, dtype=np.int64)
+    xyz = np.asarray(src_coord, dtype=np.float32).astype(np.float64)
+    d = xyz[:, :, None, :] - xyz[:, None, :, :]
+    sq = np.abs(d) ** 2
+    dist = np.sqrt((sq[..., 0] + sq[..., 1]) + sq[..., 2])
+    valid = (tok != pad_idx)
+    pair = valid[:, :, None] & valid[:, None, :]
+    et = tok[:, :, None] * n_dict + tok[:, None, :]
+    return torch.from_numpy(np.where(pair, dist, 0.0).astype(np.float32)), torch.from_numpy(np.where(pair, et, 0))
+
+
 def gaussian(x, mean, std):
     """models/mm_model.py:211-224."""
     a = (2 * GAUSS_PI) ** 0.5

@@ -123,3 +123,11 @@ def test_fds_golden():
     assert rel_err(restate.calibrate_mean_var(m.clone(), *args), g["out.cal_full"]) < 1e-6
     assert rel_err(restate.calibrate_mean_var(m.clone(), args[0], v1z, args[2], args[3]), g["out.cal_zero_cols"]) < 1e-6
     assert rel_err(restate.calibrate_mean_var(m.clone(), args[0], args[1] * 0, args[2], args[3]), g["out.cal_tiny"]) < 1e-6
+
+
+def test_featurise_restatement_matches_reference_fixture():
+    """data/conformer.py coords2unimol + utils/util.py padding, executed from the reference tree by make_golden.py"""
+    g = load_golden("featurise")
+    dist, et = restate.featurise(g["in.src_tokens"], g["in.src_coord"], n_dict=31, pad_idx=0)
+    assert torch.equal(dist, g["out.src_distance"])
+    assert torch.equal(et, g["out.src_edge_type"])
