@@ -116,7 +116,9 @@ struct FwdStage {
 // register budget is capped so that ~640 threads stay resident per SM (4 CTAs of 160 threads at L = 66)
 template <int NKB> struct FwdLaunch {
     static constexpr int MAXT = (NKB + 1) / 2 * 32 < 256 ? (NKB + 1) / 2 * 32 : 256;
-    static constexpr int MINB = 640 / MAXT < 1 ? 1 : (640 / MAXT > 8 ? 8 : 640 / MAXT);
+    // NKB >= 25 (L > 136): a thread holds >= 100 score registers and shared memory limits the SM to 2 CTAs of <= 96
+    // threads anyway, so the register cap is lifted (no spills) instead of kept at 128
+    static constexpr int MINB = NKB >= 25 ? 1 : (640 / MAXT < 1 ? 1 : (640 / MAXT > 8 ? 8 : 640 / MAXT));
 };
 
 template <typename T, typename TP, int NKB>
