@@ -894,6 +894,10 @@ int launch_bwd(BwdParams p, cudaStream_t st) {
         return s;
     };
     while (p.crb > 1 && smem_of(p.crb) > SMEM_CAP) --p.crb;
+    // two resident CTAs beat one with a longer chunk (L = 258: 3 warps/SM -> 6, 722 -> 576 us)
+    if (p.nchunks > 1)
+        while (p.crb > 2 && smem_of(p.crb) > 113 * 1024) --p.crb;
+    if (const char* e = getenv("MMDTI_K2_BWD_CRB")) p.crb = std::max(1, std::min(p.crb, atoi(e)));      // tuning knob
     const int nkb16 = (p.L + 15) / 16;
     p.nchunks = (nkb16 + p.crb - 1) / p.crb;
     // phase 1 uses one warp per 16-row block of the chunk; phase 2 spreads the 16-key blocks over all warps
