@@ -169,7 +169,11 @@ def run_ours(args, rank, local_rank, world):
         from mmdti_b200.dist import OverlappedGradReducer
         for prm in model.parameters():
             dist.broadcast(prm.data, src=0)
-        reducer = OverlappedGradReducer(model.parameters(), average=True)
+        # the embedding and K1 (pair-bias) gradients arrive after layer 0's: their own small bucket at the end, so that
+        # the bucket holding the first layers is reduced under K1's backward; flat buckets feed FusedAdam directly
+        late = [model.embed_tokens.weight] + list(model.gbf.parameters()) + list(model.gbf_proj.parameters()) \
+            + list(model.encoder.emb_layer_norm.parameters())
+        reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam)
 
     tokens, dmat, et, g, coord = make_batch(1234 + rank)
     # --inputs pair (default): the reference's batch format (src_tokens, src_distance, src_edge_type);
@@ -184,7 +188,9 @@ def run_ours(args, rank, local_rank, world):
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
     else:
         from mmdti_b200.optim import FusedAdam
-        opt = FusedAdam(model.parameters(), lr=1e-4, eps=1e-6, shadows=model.encoder.use_external_lowp())
+        flat = dist_on and use_graph
+        opt = FusedAdam(model.parameters(), lr=1e-4, eps=1e-6, shadows=model.encoder.use_external_lowp(),
+                        grad_scale=reducer.grad_scale if flat else 1.0, grad_source=reducer.reduced_grad if flat else None)
 
     params = [prm for prm in model.parameters() if prm.requires_grad]
 

@@ -102,14 +102,28 @@ class OverlappedGradReducer:
     running the rest of the backward.  ``finish()`` (call it after ``loss.backward()``) reduces whatever is left
     (parameters that received no gradient contribute zeros) and joins the streams.  Every rank issues the same
     collectives in the same order.  Works inside a CUDA-graph capture (the communication stream becomes a parallel
-    branch of the graph); on CPU tensors (gloo tests) the reduction runs synchronously."""
+    branch of the graph); on CPU tensors (gloo tests) the reduction runs synchronously.
 
-    def __init__(self, params, group=None, average=True, bucket_bytes=32 << 20):
-        self.group, self.average = group, average
+    tail_params: parameters whose gradients arrive LAST although they are registered early (here: the token embedding
+    and the K1 pair-bias parameters, whose backward runs after layer 0).  They get a bucket of their own at the end, so
+    the bucket holding the first encoder layers is reduced while K1's backward still runs and only a few KB stay exposed.
+
+    keep_flat=True: every bucket owns a persistent flat buffer (16-byte aligned slots); a complete bucket is gathered
+    into it with one multi-tensor copy and all-reduced IN PLACE -- no division, no copy back.  ``p.grad`` then keeps the
+    LOCAL gradient; the reduced one is ``reduced_grad(p)`` (a view of the flat buffer), to be scaled by ``grad_scale``
+    (1/world when average=True).  ``optim.FusedAdam(grad_source=reducer.reduced_grad, grad_scale=reducer.grad_scale)``
+    consumes it directly."""
+
+    def __init__(self, params, group=None, average=True, bucket_bytes=32 << 20, tail_params=None, keep_flat=False):
+        self.group, self.average, self.keep_flat = group, average, keep_flat
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
+        tail = [p for p in (tail_params or []) if p.requires_grad]
+        tail_ids = {id(p) for p in tail}
         self.buckets, cur, size = [], [], 0
         for p in reversed(self.params):
+            if id(p) in tail_ids:
+                continue
             nb = p.numel() * p.element_size()
             if cur and (size + nb > bucket_bytes or p.dtype != cur[0].dtype):
                 self.buckets.append(cur)
@@ -118,11 +132,37 @@ class OverlappedGradReducer:
             size += nb
         if cur:
             self.buckets.append(cur)
+        for p in tail:                                   # same-dtype runs of the late parameters
+            if self.buckets and getattr(self.buckets[-1], "is_tail", False) and self.buckets[-1][0].dtype == p.dtype:
+                self.buckets[-1].append(p)
+            else:
+                b = _Bucket([p])
+                b.is_tail = True
+                self.buckets.append(b)
         self.bucket_of = {p: i for i, b in enumerate(self.buckets) for p in b}
         self.comm = torch.cuda.Stream(device=self.params[0].device) if self.params[0].is_cuda else None
+        self.flat, self.slot = [], {}
+        if keep_flat:
+            for b in self.buckets:
+                offs, off = [], 0
+                for p in b:
+                    offs.append(off)
+                    off += (p.numel() + 3) // 4 * 4
+                flat = torch.zeros(off, device=b[0].device, dtype=b[0].dtype)
+                self.flat.append(flat)
+                for p, o in zip(b, offs):
+                    self.slot[p] = flat[o:o + p.numel()].view_as(p)
         self._reset()
         self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
         self.collectives = 0
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world if self.average else 1.0
+
+    def reduced_grad(self, p):
+        """keep_flat mode: the all-reduced (SUMMED) gradient of p after finish(); multiply by grad_scale."""
+        return self.slot[p]
 
     def _reset(self):
         self.pending = [len(b) for b in self.buckets]
@@ -143,6 +183,10 @@ class OverlappedGradReducer:
                 p.grad = torch.zeros_like(p)
 
         def run():
+            if self.keep_flat:
+                torch._foreach_copy_([self.slot[p] for p in bucket], [p.grad for p in bucket])
+                dist.all_reduce(self.flat[i], op=dist.ReduceOp.SUM, group=self.group)
+                return
             flat = torch.cat([p.grad.reshape(-1) for p in bucket])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             if self.average:
@@ -175,6 +219,11 @@ class OverlappedGradReducer:
     def remove(self):
         for h in self.handles:
             h.remove()
+
+
+class _Bucket(list):
+    """list of parameters with room for an attribute"""
+    is_tail = False
 
 
 def shard_rows(n_total, rank, world):

@@ -14,9 +14,11 @@ class FusedAdam:
     """Same update rule and state meaning as ``torch.optim.Adam(params, lr, betas, eps)`` (no weight decay / amsgrad).
 
     ``shadows``: optional {parameter: bf16 tensor of the same shape}; every step writes the updated parameter into its
-    shadow (see ``TransformerEncoderWithPair.use_external_lowp``).  ``grad_scale`` multiplies every gradient first."""
+    shadow (see ``TransformerEncoderWithPair.use_external_lowp``).  ``grad_scale`` multiplies every gradient first.
+    ``grad_source``: optional callable parameter -> tensor read INSTEAD of ``p.grad`` (e.g. the flat all-reduced
+    buffers of ``dist.OverlappedGradReducer(keep_flat=True)``, which saves the copy back into ``p.grad``)."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, shadows=None, grad_scale=1.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, shadows=None, grad_scale=1.0, grad_source=None):
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FusedAdam got an empty parameter list")
@@ -46,6 +48,7 @@ class FusedAdam:
         self._host_table = torch.empty((len(self.params), 6), dtype=torch.int64).pin_memory()
         self.table = torch.empty((len(self.params), 6), dtype=torch.int64, device=dev)
         self._grad_ptrs = None
+        self.grad_source = grad_source
         self.total_elements = total
 
     def state_for(self, p):
@@ -55,12 +58,13 @@ class FusedAdam:
         return self.exp_avg[o:o + n].view_as(p), self.exp_avg_sq[o:o + n].view_as(p)
 
     def _refresh_table(self):
-        ptrs = tuple(p.grad.data_ptr() for p in self.params)
+        src = self.grad_source if self.grad_source is not None else (lambda q: q.grad)
+        ptrs = tuple(src(p).data_ptr() for p in self.params)
         if ptrs == self._grad_ptrs:
             return
         t = self._host_table
         for i, p in enumerate(self.params):
-            g = p.grad
+            g = src(p)
             if g.dtype != torch.float32 or not g.is_contiguous():
                 raise _lib.MMDTIError("FusedAdam needs contiguous fp32 gradients")
             o = self._offs[i]
@@ -74,9 +78,10 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
-        for p in self.params:
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
+        if self.grad_source is None:
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
         self._refresh_table()
         self.step_count.add_(1)
         d = ctypes.c_double

@@ -78,6 +78,29 @@ def _worker(rank, world, port, q):
             for t_, prm in zip(tot, net2.parameters()):
                 assert torch.allclose(prm.grad, t_ / world, atol=1e-6)
         assert red.collectives == 2 * len(red.buckets)
+        red.remove()
+        # flat-bucket mode with a tail bucket: p.grad stays local, reduced_grad(p) * grad_scale is the average
+        net3 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+        net3.load_state_dict({k: v for k, v in net2.state_dict().items() if not k.startswith("2.")})
+        red3 = OverlappedGradReducer(net3.parameters(), average=True, bucket_bytes=256, tail_params=[net3[0].bias], keep_flat=True)
+        assert red3.buckets[-1] == [net3[0].bias] and all(net3[0].bias is not p_ for b in red3.buckets[:-1] for p_ in b)
+        for prm in net3.parameters():
+            prm.grad = None
+        net3(x).sum().backward()
+        local = [prm.grad.clone() for prm in net3.parameters()]
+        red3.finish()
+        tot = [torch.zeros_like(prm) for prm in net3.parameters()]
+        for r in range(world):
+            xr = torch.randn(5, 8, generator=torch.Generator().manual_seed(r))
+            ref3 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+            ref3.load_state_dict(net3.state_dict())
+            ref3(xr).sum().backward()
+            for t_, prm in zip(tot, ref3.parameters()):
+                t_ += prm.grad
+        for t_, prm, lg in zip(tot, net3.parameters(), local):
+            assert torch.allclose(red3.reduced_grad(prm) * red3.grad_scale, t_ / world, atol=1e-6)
+            assert torch.equal(prm.grad, lg)
+            assert red3.reduced_grad(prm).data_ptr() % 16 == 0
         q.put((rank, "ok"))
     except Exception as e:                                       # noqa: BLE001
         q.put((rank, "fail: %r" % (e,)))
