@@ -173,7 +173,8 @@ def run_ours(args, rank, local_rank, world):
         # the bucket holding the first layers is reduced under K1's backward; flat buckets feed FusedAdam directly
         late = [model.embed_tokens.weight] + list(model.gbf.parameters()) + list(model.gbf_proj.parameters()) \
             + list(model.encoder.emb_layer_norm.parameters())
-        reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam)
+        reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam,
+                                        bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
 
     tokens, dmat, et, g, coord = make_batch(1234 + rank)
     # --inputs pair (default): the reference's batch format (src_tokens, src_distance, src_edge_type);
