@@ -99,7 +99,7 @@ def cpu_reference_run(steps, warmup, sample_b=32):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5).items()}
-    tokens, dist, et, g = make_batch(1234)
+    tokens, dist, et, g, _ = make_batch(1234)
     tokens, dist, et, g = tokens[:sample_b], dist[:sample_b], et[:sample_b], g[:sample_b]
     opt = torch.optim.Adam(list(p.values()), lr=1e-4, eps=1e-6)        # tasks/trainer.py:160
     ts = []

@@ -62,3 +62,29 @@ def test_fused_adam_under_cuda_graph():
     assert int(mine.step_count.item()) == 4
     for a, b in zip(pa, pb):
         assert (b - a).abs().max().item() < 1e-6 + 1e-5 * a.abs().max().item()      # lr = 1e-3: updates are O(1e-3)
+
+
+def test_fused_adam_reads_external_gradient_buffers():
+    """grad_source + grad_scale: the flat all-reduced buckets of dist.OverlappedGradReducer(keep_flat=True) are consumed
+    in place (summed gradients, scaled by 1/world inside the kernel); p.grad is ignored"""
+    pa, pb = _params(5), _params(5)
+    world = 4
+    ref = torch.optim.Adam(pa, lr=1e-3, eps=1e-6)
+    offs, off = [], 0
+    for p in pb:
+        offs.append(off)
+        off += (p.numel() + 3) // 4 * 4
+    flat = torch.zeros(off, device="cuda")
+    slot = {p: flat[o:o + p.numel()].view_as(p) for p, o in zip(pb, offs)}
+    mine = FusedAdam(pb, lr=1e-3, eps=1e-6, grad_scale=1.0 / world, grad_source=lambda p: slot[p])
+    g = torch.Generator().manual_seed(6)
+    for step in range(3):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad = gr.clone()
+            slot[b].copy_(gr * world)                # what an all-reduce(SUM) over `world` identical ranks leaves
+            b.grad = None
+        ref.step()
+        mine.step()
+        for a, b in zip(pa, pb):
+            assert rel_err(b, a) < 2e-6, (step, a.shape)
