@@ -44,6 +44,7 @@ class TransformerEncoderWithPair(nn.Module):
         ])
         # MM-DTI discards outputs 1..4 (models/mm_model.py:559); set False to skip producing them
         self.pair_outputs = True
+        self.chain_layers = True      # fuse dropout+residual of layer i with LayerNorm-1 of layer i+1
 
     def forward(self, emb: torch.Tensor, attn_mask: Optional[torch.Tensor] = None,
                 padding_mask: Optional[torch.Tensor] = None):
@@ -110,9 +111,19 @@ class TransformerEncoderWithPair(nn.Module):
             x = x * (1 - padding_mask.unsqueeze(-1).type_as(x))
         pair_first = pair
         lowp = self._lowp_weights()
+        # cross-layer fusion: the final dropout+residual of layer i and LayerNorm-1 of layer i+1 run as one kernel
+        # (forward and backward) whenever both layers take the fused path; `chain` carries (h1, statistics)
+        chain = None
+        n_layers = len(self.layers)
         for i, layer in enumerate(self.layers):
-            x, pair, _ = layer(x, padding_mask=None, attn_bias=pair, return_attn=True,
-                               lowp=None if lowp is None else lowp[8 * i:8 * i + 8])
+            nxt = self.layers[i + 1] if i + 1 < n_layers else None
+            fuse_next = (self.chain_layers and nxt is not None and layer._fusable(x, pair, None, True)
+                         and isinstance(nxt.self_attn_layer_norm, torch.nn.LayerNorm))
+            out = layer(x, padding_mask=None, attn_bias=pair, return_attn=True,
+                        lowp=None if lowp is None else lowp[8 * i:8 * i + 8],
+                        chain_in=chain, next_ln=nxt.self_attn_layer_norm if fuse_next else None)
+            x, pair = out[0], out[1]
+            chain = out[3] if len(out) > 3 else None
 
         if not self.pair_outputs:
             if self.final_layer_norm is not None:

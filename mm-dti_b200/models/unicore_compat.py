@@ -176,7 +176,11 @@ class TransformerEncoderLayer(nn.Module):
         return [t.detach().to(dt) for t in (sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias,
                                             self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)]
 
-    def forward(self, x, attn_bias=None, padding_mask=None, return_attn=False, inplace_pair=False, lowp=None):
+    def forward(self, x, attn_bias=None, padding_mask=None, return_attn=False, inplace_pair=False, lowp=None,
+                chain_in=None, next_ln=None):
+        """chain_in / next_ln (fused path only, used by TransformerEncoderWithPair): ``chain_in`` = (h1, stats) of this
+        layer's LayerNorm-1 already computed by the previous layer, ``next_ln`` = the next layer's LayerNorm-1 module;
+        with next_ln the result is (x, scores, None, (h_next, stats_next))."""
         dt = config.act_dtype()
         if self._fusable(x, attn_bias, padding_mask, return_attn):
             # single autograd node with a hand-written backward (ops.EncoderLayerFn)
@@ -189,12 +193,16 @@ class TransformerEncoderLayer(nn.Module):
             cfg = (B, self.attention_heads, L, sa.scaling, p_attn, p_drop, seeds, dt)
             if dt == torch.float32:
                 lowp = None
-            x, scores = ops.EncoderLayerFn.apply(
+            h1_in, st1_in = chain_in if chain_in is not None else (None, None)
+            out = ops.EncoderLayerFn.apply(
                 x, attn_bias.contiguous(), self.self_attn_layer_norm.weight, self.self_attn_layer_norm.bias,
                 sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias,
                 self.final_layer_norm.weight, self.final_layer_norm.bias, self.fc1.weight, self.fc1.bias,
-                self.fc2.weight, self.fc2.bias, lowp, cfg)
-            return x, scores, None
+                self.fc2.weight, self.fc2.bias, lowp, cfg, h1_in, st1_in,
+                None if next_ln is None else next_ln.weight, None if next_ln is None else next_ln.bias)
+            if next_ln is not None:
+                return out[0], out[1], None, (out[2], out[3])
+            return out[0], out[1], None
         residual = x
         if not self.post_ln:
             x = self.self_attn_layer_norm(x)

@@ -380,7 +380,11 @@ class EncoderLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pair_in, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc1, b_fc1, w_fc2, b_fc2,
-                lowp, cfg):
+                lowp, cfg, h1_in=None, st1_in=None, nxt_w=None, nxt_b=None):
+        """Cross-layer chaining (optional): ``h1_in, st1_in`` = this layer's LayerNorm-1 output and statistics, already
+        produced by the PREVIOUS layer; ``nxt_w, nxt_b`` = the NEXT layer's LayerNorm-1 parameters, in which case the
+        final dropout+residual is fused with that LayerNorm (one kernel instead of two, forward and backward) and the
+        function returns (x2, pair_out, h_next, st_next)."""
         B, H, L, scale, p_attn, p_drop, seeds, dt = cfg
         _lib.require_cuda(x, pair_in)
         D = x.shape[-1]
@@ -393,7 +397,11 @@ class EncoderLayerFn(torch.autograd.Function):
         x2d = x.detach().reshape(rows, D).contiguous().float()
         ln1_wd, ln1_bd, ln2_wd, ln2_bd = (t.detach().float().contiguous() for t in (ln1_w, ln1_b, ln2_w, ln2_b))
         pair_in = pair_in.detach()
-        h1, st1 = layernorm_fwd(x2d, ln1_wd, ln1_bd, dt)
+        chain_in = h1_in is not None
+        if chain_in:
+            h1, st1 = h1_in.detach(), st1_in.detach()
+        else:
+            h1, st1 = layernorm_fwd(x2d, ln1_wd, ln1_bd, dt)
         qkv = torch.addmm(b_in_l, h1, w_in_l.t())
         o = torch.empty((rows, D), device=x.device, dtype=dt)
         pair_out = torch.empty_like(pair_in)
@@ -410,17 +418,31 @@ class EncoderLayerFn(torch.autograd.Function):
         call("mmdti_gelu_fwd", z, u, i64(z.numel()), i32(code), sp)
         f = torch.addmm(b_fc2_l, u, w_fc2_l.t())
         x2 = torch.empty_like(x2d)
-        call("mmdti_dropout_residual_fwd", x1, f, x2, i64(rows * D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+        chain_out = nxt_w is not None
+        if chain_out:
+            nxt_wd, nxt_bd = nxt_w.detach().float().contiguous(), nxt_b.detach().float().contiguous()
+            h_next = torch.empty((rows, D), device=x.device, dtype=dt)
+            st_next = torch.empty((2, rows), device=x.device, dtype=torch.float32)
+            call("mmdti_dropres_layernorm_fwd", x1, f, x2, nxt_wd, nxt_bd, h_next, st_next[0], st_next[1], i32(rows), i32(D),
+                 f32(1e-5), f32(p_drop), u64(seeds[2]), i32(code), i32(code), sp)
+        else:
+            nxt_wd = h_next = st_next = None
+            call("mmdti_dropout_residual_fwd", x1, f, x2, i64(rows * D), f32(p_drop), u64(seeds[2]), i32(code), sp)
         ctx.save_for_backward(x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_wd, ln2_wd, w_in_l, w_out_l,
-                              w_fc1_l, w_fc2_l)
+                              w_fc1_l, w_fc2_l, *((x2, st_next, nxt_wd) if chain_out else ()))
         ctx.cfg = cfg
+        ctx.chain = (chain_in, chain_out)
         ctx.set_materialize_grads(False)
+        if chain_out:
+            ctx.mark_non_differentiable(st_next)
+            return x2.view(B, L, D), pair_out, h_next, st_next
         return x2.view(B, L, D), pair_out
 
     @staticmethod
-    def backward(ctx, dx2, dpair_out):
-        (x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_w, ln2_w, w_in_l, w_out_l, w_fc1_l,
-         w_fc2_l) = ctx.saved_tensors
+    def backward(ctx, dx2, dpair_out, dh_next=None, _dst_next=None):
+        saved = ctx.saved_tensors
+        (x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_w, ln2_w, w_in_l, w_out_l, w_fc1_l, w_fc2_l) = saved[:17]
+        chain_in, chain_out = ctx.chain
         B, H, L, scale, p_attn, p_drop, seeds, dt = ctx.cfg
         rows, D = x2d.shape
         F_ = z.shape[1]
@@ -435,11 +457,12 @@ class EncoderLayerFn(torch.autograd.Function):
             if dpair_out.dtype != pair_out.dtype:
                 dpair_out = dpair_out.to(pair_out.dtype)
         # one zeroed buffer for all reduced gradients of this layer
-        red = torch.zeros(4 * D + 2 * D + F_ + 3 * D, device=dev, dtype=torch.float32)
+        red = torch.zeros(4 * D + 2 * D + F_ + 3 * D + 2 * D, device=dev, dtype=torch.float32)
         dw_ln1, db_ln1, dw_ln2, db_ln2 = red[0:D], red[D:2 * D], red[2 * D:3 * D], red[3 * D:4 * D]
         db_out, db_fc2 = red[4 * D:5 * D], red[5 * D:6 * D]
         db_fc1 = red[6 * D:6 * D + F_]
-        db_in = red[6 * D + F_:]
+        db_in = red[6 * D + F_:9 * D + F_]
+        dw_nxt, db_nxt = red[9 * D + F_:10 * D + F_], red[10 * D + F_:]
         # Weight gradients (and the in_proj bias column sums) are not on the critical path of the backward
         # chain: they go to a side stream and overlap the latency-bound kernels of the main stream (in a CUDA
         # graph they become parallel branches).  The layer joins the side stream before it returns.
@@ -457,7 +480,18 @@ class EncoderLayerFn(torch.autograd.Function):
 
         # ---- feed-forward block
         df = torch.empty((rows, D), device=dev, dtype=dt)
-        call("mmdti_dropout_bwd", dx2, df, db_fc2, i32(rows), i32(D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+        if chain_out and dh_next is not None:
+            # the NEXT layer's LayerNorm-1 backward fused with this layer's final dropout backward:
+            # dxt = dx2 + dLN(dh_next) is the total gradient at x2, df = dropout'(dxt)
+            x2, st_next, nxt_w = saved[17:20]
+            dxt = torch.empty_like(x2d)
+            call("mmdti_layernorm_bwd_dropout", dh_next.contiguous(), x2, nxt_w, st_next[0], st_next[1], dx2, dxt, dw_nxt, db_nxt, df,
+                 db_fc2, i32(rows), i32(D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+            dx2 = dxt
+            g_nxt = (dw_nxt, db_nxt)
+        else:
+            call("mmdti_dropout_bwd", dx2, df, db_fc2, i32(rows), i32(D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+            g_nxt = (None, None)
         dW_fc2 = off_path(lambda: _mm_f32(df.t(), u))
         du = torch.mm(df, w_fc2_l)
         dz = torch.empty_like(z)
@@ -483,12 +517,17 @@ class EncoderLayerFn(torch.autograd.Function):
 
         dW_in = off_path(in_proj_grads)
         dh1 = torch.mm(dqkv, w_in_l)
-        dx = dx1          # in place: dx = dx1 + dLN1
-        call("mmdti_layernorm_bwd", dh1, x2d, ln1_w, st1[0], st1[1], dx1, dx, dw_ln1, db_ln1, i32(rows), i32(D), i32(code), sp)
+        if chain_in:
+            # LayerNorm-1 belongs to the previous layer's fused kernel: hand it dh1, return the residual gradient alone
+            dx, g_ln1, g_h1 = dx1, (None, None), dh1
+        else:
+            dx = dx1          # in place: dx = dx1 + dLN1
+            call("mmdti_layernorm_bwd", dh1, x2d, ln1_w, st1[0], st1[1], dx1, dx, dw_ln1, db_ln1, i32(rows), i32(D), i32(code), sp)
+            g_ln1, g_h1 = (dw_ln1, db_ln1), None
         if side is not None:
             main.wait_stream(side)
-        return (dx.view(B, L, D), dpair_in, dw_ln1, db_ln1, dW_in, db_in, dW_out, db_out, dw_ln2, db_ln2, dW_fc1, db_fc1,
-                dW_fc2, db_fc2, None, None)
+        return (dx.view(B, L, D), dpair_in, g_ln1[0], g_ln1[1], dW_in, db_in, dW_out, db_out, dw_ln2, db_ln2, dW_fc1, db_fc1,
+                dW_fc2, db_fc2, None, None, g_h1, None, g_nxt[0], g_nxt[1])
 
 
 def dropout_mask(n, p, seed, device="cuda"):
