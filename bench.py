@@ -223,9 +223,18 @@ def run_ours(args, rank, local_rank, world):
         def step_resident():
             return graphed(*dev_inputs)
 
+        primed = []
+
         def step_e2e():
-            # pinned host inputs -> static device buffers (H2D inside the timed path), replay, D2H read of the loss
-            return float(graphed(*pin).item())
+            # input pipeline of a training loop: every step copies ITS batch from pinned host memory (H2D inside the timed
+            # region, one copy per step), but the copy of step i+1 is issued on a copy stream while step i replays;
+            # then the replay and the D2H read of the loss
+            if not primed:
+                graphed.prefetch(*pin)
+                primed.append(True)
+            out = graphed()
+            graphed.prefetch(*pin)
+            return float(out.item())
     else:
         step_resident = step_eager
 
@@ -324,7 +333,9 @@ def run_ours(args, rank, local_rank, world):
                        "l2": "no flush: the per-step working set (15 x %.0f MB pair tensors + activations) exceeds the 126 MB L2"
                              % (nel * esz / 1e6)},
             "e2e": {"value": mols / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "pipeline": ("H2D of step i+1 overlaps the replay of step i (GraphedStep.prefetch), loss read back every step"
+                                 if use_graph else "H2D, step, loss read back; no overlap")},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,

@@ -33,6 +33,7 @@ class GraphedStep:
         self.static_in = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in example_inputs]
         for dst, src in zip(self.static_in, example_inputs):
             dst.copy_(src)
+        self.staging, self.copy_stream, self._staged, self._consumed = None, None, None, None
         self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         _lib.call("mmdti_set_seed_offset", self.counter)
         _lib.launch_count -= 1                       # registration is not a kernel launch
@@ -55,12 +56,38 @@ class GraphedStep:
         self.launches_per_replay = _lib.launch_count - n0      # own kernels captured in the graph
 
     def __call__(self, *inputs):
+        """Replay the step on ``inputs`` (host or device tensors, copied into the static buffers).  With no arguments
+        the batch handed to ``prefetch`` earlier is used."""
+        if not inputs:
+            if self._staged is None:
+                raise _lib.MMDTIError("GraphedStep(): no inputs given and nothing prefetched")
+            torch.cuda.current_stream(self.device).wait_event(self._staged)
+            inputs, self._staged = self.staging, None
+        staged = inputs is self.staging
         for dst, src in zip(self.static_in, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+        if staged:
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(self.device))
         self.graph.replay()
         _lib.launch_count += self.launches_per_replay
         return self.static_out
+
+    def prefetch(self, *inputs):
+        """Input pipeline: start copying the NEXT batch (pinned host tensors) into device staging buffers on a copy
+        stream; the copy overlaps the replay that is in flight.  The next ``step()`` call without arguments waits for it
+        and moves the staged batch into the static buffers with a device-to-device copy."""
+        if self.staging is None:
+            self.staging = [torch.empty_like(t) for t in self.static_in]
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        if self._consumed is not None:
+            self.copy_stream.wait_event(self._consumed)      # the previous staged batch has been moved out
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self.staging, inputs):
+                dst.copy_(src, non_blocking=True)
+            self._staged = torch.cuda.Event()
+            self._staged.record(self.copy_stream)
 
     def close(self):
         _lib.call("mmdti_set_seed_offset", None)

@@ -88,3 +88,29 @@ def test_fused_adam_reads_external_gradient_buffers():
         mine.step()
         for a, b in zip(pa, pb):
             assert rel_err(b, a) < 2e-6, (step, a.shape)
+
+
+def test_graphed_step_prefetch_pipeline():
+    """GraphedStep.prefetch: batches staged on a copy stream are consumed in order, results equal direct calls"""
+    from mmdti_b200.graph import GraphedStep
+    w = torch.randn(16, 8, device="cuda")
+
+    def fn(a, b):
+        return (a @ w).sum() + b.float().sum()
+
+    ex = [torch.zeros(4, 16, device="cuda"), torch.zeros(4, dtype=torch.int64, device="cuda")]
+    gs = GraphedStep(fn, ex, warmup=1)
+    batches = [(torch.randn(4, 16).pin_memory(), torch.randint(0, 9, (4,)).pin_memory()) for _ in range(4)]
+    want = [float(fn(a.cuda(), b.cuda())) for a, b in batches]
+    gs.prefetch(*batches[0])
+    got = []
+    for i in range(4):
+        out = gs()
+        if i + 1 < 4:
+            gs.prefetch(*batches[i + 1])
+        got.append(float(out.item()))
+    assert got == pytest.approx(want, rel=1e-5)
+    assert float(gs(*batches[2]).item()) == pytest.approx(want[2], rel=1e-5)      # direct call still works
+    with pytest.raises(Exception):
+        gs()
+    gs.close()
