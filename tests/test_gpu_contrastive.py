@@ -139,6 +139,21 @@ def test_large_n_tensor_core_tiles_match_fp32_kernels(N, D, report):
         assert e[0] < 4e-3 and all(v < 4e-2 for v in e[1:]), (name, e)
 
 
+def test_fused_and_two_step_backward_agree(monkeypatch):
+    """Dp > 256: the fused phase-2 kernel (dA accumulated in TMEM) and the two-step form (tcgen05 coefficient kernel +
+    plain GEMM) evaluate the same H_ij in bf16; their gradients agree to bf16 accumulation noise"""
+    N, D = 3000, 512
+    f, y, yhat, w, cls = _rand_case(N, D, 99)
+    grads = {}
+    for form in ("fused", "twostep"):
+        monkeypatch.setenv("MMDTI_SIM_BWD", form)
+        a = f.cuda().requires_grad_(True)
+        with mmdti_b200.precision(act="bf16"):
+            (ctm.CT_Regress(a, y.cuda(), yhat.cuda(), weights=w.cuda(), w=0.2) + infm.info_nce(a, a.detach().roll(1, 0))).backward()
+        grads[form] = a.grad.clone()
+    assert norm_err(grads["twostep"], grads["fused"]) < 2e-3
+
+
 def test_infonce_value_errors():
     for bad in ((torch.randn(4), torch.randn(4, 3)), (torch.randn(4, 3), torch.randn(5, 3)),
                 (torch.randn(4, 3), torch.randn(4, 2))):
