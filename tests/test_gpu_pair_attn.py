@@ -158,3 +158,49 @@ def test_pair_pad_unpad_roundtrip(L):
         assert torch.equal(xp[..., :L].cpu().reshape(B * H, L, L), x.to(dt))
         assert torch.isinf(xp[..., L:]).all()
         assert torch.equal(ops.pair_unpad(xp, L, torch.float32).cpu(), x.to(dt).float())
+
+
+@pytest.mark.parametrize("L", [5, 66, 130, 258])
+def test_keep_bits_equal_the_in_kernel_mask(L):
+    """mmdti_pair_attn_keep_bits (bit-packed, shared by forward and backward) == the mask the kernels hash themselves"""
+    from mmdti_b200 import _lib, ops
+    from mmdti_b200._lib import call, f32, i32, stream_ptr, u64
+    B, H, p, seed = 2, 3, 0.3, 1234567
+    nw = _lib.lib().mmdti_pair_keep_words(L)
+    bits = torch.empty(B * H * L, nw, device="cuda", dtype=torch.int32)
+    call("mmdti_pair_attn_keep_bits", bits, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
+    dense = ops.attn_dropout_mask(B, H, L, p, seed)                      # (B,H,L,L) bool
+    cols = torch.arange(L, device="cuda")
+    words = bits.view(B, H, L, nw).long() & 0xFFFFFFFF
+    got = ((words[..., cols // 32] >> (cols % 32)) & 1).bool()
+    assert torch.equal(got, dense)
+
+
+@pytest.mark.parametrize("L", [66, 100, 258])
+def test_k2_with_keep_bits_is_bit_identical(L):
+    from mmdti_b200 import _lib, ops
+    from mmdti_b200._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
+    B, H, D, p, seed = 2, 64, 512, 0.1, 99
+    Lp = ops.pair_ld(L)
+    g = torch.Generator(device="cuda").manual_seed(L)
+    qkv = (torch.randn(B * L, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    pair = torch.randn(B, H, L, Lp, device="cuda", generator=g).bfloat16()
+    pair[..., L:] = float("-inf")
+    d_o = (torch.randn(B * L, D, device="cuda", generator=g) * 0.1).bfloat16()
+    dpo = (torch.randn(B, H, L, Lp, device="cuda", generator=g) * 0.01).bfloat16()
+    dpo[..., L:] = 0
+    keep = torch.empty(B * H * L, _lib.lib().mmdti_pair_keep_words(L), device="cuda", dtype=torch.int32)
+    call("mmdti_pair_attn_keep_bits", keep, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
+    code = DTYPE_CODE[torch.bfloat16]
+    res = []
+    for kb in (None, keep):
+        pout, o = torch.empty_like(pair), torch.empty(B * L, D, device="cuda", dtype=torch.bfloat16)
+        call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H),
+             i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(code), kb, stream_ptr())
+        dpi, dqkv = torch.empty_like(pair), torch.empty_like(qkv)
+        call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pout, o, d_o, i64(D), dpo, dpi,
+             dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L), f32(8 ** -0.5), f32(p), u64(seed),
+             i32(code), i32(code), i32(code), kb, stream_ptr())
+        res.append((o, pout, dpi[..., :L], dqkv))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
