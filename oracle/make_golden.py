@@ -445,6 +445,45 @@ def gold_featurise(ref):
     _save("featurise", {"in.src_tokens": tok, "in.src_coord": coord, "out.src_distance": dist, "out.src_edge_type": et})
 
 
+def gold_loss(ref):
+    """Task losses (models/loss.py:9-289) and the explicit-negatives / reduction='none' branches of info_nce
+    (models/infonce.py:71-88): outputs of the reference's own functions on seeded inputs; the host-side mirrors in
+    mmdti_b200/models are checked against them on CPU (tests/test_host_logic.py)."""
+    L, inf = ref["loss"], ref["infonce"]
+    g = torch.Generator().manual_seed(70)
+    B, C = 24, 5
+    x = torch.randn(B, C, generator=g)
+    y = torch.randn(B, C, generator=g)
+    yb = (torch.rand(B, C, generator=g) < 0.3).float()
+    yb_nan = yb.clone()
+    yb_nan[torch.rand(B, C, generator=g) < 0.2] = float("nan")
+    y_nan = y.clone()
+    y_nan[torch.rand(B, C, generator=g) < 0.2] = float("nan")
+    prob = torch.rand(B, generator=g)
+    cls = torch.randint(0, C, (B, 1), generator=g)
+    d = {"in.x": x, "in.y": y, "in.yb": yb, "in.yb_nan": yb_nan, "in.y_nan": y_nan, "in.prob": prob, "in.cls": cls}
+    d["out.rmse"] = L.RMSELoss()(x, y)
+    ghmc, ghmr = L.GHMC_Loss(bins=10, alpha=0.5), L.GHMR_Loss(bins=10, alpha=0.5, mu=0.02)
+    d["out.ghmc_1"], d["out.ghmc_2"] = ghmc(x, yb), ghmc(0.5 * x, yb)       # second call exercises the EMA of the bin counts
+    d["out.ghmr_1"], d["out.ghmr_2"] = ghmr(x, y), ghmr(0.5 * x, y)
+    d["out.masked_bce"] = L.MaskedBCEWithLogitsLoss()(x, yb_nan)
+    d["out.mae_nan"] = L.MAEwithNan(x, y_nan)
+    d["out.bce_nan"] = L.BCEwithNan(x, yb_nan)
+    d["out.focal"] = L.FocalLoss(prob, yb[:, 0])
+    d["out.focal_logits"] = L.FocalLossWithLogits(x, yb_nan)
+    d["out.ce"] = L.myCrossEntropyLoss(x, cls)
+    # the symmetric form (infonce.py:98) transposes the (N, 1+M) logits against N labels: the reference's explicit-negatives
+    # branches only run when M + 1 == N (anything else raises inside F.cross_entropy)
+    N, De, M = 12, 20, 11
+    q, k = torch.randn(N, De, generator=g), torch.randn(N, De, generator=g)
+    neg_u, neg_p = torch.randn(M, De, generator=g), torch.randn(N, M, De, generator=g)
+    d.update({"in.q": q, "in.k": k, "in.neg_unpaired": neg_u, "in.neg_paired": neg_p})
+    d["out.nce_unpaired"] = inf.info_nce(q, k, neg_u, temperature=0.1, negative_mode="unpaired")
+    d["out.nce_paired"] = inf.info_nce(q, k, neg_p, temperature=0.2, negative_mode="paired")
+    d["out.nce_none"] = inf.info_nce(q, k, temperature=0.1, reduction="none")
+    _save("loss", d)
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
@@ -455,6 +494,7 @@ def main():
     gold_ct(ref)
     gold_fds(ref)
     gold_featurise(ref)
+    gold_loss(ref)
     print("all fixtures written and the restatement reproduces each of them")
 
 
