@@ -8,6 +8,12 @@ Workload (BASELINE.json configs[1]): the Uni-Mol conformer encoder alone — 15 
 sum(all_repr * g) in training mode (dropout 0.1 as configured) + Adam step, synthetic molecules,
 random-init weights.  At N = 1 the step is captured once in a CUDA graph and replayed.  Metric: train molecules/s, whole job (weak scaling: 128 molecules per GPU).
 
+--workload hotpath runs the WHOLE hot path of SURVEY.md §8(a) in the step, chained the way MM_Model.forward chains it
+(models/mm_model.py:545-591): the same encoder -> InfoNCE against the second modality (a resident random (B, 64, 512)
+tensor standing in for the out-of-scope ChemBERTa output) -> masked mean pooling -> FDS.smooth (epoch 1, populated
+statistics) -> regression head -> ConR, loss = MSE + 0.1 InfoNCE + 0.1 ConR (tasks/trainer.py:68-69,193), backward, Adam.
+At N > 1 the contrastive operands are all-gathered (global-batch negatives) inside the step.
+
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
@@ -27,6 +33,9 @@ sys.path.insert(0, ROOT)
 B_PER_GPU, N_ATOMS, LAYERS, HEADS, DIM = 128, 64, 15, 64, 512
 L = N_ATOMS + 2
 METRIC, UNIT = "train_molecules_per_sec", "molecules/s"
+S_SMILES, FDS_BUCKETS = 64, 30
+WORKLOADS = {"encoder": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms",
+             "hotpath": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd"}
 
 
 def peaks():
@@ -86,8 +95,27 @@ def make_batch(seed):
     return tokens, dist, et, g, coord
 
 
+def make_head_batch(seed, n=B_PER_GPU):
+    """Inputs of the contrastive head: second-modality activations (B, S, 512), standard-scaled regression targets,
+    sample weights (mean 1), and FDS statistics of a previous epoch."""
+    gen = torch.Generator().manual_seed(seed + 11)
+    smiles = torch.randn(n, S_SMILES, DIM, generator=gen) * 0.5
+    y = torch.randn(n, 1, generator=gen)
+    w = torch.rand(n, generator=gen) + 0.5
+    w = w / w.mean()
+    sg = torch.Generator().manual_seed(99)                      # the same statistics on every rank
+    stats = {"running_mean_last_epoch": torch.randn(FDS_BUCKETS, DIM, generator=sg) * 0.1,
+             "running_var_last_epoch": torch.rand(FDS_BUCKETS, DIM, generator=sg) + 0.5,
+             "smoothed_mean_last_epoch": torch.randn(FDS_BUCKETS, DIM, generator=sg) * 0.1,
+             "smoothed_var_last_epoch": torch.rand(FDS_BUCKETS, DIM, generator=sg) + 0.5}
+    return smiles, y, w, stats
+
+
+FDS_CFG = dict(min_value=-3.0, bin_width=0.2, bucket_num=FDS_BUCKETS, bucket_start=0, start_smooth=1)
+
+
 # ------------------------------------------------------------------ CPU arm (oracle port of the reference)
-def cpu_reference_run(steps, warmup, sample_b=32):
+def cpu_reference_run(steps, warmup, sample_b=32, workload="encoder"):
     """The reference's CPU implementation of the same path (oracle/restate.py: its own
     models/mm_model.py + models/transformers.py restated, Uni-Core layer restated), fp32, all host
     threads, on a bounded sample of the workload: `sample_b` molecules of the 128-molecule batch
@@ -101,12 +129,32 @@ def cpu_reference_run(steps, warmup, sample_b=32):
     p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5).items()}
     tokens, dist, et, g, _ = make_batch(1234)
     tokens, dist, et, g = tokens[:sample_b], dist[:sample_b], et[:sample_b], g[:sample_b]
-    opt = torch.optim.Adam(list(p.values()), lr=1e-4, eps=1e-6)        # tasks/trainer.py:160
+    hot = workload == "hotpath"
+    if hot:
+        import torch.nn.functional as F
+        smiles, y, w, stats = (x[:sample_b] if torch.is_tensor(x) else x for x in make_head_batch(1234))
+        torch.manual_seed(5)
+        mods = torch.nn.ModuleDict({"infonce": torch.nn.ModuleDict({
+            "info_proj_query": torch.nn.Sequential(torch.nn.Linear(DIM, DIM), torch.nn.GELU(), torch.nn.Linear(DIM, 50)),
+            "info_proj_positive": torch.nn.Sequential(torch.nn.Linear(DIM, DIM), torch.nn.GELU(), torch.nn.Linear(DIM, 50))}),
+            "head": torch.nn.Linear(DIM, 1)})
+        pi = {k: v for k, v in mods.named_parameters() if k.startswith("infonce.")}
+        hw, hb = mods["head"].weight, mods["head"].bias
+        mask = tokens.ne(0).float().unsqueeze(-1)
+    opt = torch.optim.Adam(list(p.values()) + (list(mods.parameters()) if hot else []), lr=1e-4, eps=1e-6)   # tasks/trainer.py:160
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         rep = restate.unimol_encoder(tokens, dist, et, p, heads=HEADS, n_layers=LAYERS)
-        (rep * g).sum().backward()
+        if hot:
+            l_inf = restate.infonce_head(rep, smiles, pi)
+            pooled = (rep * mask).sum(1) / mask.sum(1)
+            feats = restate.fds_smooth(pooled * 1.0, y, 1, stats, FDS_CFG)
+            logits = F.linear(feats, hw, hb)
+            l_ct = restate.ct_regress(feats, y, logits, weights=w, w=0.2)
+            (F.mse_loss(logits, y) + 0.1 * l_inf + 0.1 * l_ct).backward()
+        else:
+            (rep * g).sum().backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
         if i >= warmup:
@@ -121,12 +169,12 @@ def run_reference(args, rank):
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
     sample_b = 32
-    val, sec, cores = cpu_reference_run(steps, warm, sample_b)
+    val, sec, cores = cpu_reference_run(steps, warm, sample_b, args.workload)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms", "per_gpu_batch": B_PER_GPU,
+        "config": {"workload": WORKLOADS[args.workload], "per_gpu_batch": B_PER_GPU,
                    "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d of the %d molecules per step (same L=%d, 15 layers, fp32), oracle/restate.py "
@@ -173,24 +221,61 @@ def run_ours(args, rank, local_rank, world):
         # the bucket holding the first layers is reduced under K1's backward; flat buckets feed FusedAdam directly
         late = [model.embed_tokens.weight] + list(model.gbf.parameters()) + list(model.gbf_proj.parameters()) \
             + list(model.encoder.emb_layer_norm.parameters())
-        reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam,
-                                        bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
+        if args.workload != "hotpath":
+            reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam,
+                                            bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
+
+    hot = args.workload == "hotpath"
+    extra_params = []
+    if hot:
+        import numpy as np
+        import torch.nn.functional as F
+        from mmdti_b200.models.contrastive import CT_Regress
+        from mmdti_b200.models.fds import FDS
+        from mmdti_b200.models.infonce import InfoNCE
+        torch.manual_seed(5)
+        inf = InfoNCE(DIM, DIM).to(dev).train()
+        head = torch.nn.Linear(DIM, 1).to(dev)
+        smiles, y_h, w_h, stats = make_head_batch(1234 + rank)
+        fds = FDS(feature_dim=DIM, raw_data=np.array([0.0, 1.0]), col_data=None, using_scale=False, bucket_num=FDS_BUCKETS).to(dev)
+        fds.min_value, fds.bin_width = FDS_CFG["min_value"], FDS_CFG["bin_width"]
+        for k, v in stats.items():
+            getattr(fds, k).copy_(v)
+        d_smiles = smiles.to(dev)
+        extra_params = list(inf.parameters()) + list(head.parameters())
+        dp_ctx = None
+        if dist_on:
+            from mmdti_b200.dist import DataParallelCtx
+            for prm in extra_params:
+                dist.broadcast(prm.data, src=0)
+            # exchange 1: every rank scores its rows against the all-gathered global batch; the gradient exchange averages
+            dp_ctx = DataParallelCtx()
+            inf.dp = fds.dp = dp_ctx
+        if dist_on and use_graph:
+            reducer = OverlappedGradReducer(list(model.parameters()) + extra_params, average=True, tail_params=late,
+                                            keep_flat=not args.torch_adam,
+                                            bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
+        elif dist_on:
+            raise SystemExit("--workload hotpath at N > 1 needs the graphed step (drop --no-graph)")
 
     tokens, dmat, et, g, coord = make_batch(1234 + rank)
     # --inputs pair (default): the reference's batch format (src_tokens, src_distance, src_edge_type);
     # --inputs coords: tokens + coordinates only, the pair features are computed on the device
     host_inputs = (tokens, dmat, et) if args.inputs == "pair" else (tokens, coord)
+    n_enc_in = len(host_inputs)
+    if hot:
+        host_inputs = host_inputs + (y_h, w_h)             # targets and sample weights travel with the batch
     pin = [t.pin_memory() for t in host_inputs]
     dev_inputs = [t.to(dev) for t in host_inputs]
     d_g = g.to(dev)
     # Adam(eps 1e-6) as in tasks/trainer.py:160: mmdti_b200.optim.FusedAdam = one launch per step that also refreshes
     # the bf16 shadows of the encoder's GEMM weights (--torch-adam: torch.optim.Adam(fused=True) + per-step cast pass)
     if args.torch_adam:
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
+        opt = torch.optim.Adam(list(model.parameters()) + extra_params, lr=1e-4, eps=1e-6, fused=True, capturable=use_graph)
     else:
         from mmdti_b200.optim import FusedAdam
         flat = dist_on and use_graph
-        opt = FusedAdam(model.parameters(), lr=1e-4, eps=1e-6, shadows=model.encoder.use_external_lowp(),
+        opt = FusedAdam(list(model.parameters()) + extra_params, lr=1e-4, eps=1e-6, shadows=model.encoder.use_external_lowp(),
                         grad_scale=reducer.grad_scale if flat else 1.0, grad_source=reducer.reduced_grad if flat else None)
 
     params = [prm for prm in model.parameters() if prm.requires_grad]
@@ -201,8 +286,19 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     def full_step(*inp):
-        rep = step_model(*inp) if args.inputs == "pair" else step_model(inp[0], src_coord=inp[1])
-        loss = (rep * d_g).sum()
+        rep = step_model(*inp[:n_enc_in]) if args.inputs == "pair" else step_model(inp[0], src_coord=inp[1])
+        if hot:
+            y_d, w_d = inp[n_enc_in], inp[n_enc_in + 1]
+            rep = rep.float()
+            l_inf = inf(rep, d_smiles)                                     # a7: InfoNCE against the second modality
+            mk = inp[0].ne(0).unsqueeze(-1).float()
+            pooled = (rep * mk).sum(1) / mk.sum(1)                          # masked mean pooling (mm_model.py:571-576)
+            feats = fds.smooth(pooled * 1.0, y_d, 1)                        # a11: in place on the pooled features
+            logits = head(feats)
+            l_ct = CT_Regress(feats, y_d, logits, weights=w_d, w=0.2, dp=dp_ctx)     # a8: ConR sees the smoothed features
+            loss = F.mse_loss(logits, y_d) + 0.1 * l_inf + 0.1 * l_ct       # tasks/trainer.py:68-69,193
+        else:
+            loss = (rep * d_g).sum()
         loss.backward()
         if dist_on and use_graph:
             reducer.finish()                # exchange 2: join the overlapped NCCL all-reduces (captured in the graph)
@@ -320,7 +416,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": METRIC, "value": mols / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms", "per_gpu_batch": B_PER_GPU,
+            "config": {"workload": WORKLOADS[args.workload], "per_gpu_batch": B_PER_GPU,
                        "global_batch": B_PER_GPU * world, "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS,
                        "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
                        "optimizer": "Adam(eps=1e-6), " + ("torch fused" if args.torch_adam else "mmdti FusedAdam (one launch, writes bf16 weight shadows)"),
@@ -342,7 +438,7 @@ def run_ours(args, rank, local_rank, world):
             "kernel_breakdown": breakdown,
         }
         if world == 1 and not args.no_cpu_baseline:
-            val, sec, cores = cpu_reference_run(steps=3, warmup=1, sample_b=32)
+            val, sec, cores = cpu_reference_run(steps=3, warmup=1, sample_b=32, workload=args.workload)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "32 of the 128 molecules per step, 3 timed steps (%.1f s/step), fp32, "
                                               "oracle/restate.py on the host cores" % sec}
@@ -371,6 +467,8 @@ def main():
     ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of mmdti_b200.optim.FusedAdam")
     ap.add_argument("--inputs", default="pair", choices=["pair", "coords"],
                     help="host batch format of the e2e path: the reference's (tokens, distance, edge_type) or (tokens, coordinates)")
+    ap.add_argument("--workload", default="encoder", choices=sorted(WORKLOADS),
+                    help="encoder = BASELINE configs[1] (default); hotpath = encoder + InfoNCE + FDS.smooth + ConR in the step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

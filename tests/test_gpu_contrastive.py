@@ -172,6 +172,9 @@ def test_infonce_module_matches_oracle_head():
     with mmdti_b200.precision(act="fp32"):
         got = mod(query.cuda(), pos.cuda())
     assert rel_err(got, ref) < 2e-5
+    with mmdti_b200.precision(act="bf16"):            # projection GEMMs on bf16 operands, fp32 accumulate
+        got = mod(query.cuda(), pos.cuda())
+    assert rel_err(got, ref) < 2e-3, rel_err(got, ref)
     assert sorted(mod.state_dict()) == sorted(["info_proj_query.0.weight", "info_proj_query.0.bias", "info_proj_query.2.weight",
                                                "info_proj_query.2.bias", "info_proj_positive.0.weight",
                                                "info_proj_positive.0.bias", "info_proj_positive.2.weight",
