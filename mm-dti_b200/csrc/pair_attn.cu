@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
             prefetch(w + 1, sn);
         }
 
-        if (warp < p.crb && row0 + warp * 16 < L) {
+        // One 16-row block per warp.  HB = false: rows +8..15 of the block lie beyond L (the leftover block of L = 66 holds 2
+        // rows), so every per-element instruction of that half is dropped; its mma operands are zero.
+        auto row_block = [&](auto hb_tag) {
+            constexpr bool HB = decltype(hb_tag)::value;
             const T* Ks = stage(s).K;
             const T* Vs = stage(s).V;
             const T* Qs = stage(s).Q;
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                 const uint32_t* ka_ = p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW;
                 const uint32_t* kb_ = p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW;
 #pragma unroll
-                for (int i = 0; i < NW; ++i) { wa[i] = ka_[i]; wb[i] = kb_[i]; }
+                for (int i = 0; i < NW; ++i) { wa[i] = ka_[i]; wb[i] = HB ? kb_[i] : 0u; }
             } else {
 #pragma unroll
                 for (int i = 0; i < NW; ++i) wa[i] = wb[i] = 0u;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
             if constexpr (!F32) {
                 const uint32_t* Q32 = reinterpret_cast<const uint32_t*>(Qs);
                 const uint32_t* K32 = reinterpret_cast<const uint32_t*>(Ks);
-                const uint32_t qa0 = Q32[la * 4 + q4], qa1 = Q32[lb * 4 + q4];
+                const uint32_t qa0 = Q32[la * 4 + q4], qa1 = HB ? Q32[lb * 4 + q4] : 0u;
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
                     sc[kb][0] = sc[kb][1] = sc[kb][2] = sc[kb][3] = 0.f;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
             } else {
                 float qa[HD], qb[HD];
 #pragma unroll
-                for (int d = 0; d < HD; ++d) { qa[d] = Qs[la * HD + d]; qb[d] = Qs[lb * HD + d]; }
+                for (int d = 0; d < HD; ++d) { qa[d] = Qs[la * HD + d]; qb[d] = HB ? Qs[lb * HD + d] : 0.f; }
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
 #pragma unroll
@@ -261,15 +264,21 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 const int col = kb * 8 + 2 * q4;
-                const float2 pa = slab_get2<TP>(srow_a, col), pb = slab_get2<TP>(srow_b, col);
+                const float2 pa = slab_get2<TP>(srow_a, col);
                 const float2 va = slab_put2<TP>(srow_a, col, fmaf(sc[kb][0], p.scale, pa.x), fmaf(sc[kb][1], p.scale, pa.y));
-                const float2 vb = slab_put2<TP>(srow_b, col, fmaf(sc[kb][2], p.scale, pb.x), fmaf(sc[kb][3], p.scale, pb.y));
-                sc[kb][0] = va.x; sc[kb][1] = va.y; sc[kb][2] = vb.x; sc[kb][3] = vb.y;
+                sc[kb][0] = va.x; sc[kb][1] = va.y;
                 ma = fmaxf(ma, fmaxf(va.x, va.y));
-                mb = fmaxf(mb, fmaxf(vb.x, vb.y));
+                if constexpr (HB) {
+                    const float2 pb = slab_get2<TP>(srow_b, col);
+                    const float2 vb = slab_put2<TP>(srow_b, col, fmaf(sc[kb][2], p.scale, pb.x), fmaf(sc[kb][3], p.scale, pb.y));
+                    sc[kb][2] = vb.x; sc[kb][3] = vb.y;
+                    mb = fmaxf(mb, fmaxf(vb.x, vb.y));
+                } else {
+                    sc[kb][2] = sc[kb][3] = 0.f;
+                }
             }
             ma = quad_max(ma);
-            mb = quad_max(mb);
+            if constexpr (HB) mb = quad_max(mb);
 
             // ---- softmax numerators, row sums, dropout
             float suma = 0.f, sumb = 0.f;
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
                     sc[kb][0] = expf(sc[kb][0] - ma); sc[kb][1] = expf(sc[kb][1] - ma);
-                    sc[kb][2] = expf(sc[kb][2] - mb); sc[kb][3] = expf(sc[kb][3] - mb);
+                    if constexpr (HB) { sc[kb][2] = expf(sc[kb][2] - mb); sc[kb][3] = expf(sc[kb][3] - mb); }
                 }
             } else {
                 const float ka = ma * LOG2E, kbm = mb * LOG2E;
@@ -285,14 +294,16 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                 for (int kb = 0; kb < NKB; ++kb) {
                     sc[kb][0] = fast_ex2(fmaf(sc[kb][0], LOG2E, -ka));
                     sc[kb][1] = fast_ex2(fmaf(sc[kb][1], LOG2E, -ka));
-                    sc[kb][2] = fast_ex2(fmaf(sc[kb][2], LOG2E, -kbm));
-                    sc[kb][3] = fast_ex2(fmaf(sc[kb][3], LOG2E, -kbm));
+                    if constexpr (HB) {
+                        sc[kb][2] = fast_ex2(fmaf(sc[kb][2], LOG2E, -kbm));
+                        sc[kb][3] = fast_ex2(fmaf(sc[kb][3], LOG2E, -kbm));
+                    }
                 }
             }
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 suma += sc[kb][0] + sc[kb][1];
-                sumb += sc[kb][2] + sc[kb][3];
+                if constexpr (HB) sumb += sc[kb][2] + sc[kb][3];
             }
             // dropout: one hash per 4 elements; the odd column's 16 bits are compared in place (bits >= t << 16),
             // the even column's after one shift
@@ -306,31 +317,41 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                     const uint32_t m0 = 1u << (8 * (kb & 3)), m1 = 2u << (8 * (kb & 3));
                     if (!(wa[kb >> 2] & m0)) sc[kb][0] = 0.f;
                     if (!(wa[kb >> 2] & m1)) sc[kb][1] = 0.f;
-                    if (!(wb[kb >> 2] & m0)) sc[kb][2] = 0.f;
-                    if (!(wb[kb >> 2] & m1)) sc[kb][3] = 0.f;
+                    if constexpr (HB) {
+                        if (!(wb[kb >> 2] & m0)) sc[kb][2] = 0.f;
+                        if (!(wb[kb >> 2] & m1)) sc[kb][3] = 0.f;
+                    }
                 }
-            } else             if (do_drop) {
+            } else if (do_drop) {
                 const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
                 const uint32_t thi = p.thresh16 << 16;
 #pragma unroll
                 for (int kb = 0; kb < NKB; kb += 2) {
-                    const uint2 wa = rng_quad_bits(rkey, ra, kb * 8 + 2 * q4), wb = rng_quad_bits(rkey, rbb, kb * 8 + 2 * q4);
+                    const uint2 wa = rng_quad_bits(rkey, ra, kb * 8 + 2 * q4);
                     if ((wa.x << 16) < thi) sc[kb][0] = 0.f;
                     if (wa.x < thi) sc[kb][1] = 0.f;
-                    if ((wb.x << 16) < thi) sc[kb][2] = 0.f;
-                    if (wb.x < thi) sc[kb][3] = 0.f;
                     if (kb + 1 < NKB) {
                         if ((wa.y << 16) < thi) sc[kb + 1][0] = 0.f;
                         if (wa.y < thi) sc[kb + 1][1] = 0.f;
-                        if ((wb.y << 16) < thi) sc[kb + 1][2] = 0.f;
-                        if (wb.y < thi) sc[kb + 1][3] = 0.f;
+                    }
+                    if constexpr (HB) {
+                        const uint2 wb = rng_quad_bits(rkey, rbb, kb * 8 + 2 * q4);
+                        if ((wb.x << 16) < thi) sc[kb][2] = 0.f;
+                        if (wb.x < thi) sc[kb][3] = 0.f;
+                        if (kb + 1 < NKB) {
+                            if ((wb.y << 16) < thi) sc[kb + 1][2] = 0.f;
+                            if (wb.y < thi) sc[kb + 1][3] = 0.f;
+                        }
                     }
                 }
             }
             suma = quad_sum(suma);
-            sumb = quad_sum(sumb);
             const float inva = F32 ? p.keep_scale / suma : p.keep_scale * fast_rcp(suma);
-            const float invb = F32 ? p.keep_scale / sumb : p.keep_scale * fast_rcp(sumb);
+            float invb = 0.f;
+            if constexpr (HB) {
+                sumb = quad_sum(sumb);
+                invb = F32 ? p.keep_scale / sumb : p.keep_scale * fast_rcp(sumb);
+            }
             T* og = static_cast<T*>(p.o) + (size_t)b * L * p.ldo + h * HD;
 
             // ---- O = A' V
@@ -358,7 +379,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                 }
                 if (ra < L)
                     *reinterpret_cast<uint32_t*>(og + (size_t)ra * p.ldo + 2 * q4) = pack_bf16(o[0] * inva, o[1] * inva);
-                if (rbb < L)
+                if (HB && rbb < L)
                     *reinterpret_cast<uint32_t*>(og + (size_t)rbb * p.ldo + 2 * q4) = pack_bf16(o[2] * invb, o[3] * invb);
             } else {
                 float oa[HD], ob[HD];
@@ -379,7 +400,7 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
 #pragma unroll
                 for (int d = 0; d < HD; ++d) {
                     oa[d] = quad_sum(oa[d]) * inva;
-                    ob[d] = quad_sum(ob[d]) * invb;
+                    if constexpr (HB) ob[d] = quad_sum(ob[d]) * invb;
                 }
                 if (q4 == 0) {
                     if (ra < L) {
@@ -387,13 +408,17 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                         dst[0] = make_float4(oa[0], oa[1], oa[2], oa[3]);
                         dst[1] = make_float4(oa[4], oa[5], oa[6], oa[7]);
                     }
-                    if (rbb < L) {
+                    if (HB && rbb < L) {
                         float4* dst = reinterpret_cast<float4*>(og + (size_t)rbb * p.ldo);
                         dst[0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
                         dst[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
                     }
                 }
             }
+        };
+        if (warp < p.crb && row0 + warp * 16 < L) {
+            if (row0 + warp * 16 + 8 < L) row_block(std::true_type{});
+            else row_block(std::false_type{});
         }
         fence_proxy_async();
         __syncthreads();
@@ -554,7 +579,10 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
         T* dSt = ALIAS_DS ? reinterpret_cast<T*>(stage(s).sG) : dSt_own;
 
         // ================= phase 1: per 16-row block: A, dA, dS, dQ
-        if (warp < nrb_chunk) {
+        // HB = false: rows +8..15 of the warp's 16-row block lie beyond L (the leftover block of L = 66 holds 2 rows): the
+        // per-element work of that half is dropped; its A' / dS rows are stored as zeros (phase 2 reads whole blocks).
+        auto row_block = [&](auto hb_tag) {
+            constexpr bool HB = decltype(hb_tag)::value;
             const int la = warp * 16 + g, lb = la + 8;
             const int ra = row0 + la, rbb = row0 + lb;
             const TP* srow_a = stage(s).sS + la * G::STRIDE;
@@ -565,7 +593,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
             T* ap_b = Apt + lb * G::STRIDE;
             T* ds_a = dSt + la * G::STRIDE;
             T* ds_b = dSt + lb * G::STRIDE;
-            const bool va_ok = ra < L, vb_ok = rbb < L;
+            const bool va_ok = ra < L, vb_ok = HB && rbb < L;
             // keep-mask words of the two rows: issued first, consumed after the softmax recompute
             constexpr int NW = (NKB * 8 + 31) / 32;
             uint32_t kwa[NW], kwb[NW];
@@ -573,7 +601,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 const uint32_t* ka_ = p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW;
                 const uint32_t* kb_ = p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW;
 #pragma unroll
-                for (int i = 0; i < NW; ++i) { kwa[i] = ka_[i]; kwb[i] = kb_[i]; }
+                for (int i = 0; i < NW; ++i) { kwa[i] = ka_[i]; kwb[i] = HB ? kb_[i] : 0u; }
             } else {
 #pragma unroll
                 for (int i = 0; i < NW; ++i) kwa[i] = kwb[i] = 0u;
@@ -585,13 +613,19 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 const int col = kb * 8 + 2 * q4;
-                const float2 xa = slab_get2<TP>(srow_a, col), xb = slab_get2<TP>(srow_b, col);
-                sc[kb][0] = xa.x; sc[kb][1] = xa.y; sc[kb][2] = xb.x; sc[kb][3] = xb.y;
+                const float2 xa = slab_get2<TP>(srow_a, col);
+                sc[kb][0] = xa.x; sc[kb][1] = xa.y;
                 ma = fmaxf(ma, fmaxf(xa.x, xa.y));
-                mb = fmaxf(mb, fmaxf(xb.x, xb.y));
+                if constexpr (HB) {
+                    const float2 xb = slab_get2<TP>(srow_b, col);
+                    sc[kb][2] = xb.x; sc[kb][3] = xb.y;
+                    mb = fmaxf(mb, fmaxf(xb.x, xb.y));
+                } else {
+                    sc[kb][2] = sc[kb][3] = 0.f;
+                }
             }
             ma = quad_max(ma);
-            mb = quad_max(mb);
+            if constexpr (HB) mb = quad_max(mb);
             if (!(ma > -INFINITY)) ma = 0.f;      // stale / fully masked rows: keep everything finite
             if (!(mb > -INFINITY)) mb = 0.f;
             float suma = 0.f, sumb = 0.f;
@@ -599,7 +633,7 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
 #pragma unroll
                 for (int kb = 0; kb < NKB; ++kb) {
                     sc[kb][0] = expf(sc[kb][0] - ma); sc[kb][1] = expf(sc[kb][1] - ma);
-                    sc[kb][2] = expf(sc[kb][2] - mb); sc[kb][3] = expf(sc[kb][3] - mb);
+                    if constexpr (HB) { sc[kb][2] = expf(sc[kb][2] - mb); sc[kb][3] = expf(sc[kb][3] - mb); }
                 }
             } else {
                 const float ka = ma * LOG2E, kbm = mb * LOG2E;
@@ -607,17 +641,19 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 for (int kb = 0; kb < NKB; ++kb) {
                     sc[kb][0] = fast_ex2(fmaf(sc[kb][0], LOG2E, -ka));
                     sc[kb][1] = fast_ex2(fmaf(sc[kb][1], LOG2E, -ka));
-                    sc[kb][2] = fast_ex2(fmaf(sc[kb][2], LOG2E, -kbm));
-                    sc[kb][3] = fast_ex2(fmaf(sc[kb][3], LOG2E, -kbm));
+                    if constexpr (HB) {
+                        sc[kb][2] = fast_ex2(fmaf(sc[kb][2], LOG2E, -kbm));
+                        sc[kb][3] = fast_ex2(fmaf(sc[kb][3], LOG2E, -kbm));
+                    }
                 }
             }
 #pragma unroll
             for (int kb = 0; kb < NKB; ++kb) {
                 suma += sc[kb][0] + sc[kb][1];
-                sumb += sc[kb][2] + sc[kb][3];
+                if constexpr (HB) sumb += sc[kb][2] + sc[kb][3];
             }
             suma = quad_sum(suma);
-            sumb = quad_sum(sumb);
+            if constexpr (HB) sumb = quad_sum(sumb);
             // rows beyond L (stale slab rows) get A = 0
             const float inva = (va_ok && suma > 0.f) ? (F32 ? 1.f / suma : fast_rcp(suma)) : 0.f;
             const float invb = (vb_ok && sumb > 0.f) ? (F32 ? 1.f / sumb : fast_rcp(sumb)) : 0.f;
@@ -630,21 +666,24 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 const uint32_t* dO32 = reinterpret_cast<const uint32_t*>(dOs);
                 const uint32_t* O32 = reinterpret_cast<const uint32_t*>(Os);
                 ga0 = dO32[la * 4 + q4];
-                ga1 = dO32[lb * 4 + q4];
                 const float2 x = unpack_bf16(ga0), y = unpack_bf16(O32[la * 4 + q4]);
-                const float2 x2 = unpack_bf16(ga1), y2 = unpack_bf16(O32[lb * 4 + q4]);
                 dela = x.x * y.x + x.y * y.y;
-                delb = x2.x * y2.x + x2.y * y2.y;
+                delb = 0.f;
+                if constexpr (HB) {
+                    ga1 = dO32[lb * 4 + q4];
+                    const float2 x2 = unpack_bf16(ga1), y2 = unpack_bf16(O32[lb * 4 + q4]);
+                    delb = x2.x * y2.x + x2.y * y2.y;
+                }
             } else {
                 const float* dOf = reinterpret_cast<const float*>(dOs);
                 const float* Of = reinterpret_cast<const float*>(Os);
 #pragma unroll
-                for (int d = 0; d < HD; ++d) { gfa[d] = dOf[la * HD + d]; gfb[d] = dOf[lb * HD + d]; }
+                for (int d = 0; d < HD; ++d) { gfa[d] = dOf[la * HD + d]; gfb[d] = HB ? dOf[lb * HD + d] : 0.f; }
                 dela = dOf[la * HD + 2 * q4] * Of[la * HD + 2 * q4] + dOf[la * HD + 2 * q4 + 1] * Of[la * HD + 2 * q4 + 1];
-                delb = dOf[lb * HD + 2 * q4] * Of[lb * HD + 2 * q4] + dOf[lb * HD + 2 * q4 + 1] * Of[lb * HD + 2 * q4 + 1];
+                delb = HB ? dOf[lb * HD + 2 * q4] * Of[lb * HD + 2 * q4] + dOf[lb * HD + 2 * q4 + 1] * Of[lb * HD + 2 * q4 + 1] : 0.f;
             }
             dela = quad_sum(dela);
-            delb = quad_sum(delb);
+            if constexpr (HB) delb = quad_sum(delb);
 
             // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
             const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
@@ -675,43 +714,55 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                     const uint32_t m0 = 1u << (8 * (kb & 3)), m1 = 2u << (8 * (kb & 3));
                     k0 = (kwa[kb >> 2] & m0) ? p.keep_scale : 0.f;
                     k1 = (kwa[kb >> 2] & m1) ? p.keep_scale : 0.f;
-                    k2 = (kwb[kb >> 2] & m0) ? p.keep_scale : 0.f;
-                    k3 = (kwb[kb >> 2] & m1) ? p.keep_scale : 0.f;
+                    if constexpr (HB) {
+                        k2 = (kwb[kb >> 2] & m0) ? p.keep_scale : 0.f;
+                        k3 = (kwb[kb >> 2] & m1) ? p.keep_scale : 0.f;
+                    }
                 } else if (do_drop) {
-                    if ((kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
+                    if ((kb & 1) == 0) {
+                        qwa = rng_quad_bits(rkey, ra, col);
+                        if constexpr (HB) qwb = rng_quad_bits(rkey, rbb, col);
+                    }
                     const uint32_t ba = (kb & 1) ? qwa.y : qwa.x, bb = (kb & 1) ? qwb.y : qwb.x;
                     const uint32_t thi = p.thresh16 << 16;
                     k0 = (ba << 16) >= thi ? p.keep_scale : 0.f;
                     k1 = ba >= thi ? p.keep_scale : 0.f;
-                    k2 = (bb << 16) >= thi ? p.keep_scale : 0.f;
-                    k3 = bb >= thi ? p.keep_scale : 0.f;
+                    if constexpr (HB) {
+                        k2 = (bb << 16) >= thi ? p.keep_scale : 0.f;
+                        k3 = bb >= thi ? p.keep_scale : 0.f;
+                    }
                 }
-                const float A0 = sc[kb][0] * inva, A1 = sc[kb][1] * inva, A2 = sc[kb][2] * invb, A3 = sc[kb][3] * invb;
-                if constexpr (F32) {
-                    *reinterpret_cast<float2*>(ap_a + col) = make_float2(A0 * k0, A1 * k1);
-                    *reinterpret_cast<float2*>(ap_b + col) = make_float2(A2 * k2, A3 * k3);
-                } else {
-                    *reinterpret_cast<uint32_t*>(ap_a + col) = pack_bf16(A0 * k0, A1 * k1);
-                    *reinterpret_cast<uint32_t*>(ap_b + col) = pack_bf16(A2 * k2, A3 * k3);
-                }
-                float2 ua = make_float2(0.f, 0.f), ub = make_float2(0.f, 0.f);
-                if (has_dpo) {
-                    ua = slab_get2<TG>(grow_a, col);
-                    ub = slab_get2<TG>(grow_b, col);
-                }
+                const float A0 = sc[kb][0] * inva, A1 = sc[kb][1] * inva;
+                if constexpr (F32) *reinterpret_cast<float2*>(ap_a + col) = make_float2(A0 * k0, A1 * k1);
+                else *reinterpret_cast<uint32_t*>(ap_a + col) = pack_bf16(A0 * k0, A1 * k1);
+                float2 ua = make_float2(0.f, 0.f);
+                if (has_dpo) ua = slab_get2<TG>(grow_a, col);
                 float d0 = fmaf(A0, fmaf(da[0], k0, -dela), ua.x);
                 float d1 = fmaf(A1, fmaf(da[1], k1, -dela), ua.y);
-                float d2 = fmaf(A2, fmaf(da[2], k2, -delb), ub.x);
-                float d3 = fmaf(A3, fmaf(da[3], k3, -delb), ub.y);
                 if (!va_ok) { d0 = 0.f; d1 = 0.f; }      // rows beyond L: stale slab rows
-                if (!vb_ok) { d2 = 0.f; d3 = 0.f; }
                 // stored (rounded) values are what the previous layer sees; use them for dQ/dK too
                 const float2 sa = slab_put2<TG>(grow_a, col, d0, d1);
-                const float2 sb = slab_put2<TG>(grow_b, col, d2, d3);
-                sc[kb][0] = sa.x; sc[kb][1] = sa.y; sc[kb][2] = sb.x; sc[kb][3] = sb.y;
-                if constexpr (!ALIAS_DS) {
-                    *reinterpret_cast<uint32_t*>(ds_a + col) = pack_bf16(sa.x, sa.y);
-                    *reinterpret_cast<uint32_t*>(ds_b + col) = pack_bf16(sb.x, sb.y);
+                sc[kb][0] = sa.x; sc[kb][1] = sa.y;
+                if constexpr (!ALIAS_DS) *reinterpret_cast<uint32_t*>(ds_a + col) = pack_bf16(sa.x, sa.y);
+                if constexpr (HB) {
+                    const float A2 = sc[kb][2] * invb, A3 = sc[kb][3] * invb;
+                    if constexpr (F32) *reinterpret_cast<float2*>(ap_b + col) = make_float2(A2 * k2, A3 * k3);
+                    else *reinterpret_cast<uint32_t*>(ap_b + col) = pack_bf16(A2 * k2, A3 * k3);
+                    float2 ub = make_float2(0.f, 0.f);
+                    if (has_dpo) ub = slab_get2<TG>(grow_b, col);
+                    float d2 = fmaf(A2, fmaf(da[2], k2, -delb), ub.x);
+                    float d3 = fmaf(A3, fmaf(da[3], k3, -delb), ub.y);
+                    if (!vb_ok) { d2 = 0.f; d3 = 0.f; }
+                    const float2 sb = slab_put2<TG>(grow_b, col, d2, d3);
+                    sc[kb][2] = sb.x; sc[kb][3] = sb.y;
+                    if constexpr (!ALIAS_DS) *reinterpret_cast<uint32_t*>(ds_b + col) = pack_bf16(sb.x, sb.y);
+                } else {
+                    // zero rows: with several chunks per tile the same local rows held real values one chunk earlier
+                    if constexpr (F32) *reinterpret_cast<float2*>(ap_b + col) = make_float2(0.f, 0.f);
+                    else *reinterpret_cast<uint32_t*>(ap_b + col) = 0u;
+                    slab_put2<TG>(grow_b, col, 0.f, 0.f);
+                    sc[kb][2] = sc[kb][3] = 0.f;
+                    if constexpr (!ALIAS_DS) *reinterpret_cast<uint32_t*>(ds_b + col) = 0u;
                 }
             }
 
@@ -777,6 +828,10 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                     }
                 }
             }
+        };
+        if (warp < nrb_chunk) {
+            if (row0 + warp * 16 + 8 < L) row_block(std::true_type{});
+            else row_block(std::false_type{});
         }
         fence_proxy_async();
         __syncthreads();
