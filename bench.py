@@ -38,6 +38,16 @@ WORKLOADS = {"encoder": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms",
              "hotpath": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd"}
 
 
+def set_shape(batch, n_atoms, smiles_len):
+    """Default = BASELINE configs[1] (128 x 64 atoms).  --batch 32 --n-atoms 256 --smiles-len 256 with --workload hotpath is
+    the per-GPU shape of configs[3] (large-molecule stress: L = 258, ConR + FDS)."""
+    global B_PER_GPU, N_ATOMS, L, S_SMILES
+    B_PER_GPU, N_ATOMS, S_SMILES = batch, n_atoms, smiles_len
+    L = N_ATOMS + 2
+    for k in WORKLOADS:
+        WORKLOADS[k] = WORKLOADS[k].replace("b128x64atoms", "b%dx%datoms" % (batch, n_atoms))
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -95,9 +105,10 @@ def make_batch(seed):
     return tokens, dist, et, g, coord
 
 
-def make_head_batch(seed, n=B_PER_GPU):
+def make_head_batch(seed, n=None):
     """Inputs of the contrastive head: second-modality activations (B, S, 512), standard-scaled regression targets,
     sample weights (mean 1), and FDS statistics of a previous epoch."""
+    n = B_PER_GPU if n is None else n
     gen = torch.Generator().manual_seed(seed + 11)
     smiles = torch.randn(n, S_SMILES, DIM, generator=gen) * 0.5
     y = torch.randn(n, 1, generator=gen)
@@ -128,6 +139,7 @@ def cpu_reference_run(steps, warmup, sample_b=32, workload="encoder"):
     torch.set_num_threads(cores)
     p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5).items()}
     tokens, dist, et, g, _ = make_batch(1234)
+    sample_b = min(sample_b, B_PER_GPU)
     tokens, dist, et, g = tokens[:sample_b], dist[:sample_b], et[:sample_b], g[:sample_b]
     hot = workload == "hotpath"
     if hot:
@@ -168,8 +180,9 @@ def run_reference(args, rank):
         return
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
-    sample_b = 32
+    sample_b = args.cpu_sample
     val, sec, cores = cpu_reference_run(steps, warm, sample_b, args.workload)
+    sample_b = min(sample_b, B_PER_GPU)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -438,10 +451,10 @@ def run_ours(args, rank, local_rank, world):
             "kernel_breakdown": breakdown,
         }
         if world == 1 and not args.no_cpu_baseline:
-            val, sec, cores = cpu_reference_run(steps=3, warmup=1, sample_b=32, workload=args.workload)
+            val, sec, cores = cpu_reference_run(steps=3, warmup=1, sample_b=args.cpu_sample, workload=args.workload)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "32 of the 128 molecules per step, 3 timed steps (%.1f s/step), fp32, "
-                                              "oracle/restate.py on the host cores" % sec}
+                                    "sample": "%d of the %d molecules per step, 3 timed steps (%.1f s/step), fp32, "
+                                              "oracle/restate.py on the host cores" % (min(args.cpu_sample, B_PER_GPU), B_PER_GPU, sec)}
         print(json.dumps(line), file=json_out, flush=True)
     if dist_on:
         # tear down in a fixed order: drain the device, drop the captured graph (it holds NCCL kernels), then leave
@@ -469,8 +482,13 @@ def main():
                     help="host batch format of the e2e path: the reference's (tokens, distance, edge_type) or (tokens, coordinates)")
     ap.add_argument("--workload", default="encoder", choices=sorted(WORKLOADS),
                     help="encoder = BASELINE configs[1] (default); hotpath = encoder + InfoNCE + FDS.smooth + ConR in the step")
+    ap.add_argument("--batch", type=int, default=128, help="molecules per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--n-atoms", type=int, default=64, help="atoms per molecule; L = n_atoms + 2 <= 264")
+    ap.add_argument("--smiles-len", type=int, default=64, help="length of the second-modality sequence (hotpath workload)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="molecules per step of the CPU arm's bounded sample")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
+    set_shape(args.batch, args.n_atoms, args.smiles_len)
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
