@@ -25,6 +25,7 @@ namespace {
 
 constexpr int HD = MMDTI_HEAD_DIM;  // 8
 constexpr int NSTAGE = 2;      // backward ring
+constexpr bool K2_BWD_CS_DEFAULT = true;    // column-split backward for L > 136 (MMDTI_K2_BWD_CS=0/1 overrides)
 constexpr int NSTAGE_F = 3;    // forward ring: the bulk store of item w-1 may still be reading its stage while w+1 loads
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -458,13 +459,16 @@ struct BwdStage {
     }
 };
 
-template <typename T, typename TP, typename TG, int NKB>
-__global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
+// CS (column split, bf16 activations, NKB >= 25 i.e. L > 136): shared memory limits a chunk to 32 rows at two CTAs per SM, so
+// with one warp per 16-row block only 2 warps per CTA would work in phase 1.  Instead 4 warps share a row block, each owning
+// a quarter of the key blocks: row max / row sum / dQ partials are exchanged through shared memory behind a named barrier.
+template <typename T, typename TP, typename TG, int NKB, bool CS = false>
+__global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const BwdParams p) {
     using G = Geo<NKB>;
     constexpr bool F32 = std::is_same<T, float>::value;
     // dS in the mma operand type: aliases the dP slab when that already has this type
     constexpr bool ALIAS_DS = std::is_same<T, TG>::value;
-    constexpr int MAXKB16 = G::MAXKB16;
+    constexpr int MAXKB16 = CS ? (G::NKB16 + 7) / 8 : G::MAXKB16;      // CS: always 8 warps
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NSTAGE];
 
@@ -829,7 +833,190 @@ __global__ void __launch_bounds__(256) pair_attn_bwd_kernel(const BwdParams p) {
                 }
             }
         };
-        if (warp < nrb_chunk) {
+        if constexpr (CS) {
+            constexpr int NSPLIT = 4;
+            constexpr int KBW = (NKB + NSPLIT - 1) / NSPLIT;          // key blocks per warp
+            __shared__ float cs_max[2][NSPLIT][16];
+            __shared__ float cs_sum[2][NSPLIT][16];
+            __shared__ float cs_dq[2][NSPLIT - 1][16][HD];
+            const int rb = warp >> 2, cs = warp & 3;                   // launched with 8 warps, crb = 2
+            if (rb < nrb_chunk) {
+                const int kb0 = cs * KBW;
+                const int la = rb * 16 + g, lb = la + 8;
+                const int ra = row0 + la, rbb = row0 + lb;
+                const TP* srow_a = stage(s).sS + la * G::STRIDE;
+                const TP* srow_b = stage(s).sS + lb * G::STRIDE;
+                TG* grow_a = stage(s).sG + la * G::STRIDE;
+                TG* grow_b = stage(s).sG + lb * G::STRIDE;
+                T* ap_a = Apt + la * G::STRIDE;
+                T* ap_b = Apt + lb * G::STRIDE;
+                T* ds_a = dSt + la * G::STRIDE;
+                T* ds_b = dSt + lb * G::STRIDE;
+                const bool va_ok = ra < L, vb_ok = rbb < L;
+                const unsigned bar_id = 1u + (unsigned)rb;
+
+                // ---- softmax recompute over this warp's key blocks; row max and row sum across the 4 warps
+                float sc[KBW][4];
+                float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < KBW; ++j) {
+                    const int kb = kb0 + j;
+                    if (kb < NKB) {
+                        const int col = kb * 8 + 2 * q4;
+                        const float2 xa = slab_get2<TP>(srow_a, col), xb = slab_get2<TP>(srow_b, col);
+                        sc[j][0] = xa.x; sc[j][1] = xa.y; sc[j][2] = xb.x; sc[j][3] = xb.y;
+                        ma = fmaxf(ma, fmaxf(xa.x, xa.y));
+                        mb = fmaxf(mb, fmaxf(xb.x, xb.y));
+                    } else {
+                        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
+                    }
+                }
+                ma = quad_max(ma);
+                mb = quad_max(mb);
+                if (q4 == 0) { cs_max[rb][cs][g] = ma; cs_max[rb][cs][g + 8] = mb; }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(128) : "memory");
+#pragma unroll
+                for (int c = 0; c < NSPLIT; ++c) {
+                    ma = fmaxf(ma, cs_max[rb][c][g]);
+                    mb = fmaxf(mb, cs_max[rb][c][g + 8]);
+                }
+                if (!(ma > -INFINITY)) ma = 0.f;      // stale / fully masked rows: keep everything finite
+                if (!(mb > -INFINITY)) mb = 0.f;
+                float suma = 0.f, sumb = 0.f;
+                {
+                    const float ka = ma * LOG2E, kbm = mb * LOG2E;
+#pragma unroll
+                    for (int j = 0; j < KBW; ++j) {
+                        sc[j][0] = fast_ex2(fmaf(sc[j][0], LOG2E, -ka));
+                        sc[j][1] = fast_ex2(fmaf(sc[j][1], LOG2E, -ka));
+                        sc[j][2] = fast_ex2(fmaf(sc[j][2], LOG2E, -kbm));
+                        sc[j][3] = fast_ex2(fmaf(sc[j][3], LOG2E, -kbm));
+                        suma += sc[j][0] + sc[j][1];
+                        sumb += sc[j][2] + sc[j][3];
+                    }
+                }
+                suma = quad_sum(suma);
+                sumb = quad_sum(sumb);
+                if (q4 == 0) { cs_sum[rb][cs][g] = suma; cs_sum[rb][cs][g + 8] = sumb; }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(128) : "memory");
+                suma = 0.f;
+                sumb = 0.f;
+#pragma unroll
+                for (int c = 0; c < NSPLIT; ++c) {
+                    suma += cs_sum[rb][c][g];
+                    sumb += cs_sum[rb][c][g + 8];
+                }
+                const float inva = (va_ok && suma > 0.f) ? fast_rcp(suma) : 0.f;
+                const float invb = (vb_ok && sumb > 0.f) ? fast_rcp(sumb) : 0.f;
+
+                // ---- delta = dO . O per row (every warp of the row block evaluates it); dO fragments
+                const uint32_t* dO32 = reinterpret_cast<const uint32_t*>(dOs);
+                const uint32_t* O32 = reinterpret_cast<const uint32_t*>(Os);
+                const uint32_t ga0 = dO32[la * 4 + q4], ga1 = dO32[lb * 4 + q4];
+                float dela, delb;
+                {
+                    const float2 x = unpack_bf16(ga0), y = unpack_bf16(O32[la * 4 + q4]);
+                    const float2 x2 = unpack_bf16(ga1), y2 = unpack_bf16(O32[lb * 4 + q4]);
+                    dela = quad_sum(x.x * y.x + x.y * y.y);
+                    delb = quad_sum(x2.x * y2.x + x2.y * y2.y);
+                }
+
+                // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
+                const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
+                const uint32_t thi = p.thresh16 << 16;
+                const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
+                constexpr int NW = (NKB * 8 + 31) / 32;
+                const uint32_t* ka_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW : nullptr;
+                const uint32_t* kb_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW : nullptr;
+                uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
+#pragma unroll
+                for (int j = 0; j < KBW; ++j) {
+                    const int kb = kb0 + j;
+                    if (kb < NKB) {
+                        const int col = kb * 8 + 2 * q4;
+                        float da[4] = {0.f, 0.f, 0.f, 0.f};
+                        mma_bf16_1688(da, ga0, ga1, Vs32[(kb * 8 + g) * 4 + q4]);
+                        float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+                        if (do_drop && ka_) {
+                            const int sh = 8 * (kb & 3) + 2 * q4;
+                            const uint32_t wa_ = ka_[kb >> 2] >> sh, wb_ = kb_[kb >> 2] >> sh;
+                            k0 = (wa_ & 1u) ? p.keep_scale : 0.f;
+                            k1 = (wa_ & 2u) ? p.keep_scale : 0.f;
+                            k2 = (wb_ & 1u) ? p.keep_scale : 0.f;
+                            k3 = (wb_ & 2u) ? p.keep_scale : 0.f;
+                        } else if (do_drop) {
+                            // one hash serves the key-block pair (2m, 2m+1): .x even block, .y odd block
+                            if (j == 0 || (kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
+                            const uint32_t ba = (kb & 1) ? qwa.y : qwa.x, bb = (kb & 1) ? qwb.y : qwb.x;
+                            k0 = (ba << 16) >= thi ? p.keep_scale : 0.f;
+                            k1 = ba >= thi ? p.keep_scale : 0.f;
+                            k2 = (bb << 16) >= thi ? p.keep_scale : 0.f;
+                            k3 = bb >= thi ? p.keep_scale : 0.f;
+                        }
+                        const float A0 = sc[j][0] * inva, A1 = sc[j][1] * inva, A2 = sc[j][2] * invb, A3 = sc[j][3] * invb;
+                        *reinterpret_cast<uint32_t*>(ap_a + col) = pack_bf16(A0 * k0, A1 * k1);
+                        *reinterpret_cast<uint32_t*>(ap_b + col) = pack_bf16(A2 * k2, A3 * k3);
+                        float2 ua = make_float2(0.f, 0.f), ub = make_float2(0.f, 0.f);
+                        if (has_dpo) {
+                            ua = slab_get2<TG>(grow_a, col);
+                            ub = slab_get2<TG>(grow_b, col);
+                        }
+                        float d0 = fmaf(A0, fmaf(da[0], k0, -dela), ua.x);
+                        float d1 = fmaf(A1, fmaf(da[1], k1, -dela), ua.y);
+                        float d2 = fmaf(A2, fmaf(da[2], k2, -delb), ub.x);
+                        float d3 = fmaf(A3, fmaf(da[3], k3, -delb), ub.y);
+                        if (!va_ok) { d0 = 0.f; d1 = 0.f; }      // rows beyond L: stale slab rows
+                        if (!vb_ok) { d2 = 0.f; d3 = 0.f; }
+                        const float2 sa = slab_put2<TG>(grow_a, col, d0, d1);
+                        const float2 sb = slab_put2<TG>(grow_b, col, d2, d3);
+                        sc[j][0] = sa.x; sc[j][1] = sa.y; sc[j][2] = sb.x; sc[j][3] = sb.y;
+                        if constexpr (!ALIAS_DS) {
+                            *reinterpret_cast<uint32_t*>(ds_a + col) = pack_bf16(sa.x, sa.y);
+                            *reinterpret_cast<uint32_t*>(ds_b + col) = pack_bf16(sb.x, sb.y);
+                        }
+                    }
+                }
+
+                // ---- dQ = scale * dS K: partial over this warp's key blocks (pairs of 8-key blocks from kb0), summed by warp 0
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int jp = 0; jp < (KBW + 1) / 2; ++jp) {
+                    const int kbA = kb0 + 2 * jp;
+                    if (kbA < NKB) {
+                        uint32_t b0, b1;
+                        ldmatrix_x2_trans(b0, b1, Ks + (kbA * 8 + (lane & 15)) * HD);
+                        const uint32_t a0 = pack_bf16(sc[2 * jp][0], sc[2 * jp][1]);
+                        const uint32_t a1 = pack_bf16(sc[2 * jp][2], sc[2 * jp][3]);
+                        uint32_t a2 = 0u, a3 = 0u;
+                        if (2 * jp + 1 < KBW) {
+                            if (kbA + 1 < NKB) {
+                                a2 = pack_bf16(sc[2 * jp + 1][0], sc[2 * jp + 1][1]);
+                                a3 = pack_bf16(sc[2 * jp + 1][2], sc[2 * jp + 1][3]);
+                            }
+                        }
+                        mma_bf16_16816(o, a0, a1, a2, a3, b0, b1);
+                    }
+                }
+                if (cs > 0) {
+                    *reinterpret_cast<float2*>(&cs_dq[rb][cs - 1][g][2 * q4]) = make_float2(o[0], o[1]);
+                    *reinterpret_cast<float2*>(&cs_dq[rb][cs - 1][g + 8][2 * q4]) = make_float2(o[2], o[3]);
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(128) : "memory");
+                if (cs == 0) {
+#pragma unroll
+                    for (int c = 0; c < NSPLIT - 1; ++c) {
+                        const float2 x = *reinterpret_cast<const float2*>(&cs_dq[rb][c][g][2 * q4]);
+                        const float2 y = *reinterpret_cast<const float2*>(&cs_dq[rb][c][g + 8][2 * q4]);
+                        o[0] += x.x; o[1] += x.y; o[2] += y.x; o[3] += y.y;
+                    }
+                    T* dqg = static_cast<T*>(p.dq) + (size_t)b * L * p.lddqkv + h * HD;
+                    if (va_ok)
+                        *reinterpret_cast<uint32_t*>(dqg + (size_t)ra * p.lddqkv + 2 * q4) = pack_bf16(o[0] * p.scale, o[1] * p.scale);
+                    if (vb_ok)
+                        *reinterpret_cast<uint32_t*>(dqg + (size_t)rbb * p.lddqkv + 2 * q4) = pack_bf16(o[2] * p.scale, o[3] * p.scale);
+                }
+            }
+        } else if (warp < nrb_chunk) {
             if (row0 + warp * 16 + 8 < L) row_block(std::true_type{});
             else row_block(std::false_type{});
         }
@@ -1030,6 +1217,28 @@ int launch_bwd(BwdParams p, cudaStream_t st) {
         while (p.crb > 2 && smem_of(p.crb) > 113 * 1024) --p.crb;
     if (const char* e = getenv("MMDTI_K2_BWD_CRB")) p.crb = std::max(1, std::min(p.crb, atoi(e)));      // tuning knob
     const int nkb16 = (p.L + 15) / 16;
+    if constexpr (!F32 && NKB >= 25) {
+        // column-split phase 1 (see the kernel): 8 warps, 32-row chunks, two CTAs per SM
+        const char* cs_env = getenv("MMDTI_K2_BWD_CS");       // read per launch so that a test can compare both forms
+        const bool use_cs = cs_env ? atoi(cs_env) != 0 : K2_BWD_CS_DEFAULT;
+        if (use_cs && smem_of(2) <= 112 * 1024) {
+            p.crb = 2;
+            p.nchunks = (nkb16 + 1) / 2;
+            const size_t smem = smem_of(2);
+            auto kern = pair_attn_bwd_kernel<T, TP, TG, NKB, true>;
+            static int occ_cs = 0;
+            if (!occ_cs) {
+                MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MMDTI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cs, kern, 256, smem));
+                if (occ_cs < 1) occ_cs = 1;
+            }
+            const long long ntiles = (long long)p.B * p.H;
+            const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * occ_cs);
+            kern<<<grid, 256, smem, st>>>(p);
+            MMDTI_LAUNCH_OK();
+            return MMDTI_OK;
+        }
+    }
     p.nchunks = (nkb16 + p.crb - 1) / p.crb;
     // phase 1 uses one warp per 16-row block of the chunk; phase 2 spreads the 16-key blocks over all warps
     const int nwarps = std::max(p.crb, (nkb16 + G::MAXKB16 - 1) / G::MAXKB16);

@@ -204,3 +204,47 @@ def test_k2_with_keep_bits_is_bit_identical(L):
         res.append((o, pout, dpi[..., :L], dqkv))
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("pdt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("L,keep_bits", [(137, False), (150, False), (200, True), (258, False), (258, True), (264, False)])
+def test_bwd_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
+    """L > 136: the column-split backward (4 warps per 16-row block, row max / sum / dQ exchanged through shared memory,
+    MMDTI_K2_BWD_CS=1) against the one-warp-per-row-block form on the same inputs, dropout on.  Both draw the same mask;
+    the only differences are fp32 summation orders (row sums, dQ) ahead of the rounding to the storage types."""
+    from mmdti_b200 import _lib, ops
+    from mmdti_b200._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
+    B, H, D, p, seed = 2, 64, 512, 0.1, 4321
+    Lp = ops.pair_ld(L)
+    g = torch.Generator(device="cuda").manual_seed(L)
+    qkv = (torch.randn(B * L, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    pair = torch.randn(B, H, L, Lp, device="cuda", generator=g).to(pdt)
+    pair[..., L:] = float("-inf")
+    pair[1, :, :, L - 3:L] = float("-inf")                                  # masked keys
+    d_o = (torch.randn(B * L, D, device="cuda", generator=g) * 0.1).bfloat16()
+    dpo = (torch.randn(B, H, L, Lp, device="cuda", generator=g) * 0.01).to(pdt)
+    dpo[..., L:] = 0
+    dpo[1, :, :, L - 3:L] = 0
+    keep = None
+    if keep_bits:
+        keep = torch.empty(B * H * L, _lib.lib().mmdti_pair_keep_words(L), device="cuda", dtype=torch.int32)
+        call("mmdti_pair_attn_keep_bits", keep, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
+    code, pcode = DTYPE_CODE[torch.bfloat16], DTYPE_CODE[pdt]
+    pout, o = torch.empty_like(pair), torch.empty(B * L, D, device="cuda", dtype=torch.bfloat16)
+    call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H),
+         i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(pcode), keep, stream_ptr())
+    res = []
+    for cs in ("0", "1"):
+        monkeypatch.setenv("MMDTI_K2_BWD_CS", cs)
+        dpi, dqkv = torch.full_like(pair, 7.0), torch.full_like(qkv, 7.0)
+        for dpo_ in (dpo, None):                                            # with and without an incoming pair gradient
+            call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pout, o, d_o, i64(D), dpo_, dpi,
+                 dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L), f32(8 ** -0.5), f32(p),
+                 u64(seed), i32(code), i32(pcode), i32(pcode), keep, stream_ptr())
+            torch.cuda.synchronize()
+            res.append((dpi[..., :L].float().clone(), dqkv.float().clone()))
+    for (dp0, dq0), (dp1, dq1) in ((res[0], res[2]), (res[1], res[3])):
+        assert torch.isfinite(dp1).all() and torch.isfinite(dq1).all()
+        assert (dp0 - dp1).abs().max() <= 2 ** -7 * dp0.abs().max()
+        assert (dq0 - dq1).abs().max() <= 2 ** -6 * dq0.abs().max()
+        assert (dp0 - dp1).abs().mean() <= 1e-4 * dp0.abs().mean() and (dq0 - dq1).abs().mean() <= 2e-3 * dq0.abs().mean()
