@@ -25,7 +25,8 @@ namespace {
 
 constexpr int HD = MMDTI_HEAD_DIM;  // 8
 constexpr int NSTAGE = 2;      // backward ring
-constexpr bool K2_BWD_CS_DEFAULT = true;    // column-split backward for L > 136 (MMDTI_K2_BWD_CS=0/1 overrides)
+constexpr bool K2_BWD_CS_DEFAULT = true;   // column-split backward for L > 136 (MMDTI_K2_BWD_CS=0/1 overrides)
+constexpr bool K2_FWD_CS_DEFAULT = false;  // column-split forward for L > 136 (MMDTI_K2_FWD_CS=0/1 overrides)
 constexpr int NSTAGE_F = 3;    // forward ring: the bulk store of item w-1 may still be reading its stage while w+1 loads
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -124,8 +125,12 @@ template <int NKB> struct FwdLaunch {
     static constexpr int MINB = NKB >= 25 ? 1 : (640 / MAXT < 1 ? 1 : (640 / MAXT > 8 ? 8 : 640 / MAXT));
 };
 
-template <typename T, typename TP, int NKB>
-__global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pair_attn_fwd_kernel(const FwdParams p) {
+// CS (column split, bf16 activations, NKB >= 25): as in the backward, 4 warps share a 16-row block, each owning a quarter of the
+// key blocks (<= 9 instead of 33 score blocks in registers): 32-row chunks, 8 warps, two CTAs per SM.  The row max is exchanged
+// before the exponentials, the row sums and the partial A'V products after them.
+template <typename T, typename TP, int NKB, bool CS = false>
+__global__ void __launch_bounds__(CS ? 256 : FwdLaunch<NKB>::MAXT, CS ? 2 : FwdLaunch<NKB>::MINB)
+pair_attn_fwd_kernel(const FwdParams p) {
     using G = Geo<NKB>;
     constexpr bool F32 = std::is_same<T, float>::value;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -417,7 +422,156 @@ __global__ void __launch_bounds__(FwdLaunch<NKB>::MAXT, FwdLaunch<NKB>::MINB) pa
                 }
             }
         };
-        if (warp < p.crb && row0 + warp * 16 < L) {
+        if constexpr (CS) {
+            constexpr int NSPLIT = 4;
+            constexpr int KBW = (NKB + NSPLIT - 1) / NSPLIT;          // key blocks per warp
+            __shared__ float cs_max[2][NSPLIT][16];
+            __shared__ float cs_sum[2][NSPLIT][16];
+            __shared__ float cs_o[2][NSPLIT - 1][16][HD];
+            const int rb = warp >> 2, cs = warp & 3;                   // launched with 8 warps, crb = 2
+            if (rb < p.crb && row0 + rb * 16 < L) {
+                const int kb0 = cs * KBW;
+                const T* Ks = stage(s).K;
+                const T* Vs = stage(s).V;
+                const T* Qs = stage(s).Q;
+                const int la = rb * 16 + g, lb = la + 8;
+                const int ra = row0 + la, rbb = row0 + lb;
+                TP* srow_a = stage(s).slab + la * G::STRIDE;
+                TP* srow_b = stage(s).slab + lb * G::STRIDE;
+                const unsigned bar_id = 1u + (unsigned)rb;
+                float sc[KBW][4];
+
+                // ---- S = Q K^T over this warp's key blocks; S = scale*S + P; P' := S (stored); row max
+                const uint32_t* Q32 = reinterpret_cast<const uint32_t*>(Qs);
+                const uint32_t* K32 = reinterpret_cast<const uint32_t*>(Ks);
+                const uint32_t qa0 = Q32[la * 4 + q4], qa1 = Q32[lb * 4 + q4];
+                float ma = -INFINITY, mb = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < KBW; ++j) {
+                    const int kb = kb0 + j;
+                    if (kb < NKB) {
+                        const int col = kb * 8 + 2 * q4;
+                        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+                        mma_bf16_1688(sc[j], qa0, qa1, K32[(kb * 8 + g) * 4 + q4]);
+                        const float2 pa = slab_get2<TP>(srow_a, col), pb = slab_get2<TP>(srow_b, col);
+                        const float2 va = slab_put2<TP>(srow_a, col, fmaf(sc[j][0], p.scale, pa.x), fmaf(sc[j][1], p.scale, pa.y));
+                        const float2 vb = slab_put2<TP>(srow_b, col, fmaf(sc[j][2], p.scale, pb.x), fmaf(sc[j][3], p.scale, pb.y));
+                        sc[j][0] = va.x; sc[j][1] = va.y; sc[j][2] = vb.x; sc[j][3] = vb.y;
+                        ma = fmaxf(ma, fmaxf(va.x, va.y));
+                        mb = fmaxf(mb, fmaxf(vb.x, vb.y));
+                    } else {
+                        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = -INFINITY;
+                    }
+                }
+                ma = quad_max(ma);
+                mb = quad_max(mb);
+                if (q4 == 0) { cs_max[rb][cs][g] = ma; cs_max[rb][cs][g + 8] = mb; }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(128) : "memory");
+#pragma unroll
+                for (int c = 0; c < NSPLIT; ++c) {
+                    ma = fmaxf(ma, cs_max[rb][c][g]);
+                    mb = fmaxf(mb, cs_max[rb][c][g + 8]);
+                }
+
+                // ---- softmax numerators, partial row sums (before dropout, like the row-split form), dropout
+                float suma = 0.f, sumb = 0.f;
+                {
+                    const float ka = ma * LOG2E, kbm = mb * LOG2E;
+#pragma unroll
+                    for (int j = 0; j < KBW; ++j) {
+                        if (kb0 + j < NKB) {
+                            sc[j][0] = fast_ex2(fmaf(sc[j][0], LOG2E, -ka));
+                            sc[j][1] = fast_ex2(fmaf(sc[j][1], LOG2E, -ka));
+                            sc[j][2] = fast_ex2(fmaf(sc[j][2], LOG2E, -kbm));
+                            sc[j][3] = fast_ex2(fmaf(sc[j][3], LOG2E, -kbm));
+                            suma += sc[j][0] + sc[j][1];
+                            sumb += sc[j][2] + sc[j][3];
+                        } else {
+                            sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+                        }
+                    }
+                }
+                if (do_drop) {
+                    constexpr int NW = (NKB * 8 + 31) / 32;
+                    const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
+                    const uint32_t thi = p.thresh16 << 16;
+                    const uint32_t* ka_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW : nullptr;
+                    const uint32_t* kb_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW : nullptr;
+                    uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
+#pragma unroll
+                    for (int j = 0; j < KBW; ++j) {
+                        const int kb = kb0 + j;
+                        if (kb < NKB) {
+                            if (ka_) {
+                                const int sh = 8 * (kb & 3) + 2 * q4;
+                                const uint32_t wa_ = ka_[kb >> 2] >> sh, wb_ = kb_[kb >> 2] >> sh;
+                                if (!(wa_ & 1u)) sc[j][0] = 0.f;
+                                if (!(wa_ & 2u)) sc[j][1] = 0.f;
+                                if (!(wb_ & 1u)) sc[j][2] = 0.f;
+                                if (!(wb_ & 2u)) sc[j][3] = 0.f;
+                            } else {
+                                // one hash serves the key-block pair (2m, 2m+1): .x even block, .y odd block
+                                const int col = kb * 8 + 2 * q4;
+                                if (j == 0 || (kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
+                                const uint32_t ba = (kb & 1) ? qwa.y : qwa.x, bb = (kb & 1) ? qwb.y : qwb.x;
+                                if ((ba << 16) < thi) sc[j][0] = 0.f;
+                                if (ba < thi) sc[j][1] = 0.f;
+                                if ((bb << 16) < thi) sc[j][2] = 0.f;
+                                if (bb < thi) sc[j][3] = 0.f;
+                            }
+                        }
+                    }
+                }
+                suma = quad_sum(suma);
+                sumb = quad_sum(sumb);
+
+                // ---- partial O = A' V over this warp's key blocks (pairs of 8-key blocks from kb0), summed by warp 0
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int jp = 0; jp < (KBW + 1) / 2; ++jp) {
+                    const int kbA = kb0 + 2 * jp;
+                    if (kbA < NKB) {
+                        uint32_t b0, b1;
+                        ldmatrix_x2_trans(b0, b1, Vs + (kbA * 8 + (lane & 15)) * HD);
+                        const uint32_t a0 = pack_bf16(sc[2 * jp][0], sc[2 * jp][1]);
+                        const uint32_t a1 = pack_bf16(sc[2 * jp][2], sc[2 * jp][3]);
+                        uint32_t a2 = 0u, a3 = 0u;
+                        if (2 * jp + 1 < KBW) {
+                            a2 = pack_bf16(sc[2 * jp + 1][0], sc[2 * jp + 1][1]);      // zeros beyond NKB
+                            a3 = pack_bf16(sc[2 * jp + 1][2], sc[2 * jp + 1][3]);
+                        }
+                        mma_bf16_16816(o, a0, a1, a2, a3, b0, b1);
+                    }
+                }
+                if (q4 == 0) { cs_sum[rb][cs][g] = suma; cs_sum[rb][cs][g + 8] = sumb; }
+                if (cs > 0) {
+                    *reinterpret_cast<float2*>(&cs_o[rb][cs - 1][g][2 * q4]) = make_float2(o[0], o[1]);
+                    *reinterpret_cast<float2*>(&cs_o[rb][cs - 1][g + 8][2 * q4]) = make_float2(o[2], o[3]);
+                }
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(128) : "memory");
+                if (cs == 0) {
+                    suma = 0.f;
+                    sumb = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NSPLIT; ++c) {
+                        suma += cs_sum[rb][c][g];
+                        sumb += cs_sum[rb][c][g + 8];
+                    }
+#pragma unroll
+                    for (int c = 0; c < NSPLIT - 1; ++c) {
+                        const float2 x = *reinterpret_cast<const float2*>(&cs_o[rb][c][g][2 * q4]);
+                        const float2 y = *reinterpret_cast<const float2*>(&cs_o[rb][c][g + 8][2 * q4]);
+                        o[0] += x.x; o[1] += x.y; o[2] += y.x; o[3] += y.y;
+                    }
+                    const float inva = p.keep_scale * fast_rcp(suma), invb = p.keep_scale * fast_rcp(sumb);
+                    T* og = static_cast<T*>(p.o) + (size_t)b * L * p.ldo + h * HD;
+                    if (ra < L)
+                        *reinterpret_cast<uint32_t*>(og + (size_t)ra * p.ldo + 2 * q4) = pack_bf16(o[0] * inva, o[1] * inva);
+                    if (rbb < L)
+                        *reinterpret_cast<uint32_t*>(og + (size_t)rbb * p.ldo + 2 * q4) = pack_bf16(o[2] * invb, o[3] * invb);
+                }
+            }
+        } else if (warp < p.crb && row0 + warp * 16 < L) {
             if (row0 + warp * 16 + 8 < L) row_block(std::true_type{});
             else row_block(std::false_type{});
         }
@@ -1179,6 +1333,28 @@ int launch_fwd(FwdParams p, cudaStream_t st) {
     auto smem_of = [](int crb) { return NSTAGE_F * ((FwdStage<T, TP, NKB>::bytes(crb * 16) + 127) & ~size_t(127)); };
     while (p.crb > 1 && smem_of(p.crb) > SMEM_CAP) --p.crb;
     p.nchunks = ((p.L + 15) / 16 + p.crb - 1) / p.crb;
+    if constexpr (!std::is_same<T, float>::value && NKB >= 25) {
+        // column-split form (see the kernel): 8 warps, 32-row chunks, two CTAs per SM
+        const char* cs_env = getenv("MMDTI_K2_FWD_CS");       // read per launch so that a test can compare both forms
+        const bool use_cs = cs_env ? atoi(cs_env) != 0 : K2_FWD_CS_DEFAULT;
+        if (use_cs && smem_of(2) <= 112 * 1024) {
+            p.crb = 2;
+            p.nchunks = ((p.L + 15) / 16 + 1) / 2;
+            const size_t smem = smem_of(2);
+            auto kern = pair_attn_fwd_kernel<T, TP, NKB, true>;
+            static int occ_cs = 0;
+            if (!occ_cs) {
+                MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                MMDTI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cs, kern, 256, smem));
+                if (occ_cs < 1) occ_cs = 1;
+            }
+            const long long ntiles = (long long)p.B * p.H;
+            const int grid = (int)std::min<long long>(ntiles, (long long)num_sms() * occ_cs);
+            kern<<<grid, 256, smem, st>>>(p);
+            MMDTI_LAUNCH_OK();
+            return MMDTI_OK;
+        }
+    }
     const size_t smem = smem_of(p.crb);
     MMDTI_REQUIRE(smem <= SMEM_CAP, "pair_attn_fwd: shared memory %zu exceeds cap (L=%d)", smem, p.L);
     auto kern = pair_attn_fwd_kernel<T, TP, NKB>;

@@ -208,8 +208,8 @@ def test_k2_with_keep_bits_is_bit_identical(L):
 
 @pytest.mark.parametrize("pdt", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("L,keep_bits", [(137, False), (150, False), (200, True), (258, False), (258, True), (264, False)])
-def test_bwd_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
-    """L > 136: the column-split backward (4 warps per 16-row block, row max / sum / dQ exchanged through shared memory,
+def test_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
+    """L > 136: the column-split forward (MMDTI_K2_FWD_CS=1) and backward (4 warps per 16-row block, row max / sum / dQ exchanged through shared memory,
     MMDTI_K2_BWD_CS=1) against the one-warp-per-row-block form on the same inputs, dropout on.  Both draw the same mask;
     the only differences are fp32 summation orders (row sums, dQ) ahead of the rounding to the storage types."""
     from mmdti_b200 import _lib, ops
@@ -230,9 +230,18 @@ def test_bwd_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
         keep = torch.empty(B * H * L, _lib.lib().mmdti_pair_keep_words(L), device="cuda", dtype=torch.int32)
         call("mmdti_pair_attn_keep_bits", keep, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
     code, pcode = DTYPE_CODE[torch.bfloat16], DTYPE_CODE[pdt]
-    pout, o = torch.empty_like(pair), torch.empty(B * L, D, device="cuda", dtype=torch.bfloat16)
-    call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H),
-         i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(pcode), keep, stream_ptr())
+    fw = []
+    for cs in ("1", "0"):                 # the forward has the same two forms (MMDTI_K2_FWD_CS); the row-split outputs feed the backward
+        monkeypatch.setenv("MMDTI_K2_FWD_CS", cs)
+        pout, o = torch.full_like(pair, 7.0), torch.full((B * L, D), 7.0, device="cuda", dtype=torch.bfloat16)
+        call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H),
+             i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(pcode), keep, stream_ptr())
+        torch.cuda.synchronize()
+        fw.append((pout, o))
+    assert torch.equal(fw[0][0][..., :L], fw[1][0][..., :L])              # P' = scale * QK^T + P: same operations, same bits
+    o1, o0 = fw[0][1].float(), fw[1][1].float()
+    assert torch.isfinite(o1).all()
+    assert (o1 - o0).abs().max() <= 2 ** -6 * o0.abs().max() and (o1 - o0).abs().mean() <= 2e-3 * o0.abs().mean()
     res = []
     for cs in ("0", "1"):
         monkeypatch.setenv("MMDTI_K2_BWD_CS", cs)
