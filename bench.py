@@ -3,16 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): the Uni-Mol conformer encoder alone — 15 layers, 64 heads,
-512-d, per-GPU batch 128 molecules x 64 atoms (L = 66 tokens), bf16, forward + backward of
-sum(all_repr * g) in training mode (dropout 0.1 as configured) + Adam step, synthetic molecules,
-random-init weights.  At N = 1 the step is captured once in a CUDA graph and replayed.  Metric: train molecules/s, whole job (weak scaling: 128 molecules per GPU).
+Default workload `hotpath` = BASELINE.json's metric "train molecules/sec (fwd+bwd+contrastive)" on the configs[1]
+geometry: the Uni-Mol conformer encoder (15 layers, 64 heads, 512-d, per-GPU batch 128 molecules x 64 atoms, L = 66
+tokens, bf16, dropout 0.1) chained the way MM_Model.forward chains the WHOLE hot path of SURVEY.md §8(a)
+(models/mm_model.py:545-591): encoder -> InfoNCE against the second modality (a resident random (B, 64, 512) tensor
+standing in for the out-of-scope ChemBERTa output) -> masked mean pooling -> FDS.smooth (epoch 1, populated statistics)
+-> regression head -> ConR, loss = MSE + 0.1 InfoNCE + 0.1 ConR (tasks/trainer.py:68-69,193), backward, Adam step;
+synthetic molecules, random-init weights.  The step is captured once in a CUDA graph and replayed; at N > 1 the
+contrastive operands are all-gathered (global-batch negatives, exchange 1) and the gradients all-reduced (exchange 2)
+inside the graph.  Metric: train molecules/s, whole job (weak scaling: 128 molecules per GPU).
 
---workload hotpath runs the WHOLE hot path of SURVEY.md §8(a) in the step, chained the way MM_Model.forward chains it
-(models/mm_model.py:545-591): the same encoder -> InfoNCE against the second modality (a resident random (B, 64, 512)
-tensor standing in for the out-of-scope ChemBERTa output) -> masked mean pooling -> FDS.smooth (epoch 1, populated
-statistics) -> regression head -> ConR, loss = MSE + 0.1 InfoNCE + 0.1 ConR (tasks/trainer.py:68-69,193), backward, Adam.
-At N > 1 the contrastive operands are all-gathered (global-batch negatives) inside the step.
+--workload encoder   configs[1] literally: the encoder alone, loss = sum(all_repr * g)
+--workload config3   configs[2]: classification, InfoNCE + SupCon (CT_Single), GLOBAL batch 4096 split 4096/W over the
+                     W GPUs (strong scaling), all-gathered negatives
+--workload config4   configs[3]: 256 atoms (L = 258), SMILES 256, ConR + FDS, 32 molecules per GPU
+--workload config5   configs[4]: contrastive-loss microbench, N = 1K..64K x 512-d vs the tensor roofline (its own metric)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -34,18 +39,26 @@ B_PER_GPU, N_ATOMS, LAYERS, HEADS, DIM = 128, 64, 15, 64, 512
 L = N_ATOMS + 2
 METRIC, UNIT = "train_molecules_per_sec", "molecules/s"
 S_SMILES, FDS_BUCKETS = 64, 30
-WORKLOADS = {"encoder": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms",
-             "hotpath": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd"}
+_NAMES = {"encoder": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms",
+          "hotpath": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd",
+          "config3": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+supcon_classification_fwd_bwd_global_batch_4096",
+          "config4": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd",
+          "config5": "contrastive_similarity_sweep_infonce_supcon_conr_N1K-64K_x512d"}
+WORKLOADS = dict(_NAMES)
+# per-workload defaults: (molecules per GPU | None = global batch / world, atoms, SMILES length, task, scaling)
+SPECS = {"encoder": (128, 64, 64, None, "weak"), "hotpath": (128, 64, 64, "regression", "weak"),
+         "config3": (None, 64, 64, "classification", "strong"), "config4": (32, 256, 256, "regression", "weak"),
+         "config5": (128, 64, 64, None, "weak")}
+GLOBAL_BATCH_CONFIG3 = 4096
 
 
 def set_shape(batch, n_atoms, smiles_len):
-    """Default = BASELINE configs[1] (128 x 64 atoms).  --batch 32 --n-atoms 256 --smiles-len 256 with --workload hotpath is
-    the per-GPU shape of configs[3] (large-molecule stress: L = 258, ConR + FDS)."""
+    """Shape of the per-GPU batch (defaults per workload in SPECS; BASELINE configs[1] = 128 x 64 atoms)."""
     global B_PER_GPU, N_ATOMS, L, S_SMILES
     B_PER_GPU, N_ATOMS, S_SMILES = batch, n_atoms, smiles_len
     L = N_ATOMS + 2
     for k in WORKLOADS:
-        WORKLOADS[k] = WORKLOADS[k].replace("b128x64atoms", "b%dx%datoms" % (batch, n_atoms))
+        WORKLOADS[k] = _NAMES[k].replace("b128x64atoms", "b%dx%datoms" % (batch, n_atoms))
 
 
 def peaks():
@@ -105,13 +118,16 @@ def make_batch(seed):
     return tokens, dist, et, g, coord
 
 
-def make_head_batch(seed, n=None):
-    """Inputs of the contrastive head: second-modality activations (B, S, 512), standard-scaled regression targets,
-    sample weights (mean 1), and FDS statistics of a previous epoch."""
+def make_head_batch(seed, n=None, task="regression"):
+    """Inputs of the contrastive head: second-modality activations (B, S, 512), targets (standard-scaled regression
+    targets, or Bernoulli(0.3) class labels for the classification task), sample weights (mean 1), and FDS statistics of
+    a previous epoch."""
     n = B_PER_GPU if n is None else n
     gen = torch.Generator().manual_seed(seed + 11)
     smiles = torch.randn(n, S_SMILES, DIM, generator=gen) * 0.5
     y = torch.randn(n, 1, generator=gen)
+    if task == "classification":
+        y = (torch.rand(n, 1, generator=gen) < 0.3).float()
     w = torch.rand(n, generator=gen) + 0.5
     w = w / w.mean()
     sg = torch.Generator().manual_seed(99)                      # the same statistics on every rank
@@ -125,73 +141,138 @@ def make_head_batch(seed, n=None):
 FDS_CFG = dict(min_value=-3.0, bin_width=0.2, bucket_num=FDS_BUCKETS, bucket_start=0, start_smooth=1)
 
 
-# ------------------------------------------------------------------ CPU arm (oracle port of the reference)
-def cpu_reference_run(steps, warmup, sample_b=32, workload="encoder"):
-    """The reference's CPU implementation of the same path (oracle/restate.py: its own
-    models/mm_model.py + models/transformers.py restated, Uni-Core layer restated), fp32, all host
-    threads, on a bounded sample of the workload: `sample_b` molecules of the 128-molecule batch
-    per step, same L / depth / width.  Returns (molecules/s, seconds per step, cores)."""
+# ------------------------------------------------------------------ CPU arm
+def _reference_modules():
+    """The reference's OWN modules (models/mm_model.py, models/transformers.py, models/infonce.py, models/contrastive.py)
+    when a copy of the reference tree travelled to this machine (baseline/_ref, made by scripts/install_reference.sh;
+    git-ignored) or /root/reference exists; None otherwise (then the arm runs oracle/restate.py, kind "port")."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.load() if ref_loader.available() else None
+    except Exception as exc:                                     # a broken copy must not take the bench down
+        print("[bench] reference tree not usable (%s); using the oracle port" % exc, file=sys.stderr)
+        return None
+
+
+def cpu_reference_run(steps, warmup, sample_b=32, workload="hotpath"):
+    """The reference's CPU implementation of the same path, fp32, all host threads, on a bounded sample of the workload:
+    `sample_b` molecules per step, same L / depth / width / loss chain.  kind "reference": the reference's own classes
+    (GaussianLayer, NonLinearHead, TransformerEncoderWithPair, InfoNCE, CT_Regress / CT_Single) chained as
+    models/mm_model.py:545-591 chains them, Uni-Core layer from oracle/shims; kind "port": oracle/restate.py.
+    FDS.smooth always comes from the port (the reference's FDS is CUDA-only, models/fds.py:84).
+    Returns (molecules/s, seconds per step, cores, kind)."""
+    import torch.nn.functional as F
     from oracle import restate
     from oracle.detw import det_state_dict
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from tests_util import slice_shapes
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    p = {k: v.requires_grad_(True) for k, v in det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5).items()}
+    task = SPECS[workload][3]
+    sd = det_state_dict(slice_shapes(HEADS, DIM, 2048, LAYERS), seed=5)
     tokens, dist, et, g, _ = make_batch(1234)
     sample_b = min(sample_b, B_PER_GPU)
     tokens, dist, et, g = tokens[:sample_b], dist[:sample_b], et[:sample_b], g[:sample_b]
-    hot = workload == "hotpath"
-    if hot:
-        import torch.nn.functional as F
-        smiles, y, w, stats = (x[:sample_b] if torch.is_tensor(x) else x for x in make_head_batch(1234))
-        torch.manual_seed(5)
-        mods = torch.nn.ModuleDict({"infonce": torch.nn.ModuleDict({
-            "info_proj_query": torch.nn.Sequential(torch.nn.Linear(DIM, DIM), torch.nn.GELU(), torch.nn.Linear(DIM, 50)),
-            "info_proj_positive": torch.nn.Sequential(torch.nn.Linear(DIM, DIM), torch.nn.GELU(), torch.nn.Linear(DIM, 50))}),
-            "head": torch.nn.Linear(DIM, 1)})
-        pi = {k: v for k, v in mods.named_parameters() if k.startswith("infonce.")}
-        hw, hb = mods["head"].weight, mods["head"].bias
+    ref = _reference_modules()
+    kind = "reference" if ref is not None else "port"
+    torch.manual_seed(5)
+    if ref is not None:
+        mm, tr = ref["mm_model"], ref["transformers"]
+        enc_mods = torch.nn.ModuleDict({
+            "embed_tokens": torch.nn.Embedding(31, DIM, 0), "gbf": mm.GaussianLayer(128, 961),
+            "gbf_proj": mm.NonLinearHead(128, HEADS, "gelu"),
+            "encoder": tr.TransformerEncoderWithPair(encoder_layers=LAYERS, embed_dim=DIM, ffn_embed_dim=2048, attention_heads=HEADS,
+                                                     emb_dropout=0.1, dropout=0.1, attention_dropout=0.1, activation_dropout=0.0,
+                                                     max_seq_len=512, activation_fn="gelu", no_final_head_layer_norm=True)})
+        enc_mods.load_state_dict(sd)
+        enc_mods.train()
+        enc_params = list(enc_mods.parameters())
+
+        def encode():
+            pm = tokens.eq(0)
+            x = enc_mods["embed_tokens"](tokens)
+            bias = enc_mods["gbf_proj"](enc_mods["gbf"](dist, et)).permute(0, 3, 1, 2).contiguous()
+            bias = bias.view(-1, bias.size(-2), bias.size(-1))
+            return enc_mods["encoder"](x, padding_mask=pm if pm.any() else None, attn_mask=bias)[0]
+    else:
+        p = {k: v.requires_grad_(True) for k, v in sd.items()}
+        enc_params = list(p.values())
+
+        def encode():
+            return restate.unimol_encoder(tokens, dist, et, p, heads=HEADS, n_layers=LAYERS)
+
+    head_params = []
+    if task is not None:
+        smiles, y, w, stats = (x[:sample_b] if torch.is_tensor(x) else x for x in make_head_batch(1234, task=task))
+        head = torch.nn.Linear(DIM, 1)
+        if ref is not None:
+            inf = ref["infonce"].InfoNCE(DIM, DIM)
+            ct = ref["contrastive"]
+        else:
+            inf = torch.nn.ModuleDict({
+                "info_proj_query": torch.nn.Sequential(torch.nn.Linear(DIM, DIM), torch.nn.GELU(), torch.nn.Linear(DIM, 50)),
+                "info_proj_positive": torch.nn.Sequential(torch.nn.Linear(DIM, DIM), torch.nn.GELU(), torch.nn.Linear(DIM, 50))})
+            pi = {"infonce." + k: v for k, v in inf.named_parameters()}
+        head_params = list(inf.parameters()) + list(head.parameters())
         mask = tokens.ne(0).float().unsqueeze(-1)
-    opt = torch.optim.Adam(list(p.values()) + (list(mods.parameters()) if hot else []), lr=1e-4, eps=1e-6)   # tasks/trainer.py:160
+    opt = torch.optim.Adam(enc_params + head_params, lr=1e-4, eps=1e-6)   # tasks/trainer.py:160
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        rep = restate.unimol_encoder(tokens, dist, et, p, heads=HEADS, n_layers=LAYERS)
-        if hot:
-            l_inf = restate.infonce_head(rep, smiles, pi)
-            pooled = (rep * mask).sum(1) / mask.sum(1)
-            feats = restate.fds_smooth(pooled * 1.0, y, 1, stats, FDS_CFG)
-            logits = F.linear(feats, hw, hb)
-            l_ct = restate.ct_regress(feats, y, logits, weights=w, w=0.2)
-            (F.mse_loss(logits, y) + 0.1 * l_inf + 0.1 * l_ct).backward()
-        else:
+        rep = encode()
+        if task is None:
             (rep * g).sum().backward()
+        else:
+            l_inf = inf(rep, smiles) if ref is not None else restate.infonce_head(rep, smiles, pi)
+            pooled = (rep * mask).sum(1) / mask.sum(1)
+            if task == "regression":
+                feats = restate.fds_smooth(pooled * 1.0, y, 1, stats, FDS_CFG)
+                logits = head(feats)
+                l_ct = (ct.CT_Regress(feats, y, logits, weights=w, w=0.2) if ref is not None
+                        else restate.ct_regress(feats, y, logits, weights=w, w=0.2))
+                l_task = F.mse_loss(logits, y)
+            else:
+                logits = head(pooled)
+                l_ct = ct.CT_Single(pooled, y, logits) if ref is not None else restate.ct_single(pooled, y)
+                l_task = F.binary_cross_entropy_with_logits(logits, y)
+            (l_task + 0.1 * l_inf + 0.1 * l_ct).backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    return sample_b / sec, sec, cores
+    return sample_b / sec, sec, cores, kind
 
 
-def run_reference(args, rank):
+def base_config(workload, world):
+    """The `config` object both arms print (the reference arm adds its sample size)."""
+    return {"workload": WORKLOADS[workload], "per_gpu_batch": B_PER_GPU, "global_batch": B_PER_GPU * world,
+            "n_atoms": N_ATOMS, "seq_len": L, "smiles_len": S_SMILES, "layers": LAYERS}
+
+
+def cpu_sample_text(kind, sample_b, sec):
+    what = ("the reference's own modules (copy of the reference tree in baseline/_ref, Uni-Core layer from oracle/shims)"
+            if kind == "reference" else "oracle/restate.py (no reference tree on this machine)")
+    return ("%d of the %d molecules per step (same L=%d, %d layers, same loss chain, fp32, dropout as the reference "
+            "configures it), %.1f s/step, %s" % (min(sample_b, B_PER_GPU), B_PER_GPU, L, LAYERS, sec, what))
+
+
+def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.workload == "config5":
+        return run_config5_reference(args)
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
-    sample_b = args.cpu_sample
-    val, sec, cores = cpu_reference_run(steps, warm, sample_b, args.workload)
-    sample_b = min(sample_b, B_PER_GPU)
+    val, sec, cores, kind = cpu_reference_run(steps, warm, args.cpu_sample, args.workload)
+    cfg = base_config(args.workload, world)
+    cfg["cpu_sample_molecules_per_step"] = min(args.cpu_sample, B_PER_GPU)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "per_gpu_batch": B_PER_GPU,
-                   "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of the %d molecules per step (same L=%d, 15 layers, fp32), oracle/restate.py "
-                                   "(the reference tree is not present on the GPU box)" % (sample_b, B_PER_GPU, L)},
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": SPECS[args.workload][4], "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": cpu_sample_text(kind, args.cpu_sample, sec)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -199,6 +280,7 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------ GPU arm
 def run_ours(args, rank, local_rank, world):
+    task, scaling = SPECS[args.workload][3], SPECS[args.workload][4]
     import mmdti_b200
     from mmdti_b200 import _lib, ops
     from mmdti_b200.models.encoder import UnimolEncoder
@@ -217,6 +299,7 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
 
     mmdti_b200.set_precision(act="bf16", pair=os.environ.get("MMDTI_PAIR", "bf16"))
+    ops.set_seed_rank(rank)           # data-parallel ranks draw different dropout masks (same weights: seed 0 below)
     torch.manual_seed(0)
     model = UnimolEncoder().to(dev).train()
     step_model = model
@@ -234,22 +317,22 @@ def run_ours(args, rank, local_rank, world):
         # the bucket holding the first layers is reduced under K1's backward; flat buckets feed FusedAdam directly
         late = [model.embed_tokens.weight] + list(model.gbf.parameters()) + list(model.gbf_proj.parameters()) \
             + list(model.encoder.emb_layer_norm.parameters())
-        if args.workload != "hotpath":
+        if task is None:
             reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam,
                                             bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
 
-    hot = args.workload == "hotpath"
+    hot = task is not None
     extra_params = []
     if hot:
         import numpy as np
         import torch.nn.functional as F
-        from mmdti_b200.models.contrastive import CT_Regress
+        from mmdti_b200.models.contrastive import CT_Regress, CT_Single
         from mmdti_b200.models.fds import FDS
         from mmdti_b200.models.infonce import InfoNCE
         torch.manual_seed(5)
         inf = InfoNCE(DIM, DIM).to(dev).train()
         head = torch.nn.Linear(DIM, 1).to(dev)
-        smiles, y_h, w_h, stats = make_head_batch(1234 + rank)
+        smiles, y_h, w_h, stats = make_head_batch(1234 + rank, task=task)
         fds = FDS(feature_dim=DIM, raw_data=np.array([0.0, 1.0]), col_data=None, using_scale=False, bucket_num=FDS_BUCKETS).to(dev)
         fds.min_value, fds.bin_width = FDS_CFG["min_value"], FDS_CFG["bin_width"]
         for k, v in stats.items():
@@ -306,10 +389,15 @@ def run_ours(args, rank, local_rank, world):
             l_inf = inf(rep, d_smiles)                                     # a7: InfoNCE against the second modality
             mk = inp[0].ne(0).unsqueeze(-1).float()
             pooled = (rep * mk).sum(1) / mk.sum(1)                          # masked mean pooling (mm_model.py:571-576)
-            feats = fds.smooth(pooled * 1.0, y_d, 1)                        # a11: in place on the pooled features
-            logits = head(feats)
-            l_ct = CT_Regress(feats, y_d, logits, weights=w_d, w=0.2, dp=dp_ctx)     # a8: ConR sees the smoothed features
-            loss = F.mse_loss(logits, y_d) + 0.1 * l_inf + 0.1 * l_ct       # tasks/trainer.py:68-69,193
+            if task == "regression":
+                feats = fds.smooth(pooled * 1.0, y_d, 1)                    # a11: in place on the pooled features
+                logits = head(feats)
+                l_ct = CT_Regress(feats, y_d, logits, weights=w_d, w=0.2, dp=dp_ctx)     # a8: ConR sees the smoothed features
+                loss = F.mse_loss(logits, y_d) + 0.1 * l_inf + 0.1 * l_ct   # tasks/trainer.py:68-69,193
+            else:                                                           # classification: no FDS (mm_model.py:580)
+                logits = head(pooled)
+                l_ct = CT_Single(pooled, y_d, logits, dp=dp_ctx)            # a9: SupCon over the global batch
+                loss = F.binary_cross_entropy_with_logits(logits, y_d) + 0.1 * l_inf + 0.1 * l_ct
         else:
             loss = (rep * d_g).sum()
         loss.backward()
@@ -326,7 +414,7 @@ def run_ours(args, rank, local_rank, world):
     if use_graph:
         from mmdti_b200.graph import GraphedStep
         opt.zero_grad(set_to_none=True)
-        graphed = GraphedStep(full_step, dev_inputs, device=dev,
+        graphed = GraphedStep(full_step, dev_inputs, device=dev, params=list(model.parameters()) + extra_params,
                               capture_error_mode="thread_local" if dist_on else "global")
 
         def step_resident():
@@ -428,9 +516,8 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": mols / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "per_gpu_batch": B_PER_GPU,
-                       "global_batch": B_PER_GPU * world, "n_atoms": N_ATOMS, "seq_len": L, "layers": LAYERS,
+            "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {**base_config(args.workload, world),
                        "pair_dtype": os.environ.get("MMDTI_PAIR", "bf16"), "dropout": 0.1,
                        "optimizer": "Adam(eps=1e-6), " + ("torch fused" if args.torch_adam else "mmdti FusedAdam (one launch, writes bf16 weight shadows)"),
                        "cuda_graph": bool(use_graph),
@@ -451,23 +538,154 @@ def run_ours(args, rank, local_rank, world):
             "kernel_breakdown": breakdown,
         }
         if world == 1 and not args.no_cpu_baseline:
-            val, sec, cores = cpu_reference_run(steps=3, warmup=1, sample_b=args.cpu_sample, workload=args.workload)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d of the %d molecules per step, 3 timed steps (%.1f s/step), fp32, "
-                                              "oracle/restate.py on the host cores" % (min(args.cpu_sample, B_PER_GPU), B_PER_GPU, sec)}
+            val, sec, cores, kind = cpu_reference_run(steps=3, warmup=1, sample_b=args.cpu_sample, workload=args.workload)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": cpu_sample_text(kind, args.cpu_sample, sec) + ", 3 timed steps"}
         print(json.dumps(line), file=json_out, flush=True)
     if dist_on:
-        # tear down in a fixed order: drain the device, drop the captured graph (it holds NCCL kernels), then leave
+        # Tear down in a fixed order: drain the device, make sure every rank is done, destroy the captured graph (it
+        # holds NCCL kernels and keeps the communicator's resources referenced), remove the gradient hooks, and only
+        # then destroy the process group.  A watchdog bounds the teardown: if the communicator destruction does not
+        # return within 30 s the process reports it on stderr and leaves with the result already printed.
         torch.cuda.synchronize()
-        print("[bench rank %d] finished, entering final barrier" % rank, file=sys.stderr, flush=True)
         dist.barrier()
         torch.cuda.synchronize()
         if use_graph:
+            graphed.graph.reset()
             del graphed
-        print("[bench rank %d] barrier passed" % rank, file=sys.stderr, flush=True)
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)        # skip the NCCL communicator teardown (observed to hang after graph-captured collectives)
+            reducer.remove()
+        torch.cuda.synchronize()
+
+        def _stuck():
+            print("[bench rank %d] destroy_process_group did not return within 30 s; exiting" % rank, file=sys.stderr, flush=True)
+            os._exit(0)
+
+        wd = threading.Timer(30.0, _stuck)
+        wd.daemon = True
+        wd.start()
+        dist.destroy_process_group()
+        wd.cancel()
+
+
+# ------------------------------------------------------------------ config 5: contrastive-loss microbench
+def _config5_cases(N, D, dev, gen):
+    f = torch.randn(N, D, device=dev, generator=gen)
+    f2 = torch.randn(N, D, device=dev, generator=gen)
+    y = torch.randn(N, 1, device=dev, generator=gen)
+    yhat = y + 0.3 * torch.randn(N, 1, device=dev, generator=gen)
+    cls = torch.randint(0, 10, (N, 1), device=dev, generator=gen)
+    return f, f2, y, yhat, cls
+
+
+def run_config5(args):
+    """BASELINE configs[4]: InfoNCE / SupCon / ConR on N x 512-d embeddings, N = 1K..64K, forward and forward + backward,
+    against the measured dense bf16 peak.  One JSON line; `value` = InfoNCE forward + backward TFLOP/s at the largest N
+    (flops = 12 N^2 D: two directions x (similarity + recompute + two gradient GEMMs))."""
+    import mmdti_b200
+    from mmdti_b200 import _lib
+    from mmdti_b200.models import contrastive as ctm
+    from mmdti_b200.models import infonce as infm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    mmdti_b200.set_precision(act="bf16")
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak, peak_src = float(json.load(fh)["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst: each case is timed alone)"
+    except Exception:
+        peak, peak_src = 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+    D = 512
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def timeit(fn, iters):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b) * 1e-3
+        return tot / iters
+
+    sampler = ClockSampler(0)
+    sampler.start()
+    rows, N = [], 1024
+    n0 = _lib.launch_count
+    while N <= args.nmax:
+        gen = torch.Generator(device=dev).manual_seed(N)
+        f, f2, y, yhat, cls = _config5_cases(N, D, dev, gen)
+        iters = max(2, min(args.steps, int(4e12 / (N * N * D)) + 2))
+        cases = {"infonce": (lambda a: infm.info_nce(a, f2), 4, 8),          # two directions
+                 "supcon": (lambda a: ctm.CT_Single(a, cls, None), 2, 4),
+                 "conr": (lambda a: ctm.CT_Regress(a, y, yhat), 2, 4)}
+        for name, (fn, ffl, bfl) in cases.items():
+            a = f.clone().requires_grad_(True)
+
+            def fwd():
+                with torch.no_grad():
+                    fn(a)
+
+            def fwdbwd():
+                a.grad = None
+                fn(a).backward()
+
+            tf, tb = timeit(fwd, iters), timeit(fwdbwd, iters)
+            flf, flb = ffl * N * N * D, (ffl + bfl) * N * N * D
+            rows.append({"loss": name, "N": N, "D": D, "fwd_ms": tf * 1e3, "fwd_tflops": flf / tf / 1e12, "fwd_frac": flf / tf / 1e12 / peak,
+                         "fwdbwd_ms": tb * 1e3, "fwdbwd_tflops": flb / tb / 1e12, "fwdbwd_frac": flb / tb / 1e12 / peak})
+            print("[config5] %-8s N=%6d fwd %8.3f ms %7.1f TF/s (%.2f)  fwd+bwd %8.3f ms %7.1f TF/s (%.2f)"
+                  % (name, N, tf * 1e3, flf / tf / 1e12, flf / tf / 1e12 / peak, tb * 1e3, flb / tb / 1e12, flb / tb / 1e12 / peak),
+                  file=sys.stderr, flush=True)
+        N *= 2
+    clocks = sampler.stop()
+    top = [r for r in rows if r["loss"] == "infonce"][-1]
+    line = {"metric": "contrastive_loss_fwd_bwd_tflops", "value": top["fwdbwd_tflops"], "unit": "TFLOP/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": top["fwdbwd_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOADS["config5"], "N_headline": top["N"], "D": D, "loss_headline": "infonce",
+                       "l2": "flushed (256 MB write) before every timed call"},
+            "roofline": {"kernel": "sim_tc_kernel (tcgen05 similarity engine, phase 1 + backward)", "bound": "tensor",
+                         "achieved": top["fwdbwd_tflops"], "peak": peak, "unit": "TFLOP/s", "frac": top["fwdbwd_frac"],
+                         "traffic": None, "peak_source": peak_src},
+            "gpu_launches": _lib.launch_count - n0, "clocks": clocks, "sweep": rows}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = _config5_cpu()
+    print(json.dumps(line), flush=True)
+
+
+def _config5_cpu(n=2048, d=512):
+    """CPU arm of config 5: the reference's InfoNCE arithmetic (models/infonce.py:70-98 restated in oracle/restate.py, or
+    the reference's own function when its tree is present) forward + backward on N = 2048 x 512-d, all host threads."""
+    from oracle import restate
+    ref = _reference_modules()
+    fn = ref["infonce"].info_nce if ref is not None else (lambda q, k: restate.info_nce(q, k, 0.1))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1)
+    q = torch.randn(n, d, generator=g).requires_grad_(True)
+    k = torch.randn(n, d, generator=g).requires_grad_(True)
+    ts = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        fn(q, k).backward()
+        ts.append(time.perf_counter() - t0)
+    sec = min(ts[1:])
+    return {"value": 12.0 * n * n * d / sec / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference" if ref is not None else "port",
+            "sample": "InfoNCE forward + backward at N = %d x %d-d (%.3f s), fp32" % (n, d, sec)}
+
+
+def run_config5_reference(args):
+    cb = _config5_cpu()
+    line = {"impl": "reference", "metric": "contrastive_loss_fwd_bwd_tflops", "value": cb["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": 3, "warmup": 1, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOADS["config5"], "N_headline": 2048, "D": 512, "loss_headline": "infonce"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -480,20 +698,32 @@ def main():
     ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused=True) instead of mmdti_b200.optim.FusedAdam")
     ap.add_argument("--inputs", default="pair", choices=["pair", "coords"],
                     help="host batch format of the e2e path: the reference's (tokens, distance, edge_type) or (tokens, coordinates)")
-    ap.add_argument("--workload", default="encoder", choices=sorted(WORKLOADS),
-                    help="encoder = BASELINE configs[1] (default); hotpath = encoder + InfoNCE + FDS.smooth + ConR in the step")
-    ap.add_argument("--batch", type=int, default=128, help="molecules per GPU (default: BASELINE configs[1])")
-    ap.add_argument("--n-atoms", type=int, default=64, help="atoms per molecule; L = n_atoms + 2 <= 264")
-    ap.add_argument("--smiles-len", type=int, default=64, help="length of the second-modality sequence (hotpath workload)")
+    ap.add_argument("--workload", default="hotpath", choices=sorted(WORKLOADS),
+                    help="hotpath (default) = encoder + InfoNCE + FDS.smooth + ConR in the step on the configs[1] geometry; "
+                         "encoder = configs[1] literally; config3 / config4 / config5 = BASELINE configs[2..4]")
+    ap.add_argument("--batch", type=int, default=None, help="molecules per GPU (default: per workload, 128 for configs[1])")
+    ap.add_argument("--n-atoms", type=int, default=None, help="atoms per molecule; L = n_atoms + 2 <= 264")
+    ap.add_argument("--smiles-len", type=int, default=None, help="length of the second-modality sequence")
     ap.add_argument("--cpu-sample", type=int, default=32, help="molecules per step of the CPU arm's bounded sample")
+    ap.add_argument("--nmax", type=int, default=65536, help="config5: largest N of the sweep")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
-    set_shape(args.batch, args.n_atoms, args.smiles_len)
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    n_ranks = max(world, args.gpus)
+    b0, a0, s0 = SPECS[args.workload][:3]
+    if b0 is None:                                      # config 3: the GLOBAL batch is fixed (strong scaling)
+        if GLOBAL_BATCH_CONFIG3 % n_ranks:
+            raise SystemExit("config3: the global batch %d is not divisible by %d GPUs" % (GLOBAL_BATCH_CONFIG3, n_ranks))
+        b0 = GLOBAL_BATCH_CONFIG3 // n_ranks
+    set_shape(args.batch or b0, args.n_atoms or a0, args.smiles_len or s0)
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, n_ranks)
+        return
+    if args.workload == "config5":
+        if rank == 0:
+            run_config5(args)
         return
     if world == 1 and args.gpus > 1:
         # not launched under torchrun: re-exec one rank per GPU

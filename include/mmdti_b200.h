@@ -133,7 +133,7 @@ int mmdti_pair_mask_fill(void* pair, const uint8_t* key_pad, int B, int H, int L
 int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, int64_t ldqkv,
                         const void* pair_in, void* pair_out, void* o, int64_t ldo, int B, int H,
                         int L, float scale, float dropout_p, uint64_t seed, int act_dtype,
-                        int pair_dtype, const uint32_t* keep_bits, void* stream);
+                        int pair_dtype, void* stream);
 
 /* Backward.  s = pair_out and o = the output of the forward call (same seed/dropout_p; o and d_o
  * share the row stride lddo; rowsum(dA o A) is taken as d_o . o).  d_pair_out may be NULL
@@ -146,15 +146,7 @@ int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq
                         const void* o, const void* d_o, int64_t lddo, const void* d_pair_out, void* d_pair_in,
                         void* dq, void* dk, void* dv, int64_t lddqkv, int B, int H, int L,
                         float scale, float dropout_p, uint64_t seed, int act_dtype, int pair_dtype,
-                        int gpair_dtype, const uint32_t* keep_bits, void* stream);
-
-/* Optional bit-packed dropout keep mask for the two calls above (keep_bits may be NULL: the kernels then evaluate the
- * counter-based hash themselves; the result is identical).  bits: (B*H*L rows) x mmdti_pair_keep_words(L) words,
- * bit c of word w of a row = keep(row, 32 w + c).  The mask depends on (seed, b, h, i, j) only, so it can be produced on
- * a side stream before the layer runs and is then shared by the forward and the backward (the hash costs 13.6 us per
- * launch at config 2 when evaluated in-kernel). */
-int mmdti_pair_keep_words(int L);
-int mmdti_pair_attn_keep_bits(uint32_t* bits, int B, int H, int L, float dropout_p, uint64_t seed, void* stream);
+                        int gpair_dtype, void* stream);
 
 /* Debug/test export: the keep mask (uint8, (B,H,L,L)) mmdti_pair_attn_fwd uses for `seed`. */
 int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, float dropout_p, uint64_t seed,

@@ -38,6 +38,14 @@ void mmdti_set_error(const char* fmt, ...);
 
 static inline bool mmdti_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+// Launch-configuration caches (cudaFuncSetAttribute / occupancy) are per-device facts: key them by the current device.
+constexpr int MMDTI_MAX_DEVICES = 64;
+static inline int mmdti_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < MMDTI_MAX_DEVICES ? dev : 0;
+}
+
 // ---------------------------------------------------------------- type helpers
 typedef __nv_bfloat16 bf16;
 

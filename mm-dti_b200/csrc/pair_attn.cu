@@ -26,7 +26,7 @@ namespace {
 constexpr int HD = MMDTI_HEAD_DIM;  // 8
 constexpr int NSTAGE = 2;      // backward ring
 constexpr bool K2_BWD_CS_DEFAULT = true;   // column-split backward for L > 136 (MMDTI_K2_BWD_CS=0/1 overrides)
-constexpr bool K2_FWD_CS_DEFAULT = false;  // column-split forward for L > 136 (MMDTI_K2_FWD_CS=0/1 overrides)
+constexpr bool K2_FWD_CS_DEFAULT = true;   // column-split forward for L > 136 (MMDTI_K2_FWD_CS=0/1 overrides)
 constexpr int NSTAGE_F = 3;    // forward ring: the bulk store of item w-1 may still be reading its stage while w+1 loads
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -50,7 +50,6 @@ struct FwdParams {
     uint32_t thresh16;
     unsigned long long seed;
     const unsigned long long* seed_off;
-    const uint32_t* keep_bits;   // optional bit-packed keep mask (B*H*L rows x keep_words(L) words), see mmdti_pair_attn_keep_bits
     int crb, nchunks;     // 16-row blocks per chunk, chunks per tile
 };
 
@@ -63,7 +62,6 @@ struct BwdParams {
     uint32_t thresh16;
     unsigned long long seed;
     const unsigned long long* seed_off;
-    const uint32_t* keep_bits;
     int crb, nchunks;
 };
 
@@ -221,18 +219,6 @@ pair_attn_fwd_kernel(const FwdParams p) {
             TP* srow_a = stage(s).slab + la * G::STRIDE;
             TP* srow_b = stage(s).slab + lb * G::STRIDE;
             float sc[NKB][4];
-            // keep-mask words of the two rows (precomputed mask): issued first, consumed after the softmax
-            constexpr int NW = (NKB * 8 + 31) / 32;
-            uint32_t wa[NW], wb[NW];
-            if (do_drop && p.keep_bits) {
-                const uint32_t* ka_ = p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW;
-                const uint32_t* kb_ = p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW;
-#pragma unroll
-                for (int i = 0; i < NW; ++i) { wa[i] = ka_[i]; wb[i] = HB ? kb_[i] : 0u; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) wa[i] = wb[i] = 0u;
-            }
 
             // ---- S = Q K^T
             if constexpr (!F32) {
@@ -313,22 +299,7 @@ pair_attn_fwd_kernel(const FwdParams p) {
             }
             // dropout: one hash per 4 elements; the odd column's 16 bits are compared in place (bits >= t << 16),
             // the even column's after one shift
-            if (do_drop && p.keep_bits) {
-                // precomputed mask: bit c of the row's words = keep(row, c); shift once per word so that this thread's
-                // column pair of block kb sits at the compile-time positions 8*(kb&3) and 8*(kb&3)+1
-#pragma unroll
-                for (int i = 0; i < NW; ++i) { wa[i] >>= (2 * q4); wb[i] >>= (2 * q4); }
-#pragma unroll
-                for (int kb = 0; kb < NKB; ++kb) {
-                    const uint32_t m0 = 1u << (8 * (kb & 3)), m1 = 2u << (8 * (kb & 3));
-                    if (!(wa[kb >> 2] & m0)) sc[kb][0] = 0.f;
-                    if (!(wa[kb >> 2] & m1)) sc[kb][1] = 0.f;
-                    if constexpr (HB) {
-                        if (!(wb[kb >> 2] & m0)) sc[kb][2] = 0.f;
-                        if (!(wb[kb >> 2] & m1)) sc[kb][3] = 0.f;
-                    }
-                }
-            } else if (do_drop) {
+            if (do_drop) {
                 const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
                 const uint32_t thi = p.thresh16 << 16;
 #pragma unroll
@@ -492,24 +463,14 @@ pair_attn_fwd_kernel(const FwdParams p) {
                     }
                 }
                 if (do_drop) {
-                    constexpr int NW = (NKB * 8 + 31) / 32;
                     const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
                     const uint32_t thi = p.thresh16 << 16;
-                    const uint32_t* ka_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW : nullptr;
-                    const uint32_t* kb_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW : nullptr;
                     uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
 #pragma unroll
                     for (int j = 0; j < KBW; ++j) {
                         const int kb = kb0 + j;
                         if (kb < NKB) {
-                            if (ka_) {
-                                const int sh = 8 * (kb & 3) + 2 * q4;
-                                const uint32_t wa_ = ka_[kb >> 2] >> sh, wb_ = kb_[kb >> 2] >> sh;
-                                if (!(wa_ & 1u)) sc[j][0] = 0.f;
-                                if (!(wa_ & 2u)) sc[j][1] = 0.f;
-                                if (!(wb_ & 1u)) sc[j][2] = 0.f;
-                                if (!(wb_ & 2u)) sc[j][3] = 0.f;
-                            } else {
+                            {
                                 // one hash serves the key-block pair (2m, 2m+1): .x even block, .y odd block
                                 const int col = kb * 8 + 2 * q4;
                                 if (j == 0 || (kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
@@ -752,18 +713,6 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
             T* ds_a = dSt + la * G::STRIDE;
             T* ds_b = dSt + lb * G::STRIDE;
             const bool va_ok = ra < L, vb_ok = HB && rbb < L;
-            // keep-mask words of the two rows: issued first, consumed after the softmax recompute
-            constexpr int NW = (NKB * 8 + 31) / 32;
-            uint32_t kwa[NW], kwb[NW];
-            if (do_drop && p.keep_bits) {
-                const uint32_t* ka_ = p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW;
-                const uint32_t* kb_ = p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW;
-#pragma unroll
-                for (int i = 0; i < NW; ++i) { kwa[i] = ka_[i]; kwb[i] = HB ? kb_[i] : 0u; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) kwa[i] = kwb[i] = 0u;
-            }
 
             // ---- softmax recompute: sc[][] := exp(S - max)
             float sc[NKB][4];
@@ -845,8 +794,6 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
 
             // ---- per key block: dA' = dO V^T, A', dS; dS kept in sc[][] for dQ
             const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
-#pragma unroll
-            for (int i = 0; i < NW; ++i) { kwa[i] >>= (2 * q4); kwb[i] >>= (2 * q4); }
             const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
             uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
 #pragma unroll
@@ -868,15 +815,7 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
                     }
                 }
                 float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
-                if (do_drop && p.keep_bits) {
-                    const uint32_t m0 = 1u << (8 * (kb & 3)), m1 = 2u << (8 * (kb & 3));
-                    k0 = (kwa[kb >> 2] & m0) ? p.keep_scale : 0.f;
-                    k1 = (kwa[kb >> 2] & m1) ? p.keep_scale : 0.f;
-                    if constexpr (HB) {
-                        k2 = (kwb[kb >> 2] & m0) ? p.keep_scale : 0.f;
-                        k3 = (kwb[kb >> 2] & m1) ? p.keep_scale : 0.f;
-                    }
-                } else if (do_drop) {
+                if (do_drop) {
                     if ((kb & 1) == 0) {
                         qwa = rng_quad_bits(rkey, ra, col);
                         if constexpr (HB) qwb = rng_quad_bits(rkey, rbb, col);
@@ -1079,9 +1018,6 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
                 const uint32_t rkey = rng_stream_key(eff_seed, (uint32_t)tile);
                 const uint32_t thi = p.thresh16 << 16;
                 const uint32_t* Vs32 = reinterpret_cast<const uint32_t*>(Vs);
-                constexpr int NW = (NKB * 8 + 31) / 32;
-                const uint32_t* ka_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(ra, L - 1)) * NW : nullptr;
-                const uint32_t* kb_ = p.keep_bits ? p.keep_bits + ((size_t)tile * L + min(rbb, L - 1)) * NW : nullptr;
                 uint2 qwa = make_uint2(0u, 0u), qwb = make_uint2(0u, 0u);
 #pragma unroll
                 for (int j = 0; j < KBW; ++j) {
@@ -1091,14 +1027,7 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
                         float da[4] = {0.f, 0.f, 0.f, 0.f};
                         mma_bf16_1688(da, ga0, ga1, Vs32[(kb * 8 + g) * 4 + q4]);
                         float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
-                        if (do_drop && ka_) {
-                            const int sh = 8 * (kb & 3) + 2 * q4;
-                            const uint32_t wa_ = ka_[kb >> 2] >> sh, wb_ = kb_[kb >> 2] >> sh;
-                            k0 = (wa_ & 1u) ? p.keep_scale : 0.f;
-                            k1 = (wa_ & 2u) ? p.keep_scale : 0.f;
-                            k2 = (wb_ & 1u) ? p.keep_scale : 0.f;
-                            k3 = (wb_ & 2u) ? p.keep_scale : 0.f;
-                        } else if (do_drop) {
+                        if (do_drop) {
                             // one hash serves the key-block pair (2m, 2m+1): .x even block, .y odd block
                             if (j == 0 || (kb & 1) == 0) { qwa = rng_quad_bits(rkey, ra, col); qwb = rng_quad_bits(rkey, rbb, col); }
                             const uint32_t ba = (kb & 1) ? qwa.y : qwa.x, bb = (kb & 1) ? qwb.y : qwb.x;
@@ -1267,35 +1196,6 @@ __global__ void dropout_mask_kernel(uint8_t* keep, int H, int L, uint32_t thresh
     }
 }
 
-// ------------------------------------------------------------------ bit-packed keep mask
-// bits[(bh * L + row) * NW + w], bit c of word w = keep(row, 32 w + c); exactly the mask the kernels derive from the
-// hash themselves.  One thread per (row, 4-column quad-pair): the two words of rng_quad_bits cover the column pairs
-// (2 q4, 2 q4 + 1) of blocks kb = 2m and 2m + 1.
-__global__ void keep_bits_kernel(uint32_t* __restrict__ bits, int H, int L, int NW, uint32_t thresh16, unsigned long long seed,
-                                 const unsigned long long* seed_off) {
-    seed = rng_effective_seed(seed, seed_off);
-    const int bh = blockIdx.x;
-    const uint32_t rkey = rng_stream_key(seed, (uint32_t)bh);
-    for (int e = threadIdx.x; e < L * NW; e += blockDim.x) {
-        const int r = e / NW, w = e - r * NW;
-        uint32_t word = 0u;
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {                 // 16-column groups of this word
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {             // column pairs inside an 8-column block
-                const int col = w * 32 + m * 16 + 2 * q;
-                const uint2 qb = rng_quad_bits(rkey, (uint32_t)r, (uint32_t)col);
-                const uint32_t lo = qb.x, hi = qb.y;  // block kb = 2m' (cols col, col+1), block kb + 1 (cols col+8, col+9)
-                word |= ((lo & 0xffffu) >= thresh16 ? 1u : 0u) << (m * 16 + 2 * q);
-                word |= ((lo >> 16) >= thresh16 ? 1u : 0u) << (m * 16 + 2 * q + 1);
-                word |= ((hi & 0xffffu) >= thresh16 ? 1u : 0u) << (m * 16 + 8 + 2 * q);
-                word |= ((hi >> 16) >= thresh16 ? 1u : 0u) << (m * 16 + 8 + 2 * q + 1);
-            }
-        }
-        bits[((size_t)bh * L + r) * NW + w] = word;
-    }
-}
-
 // ------------------------------------------------------------------ host-side dispatch
 inline void drop_params(float p, uint32_t& thresh16, float& keep_scale) {
     double t = floor((double)p * 65536.0 + 0.5);
@@ -1342,7 +1242,8 @@ int launch_fwd(FwdParams p, cudaStream_t st) {
             p.nchunks = ((p.L + 15) / 16 + 1) / 2;
             const size_t smem = smem_of(2);
             auto kern = pair_attn_fwd_kernel<T, TP, NKB, true>;
-            static int occ_cs = 0;
+            static int occ_dev[MMDTI_MAX_DEVICES] = {};      // per device: the attribute and the occupancy are device properties
+            int& occ_cs = occ_dev[mmdti_device_slot()];
             if (!occ_cs) {
                 MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 MMDTI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cs, kern, 256, smem));
@@ -1358,8 +1259,11 @@ int launch_fwd(FwdParams p, cudaStream_t st) {
     const size_t smem = smem_of(p.crb);
     MMDTI_REQUIRE(smem <= SMEM_CAP, "pair_attn_fwd: shared memory %zu exceeds cap (L=%d)", smem, p.L);
     auto kern = pair_attn_fwd_kernel<T, TP, NKB>;
-    static int occ = 0;
-    static size_t occ_smem = 0;
+    static int occ_dev[MMDTI_MAX_DEVICES] = {};
+    static size_t occ_smem_dev[MMDTI_MAX_DEVICES] = {};
+    const int dev_slot = mmdti_device_slot();
+    int& occ = occ_dev[dev_slot];
+    size_t& occ_smem = occ_smem_dev[dev_slot];
     const int threads = p.crb * 32;
     if (!occ || occ_smem != smem) {
         MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1402,7 +1306,8 @@ int launch_bwd(BwdParams p, cudaStream_t st) {
             p.nchunks = (nkb16 + 1) / 2;
             const size_t smem = smem_of(2);
             auto kern = pair_attn_bwd_kernel<T, TP, TG, NKB, true>;
-            static int occ_cs = 0;
+            static int occ_dev[MMDTI_MAX_DEVICES] = {};      // per device: the attribute and the occupancy are device properties
+            int& occ_cs = occ_dev[mmdti_device_slot()];
             if (!occ_cs) {
                 MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 MMDTI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cs, kern, 256, smem));
@@ -1422,8 +1327,11 @@ int launch_bwd(BwdParams p, cudaStream_t st) {
     const size_t smem = smem_of(p.crb);
     MMDTI_REQUIRE(smem <= SMEM_CAP, "pair_attn_bwd: shared memory %zu exceeds cap (L=%d)", smem, p.L);
     auto kern = pair_attn_bwd_kernel<T, TP, TG, NKB>;
-    static int occ = 0;
-    static size_t occ_smem = 0;
+    static int occ_dev[MMDTI_MAX_DEVICES] = {};
+    static size_t occ_smem_dev[MMDTI_MAX_DEVICES] = {};
+    const int dev_slot = mmdti_device_slot();
+    int& occ = occ_dev[dev_slot];
+    size_t& occ_smem = occ_smem_dev[dev_slot];
     const int threads = nwarps * 32;
     if (!occ || occ_smem != smem) {
         MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1486,8 +1394,7 @@ extern "C" int mmdti_pair_ld(int L) {
 
 extern "C" int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, int64_t ldqkv, const void* pair_in,
                                    void* pair_out, void* o, int64_t ldo, int B, int H, int L, float scale,
-                                   float dropout_p, uint64_t seed, int act_dtype, int pair_dtype, const uint32_t* keep_bits,
-                                   void* stream) {
+                                   float dropout_p, uint64_t seed, int act_dtype, int pair_dtype, void* stream) {
     if (int rc = check_common(q, k, v, ldqkv, B, H, L, act_dtype)) return rc;
     MMDTI_REQUIRE(pair_in && pair_out && o, "pair_attn_fwd: null buffer");
     MMDTI_REQUIRE(mmdti_aligned(pair_in, 16) && mmdti_aligned(pair_out, 16) && mmdti_aligned(o, 16),
@@ -1497,7 +1404,6 @@ extern "C" int mmdti_pair_attn_fwd(const void* q, const void* k, const void* v, 
     FwdParams p;
     p.q = q; p.k = k; p.v = v; p.o = o; p.pin = pair_in; p.pout = pair_out;
     p.ldqkv = ldqkv; p.ldo = ldo; p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed; p.seed_off = mmdti_seed_offset_ptr();
-    p.keep_bits = keep_bits;
     p.crb = 0; p.nchunks = 0;
     drop_params(dropout_p, p.thresh16, p.keep_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1518,7 +1424,7 @@ extern "C" int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, 
                                    const void* o, const void* d_o, int64_t lddo, const void* d_pair_out, void* d_pair_in,
                                    void* dq, void* dk, void* dv, int64_t lddqkv, int B, int H, int L, float scale,
                                    float dropout_p, uint64_t seed, int act_dtype, int pair_dtype, int gpair_dtype,
-                                   const uint32_t* keep_bits, void* stream) {
+                                   void* stream) {
     if (int rc = check_common(q, k, v, ldqkv, B, H, L, act_dtype)) return rc;
     MMDTI_REQUIRE(s && o && d_o && d_pair_in && dq && dk && dv, "pair_attn_bwd: null buffer");
     const size_t esz = act_dtype == MMDTI_F32 ? 4 : 2;
@@ -1531,7 +1437,6 @@ extern "C" int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, 
     p.q = q; p.k = k; p.v = v; p.s = s; p.o = o; p.d_o = d_o; p.dpout = d_pair_out; p.dpin = d_pair_in;
     p.dq = dq; p.dk = dk; p.dv = dv; p.ldqkv = ldqkv; p.lddo = lddo; p.lddqkv = lddqkv;
     p.B = B; p.H = H; p.L = L; p.scale = scale; p.seed = seed; p.seed_off = mmdti_seed_offset_ptr();
-    p.keep_bits = keep_bits;
     p.crb = 0; p.nchunks = 0;
     drop_params(dropout_p, p.thresh16, p.keep_scale);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1545,23 +1450,6 @@ extern "C" int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, 
     if (pair_dtype == MMDTI_F32 && gpair_dtype == MMDTI_F32) return dispatch_bwd_nkb<bf16, float, float>(p, st);
     mmdti_set_error("pair_attn_bwd: unsupported (pair_dtype=%d, gpair_dtype=%d) combination", pair_dtype, gpair_dtype);
     return MMDTI_ERR_ARG;
-}
-
-extern "C" int mmdti_pair_keep_words(int L) {
-    const int ld = mmdti_pair_ld(L);
-    return ld > 0 ? (ld + 31) / 32 : -1;
-}
-
-extern "C" int mmdti_pair_attn_keep_bits(uint32_t* bits, int B, int H, int L, float dropout_p, uint64_t seed, void* stream) {
-    MMDTI_REQUIRE(bits && B > 0 && H > 0 && L > 0 && mmdti_pair_keep_words(L) > 0, "keep_bits: bad arguments");
-    MMDTI_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "keep_bits: dropout_p out of range");
-    uint32_t thresh16;
-    float ks;
-    drop_params(dropout_p, thresh16, ks);
-    keep_bits_kernel<<<B * H, 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, H, L, mmdti_pair_keep_words(L), thresh16, seed,
-                                                                         mmdti_seed_offset_ptr());
-    MMDTI_LAUNCH_OK();
-    return MMDTI_OK;
 }
 
 extern "C" int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, float dropout_p, uint64_t seed,

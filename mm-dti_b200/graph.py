@@ -16,8 +16,14 @@ from . import _lib
 class GraphedStep:
     """step_fn(*device_tensors) -> tensor or tuple of tensors (e.g. the loss).  step_fn must run the
     complete step on the current stream (forward, backward, optionally optimizer.step()) and must not
-    synchronise with the host.  Parameters' .grad are left in static buffers (set .grad to None before
-    construction, do not set it to None afterwards).
+    synchronise with the host.
+
+    params: every parameter whose gradient the step produces.  Their ``.grad`` is set to None after the
+    warm-up and just before the capture, so that the captured backward WRITES each gradient (autograd's
+    AccumulateGrad takes the incoming buffer when ``.grad`` is undefined) instead of recording
+    ``grad += new`` against whatever the warm-up steps left behind -- with a defined ``.grad`` every replay
+    would add to the sum of all previous steps.  The gradients then live in graph-pool buffers that are
+    overwritten by each replay; do not set ``.grad`` to None (or zero it) after construction.
 
     example_inputs: tensors defining the static input signature; host (pinned) tensors are allowed,
     in which case every call copies them to the static device buffers inside the timed path.
@@ -26,7 +32,7 @@ class GraphedStep:
     pass capture_error_mode="thread_local" so that NCCL's watchdog thread does not invalidate the capture,
     and run enough warm-up steps for the communicator to exist before the capture starts."""
 
-    def __init__(self, step_fn, example_inputs, device=None, warmup=3, capture_error_mode="global"):
+    def __init__(self, step_fn, example_inputs, device=None, warmup=3, capture_error_mode="global", params=None):
         if not torch.cuda.is_available():
             raise _lib.MMDTIError("GraphedStep needs a CUDA device")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -49,6 +55,10 @@ class GraphedStep:
                 body()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        if params is not None:
+            for p in params:
+                p.grad = None
+        self.params = list(params) if params is not None else None
         n0 = _lib.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):

@@ -57,7 +57,7 @@ class TransformerEncoderWithPair(nn.Module):
         if padding_mask is not None:
             if not attn_mask.is_contiguous():
                 raise ValueError("attn_mask must be contiguous (B*H, L, L)")
-            ops.pair_mask_fill_(attn_mask, padding_mask)          # the caller's tensor, in place (Q1)
+            attn_mask = ops.pair_mask_fill_(attn_mask, padding_mask)      # the caller's tensor, in place (Q1)
         pair = ops.PairPadFn.apply(attn_mask.reshape(bsz * H, seq_len, seq_len), bsz, H, seq_len, config.pair_dtype())
         return self.forward_padded(emb, pair, padding_mask)
 

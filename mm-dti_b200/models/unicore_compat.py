@@ -131,7 +131,7 @@ class SelfMultiheadAttention(nn.Module):
             pair = ops.PairPadFn.apply(attn_bias.reshape(B * H, L, L), B, H, L, pdt)
         if key_padding_mask is not None:
             pair = pair.clone()
-            ops.pair_mask_fill_(pair, key_padding_mask)
+            pair = ops.pair_mask_fill_(pair, key_padding_mask)
         qkv = _lin(query, self.in_proj, dt).reshape(B * L, 3 * D)
         p = self.dropout if self.training else 0.0
         o, scores = ops.pair_attention(qkv, pair, B, H, L, self.scaling, p, ops.next_seed() if p > 0 else 0,

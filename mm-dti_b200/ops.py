@@ -12,15 +12,25 @@ from ._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
 
 _seed_lock = threading.Lock()
 _seed_counter = 0
+_seed_rank = 0
+
+
+def set_seed_rank(rank):
+    """Data parallel: fold the rank into every dropout seed, so that replicas which share torch's seed (identical
+    weights) still draw independent masks for their shards of the global batch, like DDP with per-rank RNG state."""
+    global _seed_rank
+    _seed_rank = int(rank)
 
 
 def next_seed():
-    """Deterministic per-call dropout seed derived from torch's seed and a call counter."""
+    """Deterministic per-call dropout seed derived from torch's seed, the data-parallel rank (set_seed_rank) and a
+    call counter."""
     global _seed_counter
     with _seed_lock:
         _seed_counter += 1
         c = _seed_counter
-    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + c * 0xBF58476D1CE4E5B9
+            + _seed_rank * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
 
 
 def reset_seed_counter():
@@ -176,9 +186,34 @@ class GaussBasisFn(torch.autograd.Function):
         return None, None, d_means.view(1, K), d_stds.view(1, K), d_mul.view(E, 1), d_bias.view(E, 1)
 
 
+class PairMaskFillFn(torch.autograd.Function):
+    """In-place fill of padded KEY columns as an autograd node: ``mark_dirty`` bumps the tensor's version counter the
+    way the reference's ``masked_fill_`` does (an upstream op that saved the tensor then raises instead of silently
+    using mutated values), and the gradient is zeroed at the filled positions."""
+
+    @staticmethod
+    def forward(ctx, pair, kp, B, H, L, ld, fill):
+        call("mmdti_pair_mask_fill", pair, kp, i32(B), i32(H), i32(L), i32(ld), i32(DTYPE_CODE[pair.dtype]), f32(fill),
+             stream_ptr())
+        ctx.mark_dirty(pair)
+        ctx.save_for_backward(kp)
+        ctx.dims = (B, H, L, ld)
+        return pair
+
+    @staticmethod
+    def backward(ctx, g):
+        (kp,) = ctx.saved_tensors
+        B, H, L, ld = ctx.dims
+        m = kp.bool()
+        if ld != L:
+            m = torch.nn.functional.pad(m, (0, ld - L), value=False)
+        return g.reshape(B, H, L, ld).masked_fill(m[:, None, None, :], 0).reshape(g.shape), None, None, None, None, None, None
+
+
 def pair_mask_fill_(pair, key_pad, fill=float("-inf")):
     """In place: pair[b,h,:,j] = fill where key_pad[b,j] (models/transformers.py:122-132).
-    ``pair`` is either the reference's dense (B*H,L,L) tensor or the padded (B,H,L,Lp) layout."""
+    ``pair`` is either the reference's dense (B*H,L,L) tensor or the padded (B,H,L,Lp) layout.  Returns ``pair``
+    (the same tensor object; use the return value so that autograd sees the in-place node)."""
     _lib.require_cuda(pair, key_pad)
     B, L = key_pad.shape
     if not pair.is_contiguous():
@@ -188,9 +223,7 @@ def pair_mask_fill_(pair, key_pad, fill=float("-inf")):
         raise _lib.MMDTIError("pair_mask_fill_: last dim %d is neither L=%d nor Lp=%d" % (ld, L, pair_ld(L)))
     H = pair.numel() // (B * L * ld)
     kp = key_pad.contiguous().to(torch.uint8)
-    call("mmdti_pair_mask_fill", pair, kp, i32(B), i32(H), i32(L), i32(ld), i32(DTYPE_CODE[pair.dtype]), f32(fill),
-         stream_ptr())
-    return pair
+    return PairMaskFillFn.apply(pair, kp, B, H, L, ld, float(fill))
 
 
 # =========================================================================== K2
@@ -212,7 +245,7 @@ class PairAttnFn(torch.autograd.Function):
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         call("mmdti_pair_attn_fwd", q, k, v, i64(3 * D), pair_in, pair_out, o, i64(D), i32(B), i32(H), i32(L),
              f32(scale), f32(dropout_p), u64(seed), i32(DTYPE_CODE[qkv.dtype]), i32(DTYPE_CODE[pair_in.dtype]),
-             None, stream_ptr())
+             stream_ptr())
         if inplace_pair:
             ctx.mark_dirty(pair_in)
         ctx.save_for_backward(qkv, pair_out, o)
@@ -241,7 +274,7 @@ class PairAttnFn(torch.autograd.Function):
         dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
         call("mmdti_pair_attn_bwd", q, k, v, i64(3 * D), s, o, d_o, i64(D), d_pair_out, d_pair_in, dq, dk, dv,
              i64(3 * D), i32(B), i32(H), i32(L), f32(scale), f32(dropout_p), u64(seed), i32(DTYPE_CODE[qkv.dtype]),
-             i32(DTYPE_CODE[s.dtype]), i32(DTYPE_CODE[gdt]), None, stream_ptr())
+             i32(DTYPE_CODE[s.dtype]), i32(DTYPE_CODE[gdt]), stream_ptr())
         return dqkv, d_pair_in, None, None, None, None, None, None, None
 
 
@@ -305,12 +338,6 @@ def _mm_f32(a, b):
 
 _side_streams = {}
 overlap_wgrad = True      # run weight-gradient GEMMs / bias column sums of a layer on a side stream (off the critical path)
-# EncoderLayerFn: bit-packed attention-dropout mask produced on a side stream instead of the in-kernel hash.  K2 gets
-# faster (forward 85.5 -> 77.9 us, backward 137.3 -> 133.0 us) but a per-layer mask kernel is NOT hidden by the short
-# LayerNorm + in_proj window: the step got 0.16 ms slower, so it is off unless the caller provides the mask (see
-# TransformerEncoderWithPair: masks of all layers generated at the start of the step).
-precomputed_keep_mask = os.environ.get("MMDTI_KEEP_BITS", "0") != "0"
-
 
 def _side_stream(dev):
     key = (dev.type, dev.index)
@@ -405,17 +432,6 @@ class EncoderLayerFn(torch.autograd.Function):
         ln1_wd, ln1_bd, ln2_wd, ln2_bd = (t.detach().float().contiguous() for t in (ln1_w, ln1_b, ln2_w, ln2_b))
         pair_in = pair_in.detach()
         chain_in = h1_in is not None
-        # attention-dropout keep mask, bit-packed: it depends on (seed, b, h, i, j) only, so it is produced on the side
-        # stream under LayerNorm-1 / in_proj and shared by K2's forward and backward (the in-kernel hash costs ~14 us a launch)
-        keep = None
-        if p_attn > 0.0 and precomputed_keep_mask:
-            main = torch.cuda.current_stream(x.device)
-            side = _side_stream(x.device)
-            keep = torch.empty((B * H * L, _lib.lib().mmdti_pair_keep_words(L)), device=x.device, dtype=torch.int32)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                call("mmdti_pair_attn_keep_bits", keep, i32(B), i32(H), i32(L), f32(p_attn), u64(seeds[0]), stream_ptr())
-            keep.record_stream(side)
         if chain_in:
             h1, st1 = h1_in.detach(), st1_in.detach()
         else:
@@ -423,10 +439,8 @@ class EncoderLayerFn(torch.autograd.Function):
         qkv = torch.addmm(b_in_l, h1, w_in_l.t())
         o = torch.empty((rows, D), device=x.device, dtype=dt)
         pair_out = torch.empty_like(pair_in)
-        if keep is not None:
-            main.wait_stream(side)
         call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_in, pair_out, o, i64(D),
-             i32(B), i32(H), i32(L), f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_in.dtype]), keep, sp)
+             i32(B), i32(H), i32(L), f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_in.dtype]), sp)
         a = torch.addmm(b_out_l, o, w_out_l.t())
         x1 = torch.empty_like(x2d)
         h2 = torch.empty((rows, D), device=x.device, dtype=dt)
@@ -450,7 +464,6 @@ class EncoderLayerFn(torch.autograd.Function):
             call("mmdti_dropout_residual_fwd", x1, f, x2, i64(rows * D), f32(p_drop), u64(seeds[2]), i32(code), sp)
         ctx.save_for_backward(x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_wd, ln2_wd, w_in_l, w_out_l,
                               w_fc1_l, w_fc2_l, *((x2, st_next, nxt_wd) if chain_out else ()))
-        ctx.keep = keep
         ctx.cfg = cfg
         ctx.chain = (chain_in, chain_out)
         ctx.set_materialize_grads(False)
@@ -531,7 +544,7 @@ class EncoderLayerFn(torch.autograd.Function):
         call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_out, o, d_o, i64(D),
              dpair_out, dpair_in, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L),
              f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_out.dtype]),
-             i32(DTYPE_CODE[pair_out.dtype]), ctx.keep, sp)
+             i32(DTYPE_CODE[pair_out.dtype]), sp)
         def in_proj_grads():
             call("mmdti_colsum", dqkv, db_in, i32(rows), i32(3 * D), i32(code), stream_ptr())
             return _mm_f32(dqkv.t(), h1)

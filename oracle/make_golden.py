@@ -216,6 +216,70 @@ def gold_encoder_slice(ref):
     _save("encoder_slice", d)
 
 
+def gold_encoder_15l(ref):
+    """The configuration bench.py times (BASELINE configs[1] geometry): the reference's OWN classes — embed -> gbf ->
+    gbf_proj -> TransformerEncoderWithPair exactly as models/mm_model.py:545-559 — at 15 layers, 64 heads x 8, 512-d,
+    FFN 2048 (models/mm_model.py:325-343), L = 66 ragged, B = 4.  Weights: oracle/detw.py (47 M parameters, not
+    stored).  Two weight regimes: 'init' (std 0.02 = init_bert_params) and 'wide' (std 0.05: sharper softmax, larger
+    pair updates, i.e. what the 15-add pair chain looks like away from initialisation).
+    Stored: all_repr, the residual stream of molecule 0 after EVERY layer (per-layer error growth), the pair tensor
+    of molecule 0 / head 0 after every layer, 12 gradients (rows [:ROWS] of the big ones)."""
+    from oracle.detw import det_state_dict
+    mm, tr = ref["mm_model"], ref["transformers"]
+    H, D, Fd, nl, ROWS = 64, 512, 2048, 15, 48
+    for tag, std, seed in (("init", 0.02, 7), ("wide", 0.05, 8)):
+        emb_tok = torch.nn.Embedding(31, D, 0)
+        gbf = mm.GaussianLayer(128, 961)
+        proj = mm.NonLinearHead(128, H, "gelu")
+        enc = tr.TransformerEncoderWithPair(encoder_layers=nl, embed_dim=D, ffn_embed_dim=Fd,
+                                            attention_heads=H, max_seq_len=512,
+                                            no_final_head_layer_norm=True)
+        mods = torch.nn.ModuleDict({"embed_tokens": emb_tok, "gbf": gbf, "gbf_proj": proj, "encoder": enc})
+        sd = det_state_dict({k: tuple(v.shape) for k, v in mods.state_dict().items()}, seed=seed, std=std)
+        mods.load_state_dict(sd)
+        mods.eval()
+        tokens, dist, et = synth_molecules(4, 64, seed=700 + seed)
+        pm = tokens.eq(0)
+        assert pm.any()
+        per_layer_x, per_layer_pair = [], []
+
+        def grab(_m, _i, o_):
+            per_layer_x.append(o_[0][0].detach().clone())
+            per_layer_pair.append(o_[1][0].detach().clone())
+
+        hooks = [layer.register_forward_hook(grab) for layer in enc.layers]
+        x = emb_tok(tokens)
+        b = proj(gbf(dist, et)).permute(0, 3, 1, 2).contiguous()
+        b = b.view(-1, b.size(-2), b.size(-1))
+        rep = enc(x, padding_mask=pm, attn_mask=b)[0]
+        for h_ in hooks:
+            h_.remove()
+        g = torch.randn(rep.shape, generator=torch.Generator().manual_seed(31 + seed))
+        (rep * g).sum().backward()
+        named = dict(mods.named_parameters())
+        gsel = ["embed_tokens.weight", "gbf.means.weight", "gbf.stds.weight", "gbf.mul.weight", "gbf.bias.weight",
+                "gbf_proj.linear1.weight", "gbf_proj.linear2.weight",
+                "encoder.layers.0.self_attn.in_proj.weight", "encoder.layers.0.self_attn.in_proj.bias",
+                "encoder.layers.14.self_attn.in_proj.weight", "encoder.layers.14.self_attn.in_proj.bias",
+                "encoder.layers.7.fc1.weight", "encoder.layers.7.fc2.bias", "encoder.layers.0.self_attn.out_proj.weight",
+                "encoder.layers.3.self_attn_layer_norm.weight", "encoder.layers.14.final_layer_norm.bias",
+                "encoder.emb_layer_norm.weight", "encoder.final_layer_norm.weight"]
+        d = {"in.tokens": tokens, "in.dist": dist, "in.edge_type": et, "in.up": g, "out.rep": rep,
+             "out.x_layers_mol0": torch.stack(per_layer_x), "out.pair_layers_mol0_head0": torch.stack(per_layer_pair),
+             "cfg": np.array([H, D, Fd, nl, seed, ROWS]), "cfg.std": np.array([std])}
+        for k in gsel:
+            gr = named[k].grad
+            d["grad." + k] = gr[:ROWS] if (gr.dim() == 2 and gr.shape[0] > ROWS and gr.numel() > 70000) else gr
+        # pin the restatement at this depth
+        p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        mine = restate.unimol_encoder(tokens, dist, et, p, heads=H, n_layers=nl)
+        _close(mine, rep, 1e-5, "enc15.%s.rep" % tag)
+        (mine * g).sum().backward()
+        for k in gsel:
+            _close(p[k].grad, named[k].grad, 1e-4, "enc15.%s.grad.%s" % (tag, k))
+        _save("encoder_15L_" + tag, d)
+
+
 def gold_infonce(ref):
     inf = ref["infonce"]
     g = torch.Generator().manual_seed(40)
@@ -490,6 +554,7 @@ def main():
     gold_pair_bias(ref)
     gold_encoder(ref)
     gold_encoder_slice(ref)
+    gold_encoder_15l(ref)
     gold_infonce(ref)
     gold_ct(ref)
     gold_fds(ref)

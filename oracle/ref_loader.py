@@ -16,8 +16,13 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("MMDTI_REFERENCE_ROOT", "/root/reference")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+# where the reference tree is looked for: an explicit override, the build container's read-only checkout, or the
+# git-ignored copy that scripts/install_reference.sh makes under baseline/_ref so that bench.py --impl reference can
+# run the reference's own modules on the GPU box (kind "reference").  The -m gpu tests and smoke() never come here.
+_CANDIDATES = [os.environ.get("MMDTI_REFERENCE_ROOT"), "/root/reference",
+               os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
+REF_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "models"))), "/root/reference")
 
 
 def available():

@@ -40,17 +40,20 @@ def gaussian(x, mean, std):
     return torch.exp(-0.5 * (((x - mean) / std) ** 2)) / (a * std)
 
 
-def gaussian_basis(dist, edge_type, p, prefix="gbf."):
+def gaussian_basis(dist, edge_type, p, prefix="gbf.", wide=False):
     """GaussianLayer.forward, models/mm_model.py:254-269.
-    dist (B,L,L) float, edge_type (B,L,L) int64 -> (B,L,L,K) fp32."""
+    dist (B,L,L) float, edge_type (B,L,L) int64 -> (B,L,L,K) fp32.
+    wide=True: the same expressions with the reference's ``.float()`` casts replaced by float64 (dist and the
+    parameters given as float64) -- a higher-precision truth for sums over > 1e5 pairs; not the reference's arithmetic."""
+    cast = torch.float64 if wide else torch.float32
     mul = p[prefix + "mul.weight"][edge_type].to(dist.dtype)      # (B,L,L,1)
     bias = p[prefix + "bias.weight"][edge_type].to(dist.dtype)
     u = mul * dist.unsqueeze(-1) + bias
     K = p[prefix + "means.weight"].shape[-1]
     u = u.expand(-1, -1, -1, K)
-    mean = p[prefix + "means.weight"].float().view(-1)
-    std = p[prefix + "stds.weight"].float().view(-1).abs() + 1e-5
-    return gaussian(u.float(), mean, std).to(p[prefix + "means.weight"].dtype)
+    mean = p[prefix + "means.weight"].to(cast).view(-1)
+    std = p[prefix + "stds.weight"].to(cast).view(-1).abs() + 1e-5
+    return gaussian(u.to(cast), mean, std).to(p[prefix + "means.weight"].dtype)
 
 
 def nonlinear_head(x, p, prefix="gbf_proj."):
@@ -60,9 +63,9 @@ def nonlinear_head(x, p, prefix="gbf_proj."):
     return F.linear(x, p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])
 
 
-def pair_bias(dist, edge_type, p):
+def pair_bias(dist, edge_type, p, wide=False):
     """models/mm_model.py:553-556: gbf -> gbf_proj -> permute(0,3,1,2) -> (B*H,L,L)."""
-    g = gaussian_basis(dist, edge_type, p)
+    g = gaussian_basis(dist, edge_type, p, wide=wide)
     o = nonlinear_head(g, p)
     o = o.permute(0, 3, 1, 2).contiguous()
     return o.view(-1, o.size(-2), o.size(-1))

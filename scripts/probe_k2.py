@@ -21,7 +21,6 @@ ap.add_argument("--pair", default="bf16")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", default="")
 ap.add_argument("--noflush", action="store_true")
-ap.add_argument("--keepbits", action="store_true", help="use the precomputed bit-packed dropout mask")
 a = ap.parse_args()
 PEAK = 6551.0
 try:
@@ -45,22 +44,17 @@ dqkv = torch.empty_like(qkv)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 code, pcode = DTYPE_CODE[torch.bfloat16], DTYPE_CODE[pdt]
 scale = 8 ** -0.5
-KEEP = None
-if a.keepbits and a.p > 0:
-    from mmdti_b200 import _lib
-    KEEP = torch.empty(B * H * L, _lib.lib().mmdti_pair_keep_words(L), device="cuda", dtype=torch.int32)
-    call("mmdti_pair_attn_keep_bits", KEEP, i32(B), i32(H), i32(L), f32(a.p), u64(7), stream_ptr())
 
 
 def fwd():
     call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H), i32(L),
-         f32(scale), f32(a.p), u64(7), i32(code), i32(pcode), KEEP, stream_ptr())
+         f32(scale), f32(a.p), u64(7), i32(code), i32(pcode), stream_ptr())
 
 
 def bwd():
     call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pout, o, d_o, i64(D), dpo, dpi, dqkv[:, :D],
          dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L), f32(scale), f32(a.p), u64(7), i32(code), i32(pcode),
-         i32(pcode), KEEP, stream_ptr())
+         i32(pcode), stream_ptr())
 
 
 def timeit(fn):

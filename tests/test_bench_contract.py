@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("workload", ["encoder", "hotpath"])
+@pytest.mark.parametrize("workload", ["encoder", "hotpath", "config3"])
 def test_reference_arm_json_contract(workload):
     cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--batch", "4",
            "--n-atoms", "10", "--smiles-len", "6", "--cpu-sample", "2", "--steps", "1", "--warmup", "1"]
@@ -23,9 +23,11 @@ def test_reference_arm_json_contract(workload):
     assert d["impl"] == "reference" and d["metric"] == "train_molecules_per_sec" and d["unit"] == "molecules/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["config"]["per_gpu_batch"] == 4 and d["config"]["seq_len"] == 12 and "b4x10atoms" in d["config"]["workload"]
-    assert ("infonce" in d["config"]["workload"]) == (workload == "hotpath")
+    assert ("infonce" in d["config"]["workload"]) == (workload != "encoder")
+    assert d["scaling"] == ("strong" if workload == "config3" else "weak")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "2 of the 4 molecules" in cb["sample"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and "2 of the 4 molecules" in cb["sample"]
+    assert d["config"]["cpu_sample_molecules_per_step"] == 2 and d["config"]["global_batch"] == 4
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -46,5 +48,3 @@ def test_batch_helpers():
         assert not torch.equal(y, y2) and all(torch.equal(stats[k], stats2[k]) for k in stats)
     finally:
         bench.set_shape(128, 64, 64)
-        for k in bench.WORKLOADS:
-            bench.WORKLOADS[k] = bench.WORKLOADS[k].replace("b6x12atoms", "b128x64atoms")

@@ -1,0 +1,71 @@
+"""GPU parity at the configuration bench.py actually times: 15 layers, 64 heads x 8, 512-d, FFN 2048, L = 66 (ragged),
+against fixtures produced by the reference's own classes (oracle/make_golden.py:gold_encoder_15l; reference
+models/mm_model.py:325-343,545-559, models/transformers.py:96-183).  This is the "decide with data" of SURVEY.md
+§7.3-3: how the bf16 / fp16 / fp32 pair tensor behaves through the 15-add pair chain, layer by layer.
+
+Tolerances (tests/tolerances.py): fp32 validation mode meets north_star's 1e-5 class; in bf16 mode the scalar losses
+meet rel 1e-3, elementwise tensors are bounded by the bf16 storage rounding (2^-9 = 2e-3 per stored activation, see
+tolerances.py for each quantity)."""
+import pytest
+import torch
+
+from conftest import load_golden, norm_err, rel_err
+from oracle.detw import det_state_dict
+from tests_util import slice_shapes
+from tolerances import TOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["init", "wide"])
+@pytest.mark.parametrize("act,pair", [("fp32", "fp32"), ("bf16", "bf16"), ("bf16", "fp16"), ("bf16", "fp32")])
+def test_unimol_encoder_15_layers_golden(tag, act, pair, report):
+    import mmdti_b200
+    from mmdti_b200 import ops
+    from mmdti_b200.models.encoder import UnimolEncoder
+    g = load_golden("encoder_15L_" + tag)
+    H, D, Fd, nl, seed, rows = [int(v) for v in g["cfg"]]
+    std = float(g["cfg.std"][0])
+    dev = "cuda"
+    m = UnimolEncoder(encoder_layers=nl)
+    m.load_state_dict(det_state_dict(slice_shapes(H, D, Fd, nl), seed=seed, std=std))
+    m = m.to(dev).eval()
+    xs, pairs = [], []
+
+    def grab(_m, _i, out):
+        L = out[0].shape[1]
+        xs.append(out[0][0].detach().float().cpu())
+        pairs.append(out[1][0, 0, :, :L].detach().float().cpu())
+
+    hooks = [layer.register_forward_hook(grab) for layer in m.encoder.layers]
+    with mmdti_b200.precision(act=act, pair=pair):
+        rep = m(g["in.tokens"].to(dev), g["in.dist"].to(dev), g["in.edge_type"].to(dev))
+        (rep * g["in.up"].to(dev)).sum().backward()
+    for h in hooks:
+        h.remove()
+    named = dict(m.named_parameters())
+    errs = {"rep": rel_err(rep, g["out.rep"]), "rep_norm": norm_err(rep, g["out.rep"])}
+    # per-layer growth of the residual-stream and pair-tensor error (molecule 0 / head 0)
+    x_growth = [norm_err(a, b) for a, b in zip(xs, g["out.x_layers_mol0"])]
+    p_growth = [norm_err(a, b) for a, b in zip(pairs, g["out.pair_layers_mol0_head0"])]
+    errs["x_layer_max"], errs["pair_layer_max"] = max(x_growth), max(p_growth)
+    gerr = {}
+    for k, v in g.items():
+        if k.startswith("grad."):
+            gr = named[k[5:]].grad
+            gr = gr[:rows] if gr.shape != v.shape else gr
+            gerr[k[5:]] = norm_err(gr, v)
+            errs["dmax_" + k[5:]] = rel_err(gr, v)
+    errs["grad_norm_max"] = max(gerr.values())
+    report("encoder_15L", tag, act, pair, "rep=%.2e rep_norm=%.2e" % (errs["rep"], errs["rep_norm"]),
+           "x_by_layer=" + ",".join("%.1e" % e for e in x_growth), "pair_by_layer=" + ",".join("%.1e" % e for e in p_growth),
+           "grad_norm=" + str({k: "%.1e" % v for k, v in gerr.items()}),
+           "grad_max=" + str({k[5:]: "%.1e" % v for k, v in errs.items() if k.startswith("dmax_")}))
+    key = "enc15." + ("fp32" if act == "fp32" else "bf16.pair_" + pair)
+    t = TOL[key]
+    assert errs["rep"] < t["rep_max"] and errs["rep_norm"] < t["rep_norm"], (errs["rep"], errs["rep_norm"])
+    assert errs["x_layer_max"] < t["x_layer_norm"] and errs["pair_layer_max"] < t["pair_layer_norm"], (x_growth, p_growth)
+    assert errs["grad_norm_max"] < t["grad_norm"], gerr
+    assert max(v for k, v in errs.items() if k.startswith("dmax_")) < t["grad_max"], errs
+    # padding: all_repr rows of padded tokens follow the reference bit pattern of finiteness
+    assert torch.isfinite(rep).all()

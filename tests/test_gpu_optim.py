@@ -114,3 +114,51 @@ def test_graphed_step_prefetch_pipeline():
     with pytest.raises(Exception):
         gs()
     gs.close()
+
+
+def test_graphed_training_step_matches_eager(report):
+    """N replays of a graphed forward + backward + FusedAdam step == the same number of eager steps with zero_grad
+    between them (dropout off): parameters AND Adam moments.  Guards against the captured backward recording
+    ``grad += new`` onto gradients the warm-up left defined (each replay would then see the sum of all previous steps)."""
+    import mmdti_b200
+    from mmdti_b200.data import synthetic_molecules
+    from mmdti_b200.graph import GraphedStep
+    from mmdti_b200.models.encoder import UnimolEncoder
+    dev = "cuda"
+    tokens, dist, et, _ = synthetic_molecules(4, 14, seed=3)
+    inputs = [tokens.to(dev), dist.to(dev), et.to(dev)]
+    g = torch.randn(4, 16, 512, generator=torch.Generator().manual_seed(1)).to(dev)
+    n_warm, n_steps = 3, 4
+    for act, pair, tol in (("fp32", "fp32", 1e-5), ("bf16", "bf16", 1e-5)):
+        out = []
+        for graphed in (False, True):
+            torch.manual_seed(0)
+            m = UnimolEncoder(encoder_layers=2).to(dev).eval()
+            opt = FusedAdam(m.parameters(), lr=1e-3, eps=1e-6, shadows=m.encoder.use_external_lowp())
+
+            def step(*inp):
+                loss = (m(*inp).float() * g).sum()
+                loss.backward()
+                opt.step()
+                return loss.detach()
+
+            with mmdti_b200.precision(act=act, pair=pair):
+                if graphed:
+                    # the warm-up steps ARE executed optimizer steps; the capture pass itself executes nothing
+                    gs = GraphedStep(step, inputs, warmup=n_warm, params=list(m.parameters()))
+                    for _ in range(n_steps):
+                        gs(*inputs)
+                    gs.close()
+                else:
+                    for _ in range(n_warm + n_steps):
+                        step(*inputs)
+                        opt.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+            assert int(opt.step_count.item()) == n_warm + n_steps
+            out.append(([p.detach().clone() for p in m.parameters()], opt.exp_avg.clone(), opt.exp_avg_sq.clone()))
+        (pe, me, ve), (pg, mg, vg) = out
+        e_p = max(rel_err(a, b) for a, b in zip(pg, pe))
+        e_m, e_v = rel_err(mg, me), rel_err(vg, ve)
+        report("graphed_vs_eager", act, "param=%.1e exp_avg=%.1e exp_avg_sq=%.1e" % (e_p, e_m, e_v))
+        # same kernels, same inputs, same order: only the atomics' summation order differs
+        assert e_p < tol and e_m < 1e-3 and e_v < 1e-3, (act, e_p, e_m, e_v)

@@ -160,55 +160,9 @@ def test_pair_pad_unpad_roundtrip(L):
         assert torch.equal(ops.pair_unpad(xp, L, torch.float32).cpu(), x.to(dt).float())
 
 
-@pytest.mark.parametrize("L", [5, 66, 130, 258])
-def test_keep_bits_equal_the_in_kernel_mask(L):
-    """mmdti_pair_attn_keep_bits (bit-packed, shared by forward and backward) == the mask the kernels hash themselves"""
-    from mmdti_b200 import _lib, ops
-    from mmdti_b200._lib import call, f32, i32, stream_ptr, u64
-    B, H, p, seed = 2, 3, 0.3, 1234567
-    nw = _lib.lib().mmdti_pair_keep_words(L)
-    bits = torch.empty(B * H * L, nw, device="cuda", dtype=torch.int32)
-    call("mmdti_pair_attn_keep_bits", bits, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
-    dense = ops.attn_dropout_mask(B, H, L, p, seed)                      # (B,H,L,L) bool
-    cols = torch.arange(L, device="cuda")
-    words = bits.view(B, H, L, nw).long() & 0xFFFFFFFF
-    got = ((words[..., cols // 32] >> (cols % 32)) & 1).bool()
-    assert torch.equal(got, dense)
-
-
-@pytest.mark.parametrize("L", [66, 100, 258])
-def test_k2_with_keep_bits_is_bit_identical(L):
-    from mmdti_b200 import _lib, ops
-    from mmdti_b200._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
-    B, H, D, p, seed = 2, 64, 512, 0.1, 99
-    Lp = ops.pair_ld(L)
-    g = torch.Generator(device="cuda").manual_seed(L)
-    qkv = (torch.randn(B * L, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
-    pair = torch.randn(B, H, L, Lp, device="cuda", generator=g).bfloat16()
-    pair[..., L:] = float("-inf")
-    d_o = (torch.randn(B * L, D, device="cuda", generator=g) * 0.1).bfloat16()
-    dpo = (torch.randn(B, H, L, Lp, device="cuda", generator=g) * 0.01).bfloat16()
-    dpo[..., L:] = 0
-    keep = torch.empty(B * H * L, _lib.lib().mmdti_pair_keep_words(L), device="cuda", dtype=torch.int32)
-    call("mmdti_pair_attn_keep_bits", keep, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
-    code = DTYPE_CODE[torch.bfloat16]
-    res = []
-    for kb in (None, keep):
-        pout, o = torch.empty_like(pair), torch.empty(B * L, D, device="cuda", dtype=torch.bfloat16)
-        call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H),
-             i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(code), kb, stream_ptr())
-        dpi, dqkv = torch.empty_like(pair), torch.empty_like(qkv)
-        call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pout, o, d_o, i64(D), dpo, dpi,
-             dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L), f32(8 ** -0.5), f32(p), u64(seed),
-             i32(code), i32(code), i32(code), kb, stream_ptr())
-        res.append((o, pout, dpi[..., :L], dqkv))
-    for a, b in zip(*res):
-        assert torch.equal(a, b)
-
-
 @pytest.mark.parametrize("pdt", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("L,keep_bits", [(137, False), (150, False), (200, True), (258, False), (258, True), (264, False)])
-def test_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
+@pytest.mark.parametrize("L", [137, 150, 200, 258, 264])
+def test_column_split_matches_row_split(L, pdt, monkeypatch):
     """L > 136: the column-split forward (MMDTI_K2_FWD_CS=1) and backward (4 warps per 16-row block, row max / sum / dQ exchanged through shared memory,
     MMDTI_K2_BWD_CS=1) against the one-warp-per-row-block form on the same inputs, dropout on.  Both draw the same mask;
     the only differences are fp32 summation orders (row sums, dQ) ahead of the rounding to the storage types."""
@@ -225,17 +179,13 @@ def test_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
     dpo = (torch.randn(B, H, L, Lp, device="cuda", generator=g) * 0.01).to(pdt)
     dpo[..., L:] = 0
     dpo[1, :, :, L - 3:L] = 0
-    keep = None
-    if keep_bits:
-        keep = torch.empty(B * H * L, _lib.lib().mmdti_pair_keep_words(L), device="cuda", dtype=torch.int32)
-        call("mmdti_pair_attn_keep_bits", keep, i32(B), i32(H), i32(L), f32(p), u64(seed), stream_ptr())
     code, pcode = DTYPE_CODE[torch.bfloat16], DTYPE_CODE[pdt]
     fw = []
     for cs in ("1", "0"):                 # the forward has the same two forms (MMDTI_K2_FWD_CS); the row-split outputs feed the backward
         monkeypatch.setenv("MMDTI_K2_FWD_CS", cs)
         pout, o = torch.full_like(pair, 7.0), torch.full((B * L, D), 7.0, device="cuda", dtype=torch.bfloat16)
         call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H),
-             i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(pcode), keep, stream_ptr())
+             i32(L), f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(pcode), stream_ptr())
         torch.cuda.synchronize()
         fw.append((pout, o))
     assert torch.equal(fw[0][0][..., :L], fw[1][0][..., :L])              # P' = scale * QK^T + P: same operations, same bits
@@ -249,7 +199,7 @@ def test_column_split_matches_row_split(L, keep_bits, pdt, monkeypatch):
         for dpo_ in (dpo, None):                                            # with and without an incoming pair gradient
             call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pout, o, d_o, i64(D), dpo_, dpi,
                  dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L), f32(8 ** -0.5), f32(p),
-                 u64(seed), i32(code), i32(pcode), i32(pcode), keep, stream_ptr())
+                 u64(seed), i32(code), i32(pcode), i32(pcode), stream_ptr())
             torch.cuda.synchronize()
             res.append((dpi[..., :L].float().clone(), dqkv.float().clone()))
     for (dp0, dq0), (dp1, dq1) in ((res[0], res[2]), (res[1], res[3])):

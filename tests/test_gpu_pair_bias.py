@@ -43,6 +43,56 @@ def test_pair_bias_golden(tag, act, pair, report):
         assert max(e_g.values()) < 6e-2, e_g
 
 
+@pytest.mark.parametrize("B,n_atoms", [(128, 64), (8, 256)])
+@pytest.mark.parametrize("tag", ["init", "pre"])
+def test_pair_bias_bench_sizes(B, n_atoms, tag, report):
+    """K1 forward + backward at the sizes bench.py runs (config 2: 128 x 66^2 = 557 568 pairs; config 4 shape:
+    8 x 258^2 = 532 512 pairs), so that the persistent multi-tile loops of csrc/pair_bias.cu (64 pairs per tile,
+    grid <= 444 => ~20 tiles per CTA) and csrc/pair_bias_bwd.cu (128 pairs per tile, grid <= 148 => ~29 tiles per CTA,
+    dW1 / dW2 register accumulators carried across all of them) iterate many times under a checker.
+    Truth = oracle/restate.pair_bias in float64 (``wide=True``), evaluated molecule-chunk by molecule-chunk."""
+    import mmdti_b200
+    from mmdti_b200 import ops
+    from mmdti_b200.data import synthetic_molecules
+    from tolerances import TOL
+    g = load_golden("pair_bias_" + tag)
+    dev = "cuda"
+    tokens, dist, et, _ = synthetic_molecules(B, n_atoms, seed=77, ragged=True)
+    L = tokens.shape[1]
+    pad = tokens.eq(0)
+    H = 64
+    up = torch.randn(B, H, L, L, generator=torch.Generator().manual_seed(3))
+    p64 = {k[2:]: v.double().requires_grad_(True) for k, v in g.items() if k.startswith("w.")}
+    want = torch.empty(B, H, L, L)
+    step = max(1, 40000 // (L * L))
+    for b0 in range(0, B, step):
+        sl = slice(b0, min(B, b0 + step))
+        o = restate.pair_bias(dist[sl].double(), et[sl], p64, wide=True).view(-1, H, L, L)
+        want[sl] = o.detach().float()
+        (o * up[sl].double().masked_fill(pad[sl][:, None, None, :], 0.0)).sum().backward()
+    want.masked_fill_(pad[:, None, None, :], float("-inf"))
+    for act, pair in (("fp32", "fp32"), ("bf16", "bf16")):
+        with mmdti_b200.precision(act=act, pair=pair):
+            gbf, proj = _mods(g, dev)
+            pj = proj
+            out = ops.pair_bias(dist.to(dev), et.to(dev), gbf.means.weight, gbf.stds.weight, gbf.mul.weight, gbf.bias.weight,
+                                pj.linear1.weight, pj.linear1.bias, pj.linear2.weight, pj.linear2.bias, key_pad=pad.to(dev))
+            assert out.shape == (B, H, L, ops.pair_ld(L))
+            # padding columns of the layout hold -inf and receive no gradient
+            upp = torch.zeros_like(out, dtype=torch.float32)
+            upp[..., :L] = up.to(dev)
+            (out.float().masked_fill(torch.isinf(out), 0.0) * upp).sum().backward()
+        got = out[..., :L].float().cpu()
+        e_out = rel_err(got, want)
+        grads = {"gbf." + k: v.grad for k, v in gbf.named_parameters()}
+        grads.update({"gbf_proj." + k: v.grad for k, v in proj.named_parameters()})
+        e_g = {k: norm_err(grads[k].float().cpu().view(-1), p64[k].grad.float().view(-1)) for k in grads}
+        report("pair_bias_bench_size", "B=%d L=%d" % (B, L), tag, act, "out=%.2e" % e_out, {k: "%.1e" % v for k, v in e_g.items()})
+        t = TOL["k1." + act]
+        assert e_out < t["out"], e_out
+        assert max(e_g.values()) < t["grad"], e_g
+
+
 def test_pair_bias_keypad_fused_and_mask_fill(report):
     """-inf merge of the key-padding mask: fused in K1 == the in-place kernel == the oracle's
     masked_fill_ (models/transformers.py:122-132), bit-exact pattern."""

@@ -186,14 +186,13 @@ def test_padding_helpers_match_the_reference_rules():
 
 def test_pair_tensor_leading_dimension_rule():
     """Lp = 8 * NKB >= L with NKB odd (16-byte rows; Lp = 8 mod 16 keeps the slab bank-conflict-free),
-    NKB from the instantiated set {3, 5, 9, 13, 17, 25, 33}; L > 264 is refused (-1), never truncated; keep-mask words
-    per row = ceil(Lp / 32).  Host arithmetic of the C ABI -- no device needed."""
+    NKB from the instantiated set {3, 5, 9, 13, 17, 25, 33}; L > 264 is refused (-1), never truncated.
+    Host arithmetic of the C ABI -- no device needed."""
     lib = _lib.lib()
     buckets = [8 * n for n in (3, 5, 9, 13, 17, 25, 33)]
     for L in range(1, 265):
         lp = lib.mmdti_pair_ld(L)
         assert lp == min(b for b in buckets if b >= L) and lp % 16 == 8, (L, lp)
-        assert lib.mmdti_pair_keep_words(L) == (lp + 31) // 32
     assert lib.mmdti_pair_ld(66) == 72 and lib.mmdti_pair_ld(258) == 264
     for L in (265, 512):
-        assert lib.mmdti_pair_ld(L) == -1 and lib.mmdti_pair_keep_words(L) == -1
+        assert lib.mmdti_pair_ld(L) == -1
