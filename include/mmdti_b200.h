@@ -152,6 +152,43 @@ int mmdti_pair_attn_bwd(const void* q, const void* k, const void* v, int64_t ldq
 int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, float dropout_p, uint64_t seed,
                                  void* stream);
 
+/* ---------------------------------------------------------------- dense projections of the encoder layer (tcgen05)
+ * The four linear layers of Uni-Core's TransformerEncoderLayer (reference call sites models/transformers.py:82-91,
+ * 136-139: in_proj / out_proj inside SelfMultiheadAttention, fc1 / fc2) with the layer's elementwise work fused into
+ * the GEMM epilogues.  All matrices bf16 row-major with row strides ld* (elements, multiples of 8), fp32 accumulation
+ * in TMEM; M = tokens (B*L), N = out features, K = in features of the linear layer in EVERY call below.  W is the
+ * nn.Linear weight (N, K).  Replaces torch.addmm / torch.mm + mmdti_gelu_fwd / mmdti_dropres_layernorm_fwd /
+ * mmdti_gelu_bwd / mmdti_layernorm_bwd_dropout / mmdti_dropout_bwd around them. */
+
+/* Y = X W^T + bias (bias (N) bf16, may be NULL).                                        [in_proj forward] */
+int mmdti_gemm_bias(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* Y,
+                    int64_t ldy, int M, int N, int K, void* stream);
+/* Z = X W^T + bias;  U = gelu(Z) (exact-erf GELU of the stored, bf16-rounded Z).         [fc1 forward] */
+int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* Z,
+                         int64_t ldz, void* U, int64_t ldu, int M, int N, int K, void* stream);
+/* xo = res + dropout(X W^T + bias) (fp32, dense (M,N));  Y = LayerNorm(xo; ln_w, ln_b, eps) (bf16, dense (M,N)),
+ * mean/rstd (M) saved.  ln_w == NULL: no LayerNorm (Y/mean/rstd unused).  N <= 512 (whole rows per CTA pair).
+ * Dropout mask = the flat-tensor mask of mmdti_dropout_mask(seed) over (M*N).           [out_proj / fc2 forward] */
+int mmdti_gemm_dropres_ln(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, const float* res,
+                          float* xo, const float* ln_w, const float* ln_b, void* Y, float* mean, float* rstd,
+                          int M, int N, int K, float eps, float dropout_p, uint64_t seed, void* stream);
+/* dX (M,K) = dY (M,N) W (N,K).                                                          [out_proj backward] */
+int mmdti_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX, int64_t lddx, int M, int N,
+                     int K, void* stream);
+/* dZ (M,K) = (dY W) * gelu'(Z);  dbias (K) += column sums of the stored dZ.             [fc2 backward -> fc1 output] */
+int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* Z, int64_t ldz,
+                          void* dZ, int64_t lddz, float* dbias, int M, int N, int K, void* stream);
+/* dh = dY W (M,K), K <= 512: gradient at the output of LayerNorm(x; ln_w) whose statistics are mean/rstd;
+ * dx = dx_add + LayerNorm'(dh) (fp32 dense (M,K); dx_add may be NULL);  da = dropout'(dx) (bf16 dense (M,K), mask of
+ * `seed` over (M*K));  dw (K) += sum_rows dh*xhat, db (K) += sum_rows dh, dbias (K) += sum_rows da.
+ *                                                                                        [fc1 / in_proj backward] */
+int mmdti_gemm_dgrad_lnbwd(const void* dY, int64_t lddy, const void* W, int64_t ldw, const float* x, const float* mean,
+                           const float* rstd, const float* ln_w, const float* dx_add, float* dx, float* dw, float* db,
+                           void* da, float* dbias, int M, int N, int K, float dropout_p, uint64_t seed, void* stream);
+/* dW (N,K) fp32 (row stride lddw) = dY^T X, or += when accumulate != 0.                 [weight gradients] */
+int mmdti_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw, int M, int N,
+                     int K, int accumulate, void* stream);
+
 /* padded (B,H,L,Lp) pair_dtype -> dense (B,L,L,H) f32 "pair" and "delta pair" outputs of
  * TransformerEncoderWithPair.forward (models/transformers.py:163-172): pair_last permuted, and
  * delta = pair_last - pair_first with padded key columns (where pair_last is -inf) set to 0. */

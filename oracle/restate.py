@@ -183,14 +183,16 @@ def encoder_with_pair(emb, attn_mask, padding_mask, p, heads, n_layers, prefix="
     return x, pair, delta, x_norm, delta_norm
 
 
-def unimol_encoder(src_tokens, src_distance, src_edge_type, p, heads=64, n_layers=15, pad_idx=0):
+def unimol_encoder(src_tokens, src_distance, src_edge_type, p, heads=64, n_layers=15, pad_idx=0, wide=False):
     """UnimolEncoder.forward (models/encoder.py:458-502) == models/mm_model.py:545-559:
-    padding mask -> embed -> pair bias -> encoder -> all_repr (B,L,D)."""
+    padding mask -> embed -> pair bias -> encoder -> all_repr (B,L,D).
+    wide=True (float64 parameters and distances): the same expressions evaluated in float64 throughout, used as a
+    higher-precision truth when the fp32 reference's own round-off is what limits a comparison."""
     padding_mask = src_tokens.eq(pad_idx)
     if not padding_mask.any():
         padding_mask = None
     x = F.embedding(src_tokens, p["embed_tokens.weight"], padding_idx=pad_idx)
-    bias = pair_bias(src_distance, src_edge_type, p)
+    bias = pair_bias(src_distance, src_edge_type, p, wide=wide)
     return encoder_with_pair(x, bias, padding_mask, p, heads, n_layers)[0]
 
 

