@@ -34,7 +34,7 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int NSTAGE = 4;
+constexpr int MAX_STAGE = 4;      // ring stages: 4 (plain epilogues) or 3 (epilogues that stream row operands through input slabs)
 constexpr int A_BYTES = BM * BK * 2;             // 16 KB
 constexpr int B_BYTES = BN * BK * 2;             // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -123,39 +123,47 @@ __device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
     return v[0];
 }
 
-__device__ __forceinline__ void load_bf16x8(const bf16* p, float (&f)[8]) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-__device__ __forceinline__ void store_bf16x8(bf16* p, const float (&f)[8]) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-}
 __device__ __forceinline__ float round_bf16(float x) { return __uint_as_float(pack_bf16(x, 0.f) << 16); }
 
-struct Smem {
+constexpr int SLAB_BYTES = BM * 64;              // staging slab: 128 rows x 64 bytes (32 bf16 / 16 fp32 columns), 64-byte swizzle
+
+// epilogues that read a per-row operand (residual, z, dx_add) stream it through TMA input slabs; they run a 3-stage ring
+__host__ __device__ constexpr bool epi_has_input(int epi) { return epi == EPI_GELU_BWD || epi == EPI_DROPRES_LN || epi == EPI_LNBWD_DROP; }
+__host__ __device__ constexpr int epi_stages(int epi) { return epi_has_input(epi) ? 3 : 4; }
+
+template <int NST>
+struct SmemT {
     static constexpr uint32_t stages = 0;
-    static constexpr uint32_t bars = NSTAGE * STAGE_BYTES;            // full[4] empty[4] tfull[2] tempty[2] xbar[2], tmem slot
-    static constexpr uint32_t cs = bars + 128;                        // column-sum scratch: 3 x 256 floats
+    static constexpr uint32_t ostage = NST * STAGE_BYTES;             // output slab, one per column half
+    static constexpr uint32_t istage = ostage + 2 * SLAB_BYTES;       // input slabs, two per column half (NST == 3 only)
+    static constexpr uint32_t bars = istage + (NST == 3 ? 4 * SLAB_BYTES : 0);      // mbarriers + tmem slot (256 bytes)
+    static constexpr uint32_t cs = bars + 256;                        // column-sum scratch: 3 x 256 floats
     static constexpr uint32_t xchg = cs + 3 * BN * 4;                 // [2 parities][4 slots][128 rows] float2
-    static constexpr uint32_t total = xchg + 2 * 4 * BM * 8;
+    static constexpr uint32_t vec = xchg + 2 * 4 * BM * 8;            // per-tile column vectors: [2 tiles][bias | ln_w | ln_b][256]
+    static constexpr uint32_t total = vec + 2 * 3 * BN * 4;
 };
 
 template <int AMN, int BMN, int EPI, int NCTA>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1)      // 10 warps: one scheduler holds 3 of them => 168 registers per thread
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
+               const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmI0, const __grid_constant__ CUtensorMap tmI1,
+               const GemmParams p) {
+    constexpr int NSTAGE = epi_stages(EPI);
+    using Smem = SmemT<NSTAGE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
-    uint64_t* full = bars;              // [NSTAGE]
-    uint64_t* empty = bars + NSTAGE;    // [NSTAGE]
-    uint64_t* tfull = bars + 2 * NSTAGE;      // [2]
+    uint64_t* full = bars;              // [MAX_STAGE]
+    uint64_t* empty = bars + MAX_STAGE; // [MAX_STAGE]
+    uint64_t* tfull = bars + 2 * MAX_STAGE;   // [2]
     uint64_t* tempty = tfull + 2;             // [2]
     uint64_t* xbar = tempty + 2;              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 2);
+    uint64_t* inbar = xbar + 2;               // [2 halves][2 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 4);
     float* s_cs = reinterpret_cast<float*>(smem + Smem::cs);
     float2* s_x = reinterpret_cast<float2*>(smem + Smem::xchg);
+    float* s_vec = reinterpret_cast<float*>(smem + Smem::vec);
     // the LayerNorm-backward epilogue parks two intermediates per element in TMEM: accumulator not double-buffered there
     constexpr bool DOUBLE_ACC = EPI != EPI_LNBWD_DROP;
 
@@ -168,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tempty[i], NUM_EPI_THREADS);
             mbar_init(&xbar[i], NCTA * NUM_EPI_THREADS);
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&inbar[i], 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < 3 * BN; i += NUM_THREADS) s_cs[i] = 0.f;
@@ -267,102 +276,162 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ================================================= epilogue warps
+        // Latency discipline (two warps per scheduler, nothing else to hide behind): per-column vectors (bias, LayerNorm
+        // weight / bias) are fetched BEFORE the wait for the accumulator and staged in shared memory (broadcast reads);
+        // per-row operands (residual, z, dx_add) are register-prefetched one 32-column chunk ahead.
         const int ew = warp - 2;
         const int quad = warp & 3, half = ew >> 2;
         const int et = ew * 32 + lane;                    // 0..255
         const int r = quad * 32 + lane;                   // accumulator row of this thread inside the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         constexpr int HC = BN / 2;                        // columns per epilogue thread
+        constexpr int NCH = HC / 32;                      // 32-column chunks per thread
+        constexpr bool HAS_VEC = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_DROPRES_LN || EPI == EPI_LNBWD_DROP;
         uint32_t key = 0;
         if (EPI == EPI_DROPRES_LN || EPI == EPI_LNBWD_DROP) key = p.thresh16 ? rng_effective_key(p.key, p.seed_off) : 0u;
+        // Coalesced output: the 128 threads of a column half write their 64-byte row segments into a swizzled shared-memory
+        // slab (conflict-free), one elected thread hands the slab to the TMA (tile store, or fp32 reduce-add for the
+        // split wgrad); rows / columns beyond the matrix are clipped by the TMA.
+        unsigned char* slab = smem + Smem::ostage + half * SLAB_BYTES;
+        const bool slab_leader = (et & 127) == 0;
+        auto half_bar = [&]() { asm volatile("bar.sync %0, 128;\n" ::"r"(2 + half) : "memory"); };
+        auto slab_store = [&](const CUtensorMap* tm, int col, int row0, const uint4 (&d)[4], bool reduce) {
+            if (slab_leader) bulk_wait_read<0>();         // the previous store has drained the slab
+            half_bar();
+            unsigned char* rowp = slab + r * 64;
+            const int sw = (r >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = d[j];
+            fence_proxy_async();
+            half_bar();
+            if (slab_leader) {
+                if (reduce) tma_reduce_add_2d(tm, slab, col, row0);
+                else tma_store_2d(tm, slab, col, row0);
+                bulk_commit();
+            }
+        };
+        // input slabs: the leader of a column half issues TMA loads (two buffers, one mbarrier each); every thread waits
+        // for the slab and reads its own 64-byte row segment (swizzled: conflict-free).  Counters are uniform per half.
+        unsigned char* islab = smem + Smem::istage + half * 2 * SLAB_BYTES;
+        uint64_t* ibar = inbar + half * 2;
+        uint32_t in_issued = 0, in_read = 0;              // in_issued is only meaningful in the leader
+        auto in_issue = [&](const CUtensorMap* tm, int col, int row0) {
+            const int b = in_issued & 1;
+            mbar_arrive_expect_tx(&ibar[b], SLAB_BYTES);
+            tma_load_2d(islab + b * SLAB_BYTES, tm, col, row0, &ibar[b]);
+            ++in_issued;
+        };
+        auto in_take = [&](uint4 (&d)[4]) {
+            const int b = in_read & 1;
+            mbar_wait_g(&ibar[b], (in_read >> 1) & 1);
+            const unsigned char* rowp = islab + b * SLAB_BYTES + r * 64;
+            const int sw = (r >> 1) & 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = *reinterpret_cast<const uint4*>(rowp + ((j ^ sw) << 4));
+            ++in_read;
+        };
         int it = 0;
         for (int item = item0; item < n_items; item += item_step, ++it) {
             int m_blk, n_blk, kc0, kc1;
             decode(item, m_blk, n_blk, kc0, kc1);
             const int buf = DOUBLE_ACC ? (it & 1) : 0;
             const int use = DOUBLE_ACC ? (it >> 1) : it;
-            const long long row = (long long)m_blk * BM + r;
+            const int row0 = m_blk * BM;
+            const long long row = (long long)row0 + r;
             const bool row_ok = row < p.M;
             const int n0 = n_blk * BN;
             const uint32_t acc_addr = lane_addr + buf * BN;
+            const int cb = half * HC;                     // first column of this thread inside the tile
+            float* sv = s_vec + (it & 1) * (3 * BN);      // column vectors of this tile: [0] bias, [1] ln_w, [2] ln_b
+            float pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
+            if (HAS_VEC && n0 + et < p.N) {
+                if (EPI != EPI_LNBWD_DROP) pv0 = __bfloat162float(p.bias[n0 + et]);
+                if (EPI == EPI_LNBWD_DROP || (EPI == EPI_DROPRES_LN && p.ln_w)) pv1 = __ldg(p.ln_w + n0 + et);
+                if (EPI == EPI_DROPRES_LN && p.ln_w) pv2 = __ldg(p.ln_b + n0 + et);
+            }
+            // per-row operand of the epilogue (residual / z / x): 64-byte slabs by TMA, two in flight per column half
+            constexpr int N_IN = EPI == EPI_GELU_BWD ? NCH : 2 * NCH;       // input slabs per tile and half: 32 bf16 or 16 fp32 columns each
+            constexpr int IN_W = EPI == EPI_GELU_BWD ? 32 : 16;
+            if (epi_has_input(EPI) && slab_leader) {
+                in_issue(&tmI0, n0 + cb, row0);
+                in_issue(&tmI0, n0 + cb + IN_W, row0);
+            }
+            float mu = 0.f, rs = 0.f;
+            if (EPI == EPI_LNBWD_DROP && row_ok) { mu = p.mean[row]; rs = p.rstd[row]; }
+
             mbar_wait_g(&tfull[buf], use & 1);
             tc_fence_after();
+            if (HAS_VEC) {
+                sv[et] = pv0; sv[BN + et] = pv1; sv[2 * BN + et] = pv2;
+                epi_bar();
+            }
 
             if constexpr (EPI == EPI_STORE || EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
-#pragma unroll 1
-                for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int c0 = cb + ci * 32;
                     uint32_t v[32];
                     tc_ld32(acc_addr + c0, v);
-                    if (row_ok) {
+                    uint4 zq[4], uq[4];
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            const int col = n0 + c0 + g8 * 8;
-                            if (col < p.N) {
-                                float f[8];
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        float f[8];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g8 * 8 + e]);
-                                if (EPI != EPI_STORE) {
-                                    float b8[8];
-                                    load_bf16x8(p.bias + col, b8);
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g8 * 8 + e]);
+                        if (EPI != EPI_STORE) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(sv + c0 + g8 * 8), b1 = *reinterpret_cast<const float4*>(sv + c0 + g8 * 8 + 4);
+                            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                        }
+                        zq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        if (EPI == EPI_BIAS_GELU) {
+                            // u = gelu(z) of the ROUNDED z, the value the backward reads back
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] += b8[e];
-                                }
-                                store_bf16x8(static_cast<bf16*>(p.out0) + row * p.ld0 + col, f);
-                                if (EPI == EPI_BIAS_GELU) {
-                                    // u = gelu(z) of the ROUNDED z, the value the backward reads back
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] = gelu_fast_val(round_bf16(f[e]));
-                                    store_bf16x8(static_cast<bf16*>(p.out1) + row * p.ld1 + col, f);
-                                }
-                            }
+                            for (int e = 0; e < 8; ++e) f[e] = gelu_fast_val(round_bf16(f[e]));
+                            uq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
                     }
+                    slab_store(&tmO0, n0 + c0, row0, zq, false);
+                    if (EPI == EPI_BIAS_GELU) slab_store(&tmO1, n0 + c0, row0, uq, false);
                 }
             } else if constexpr (EPI == EPI_WGRAD) {
-#pragma unroll 1
-                for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
+#pragma unroll 2
+                for (int c0 = cb; c0 < cb + HC; c0 += 16) {
                     uint32_t v[32];
-                    tc_ld32(acc_addr + c0, v);
-                    if (row_ok) {
-                        float* dst = static_cast<float*>(p.out0) + row * p.ld0 + n0 + c0;
+                    tc_ld16(acc_addr + c0, v);
+                    uint4 q[4];
 #pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4) {
-                            if (n0 + c0 + g4 * 4 < p.N) {
-                                const float a = __uint_as_float(v[g4 * 4]), b = __uint_as_float(v[g4 * 4 + 1]);
-                                const float c = __uint_as_float(v[g4 * 4 + 2]), d = __uint_as_float(v[g4 * 4 + 3]);
-                                if (p.use_atomics) red_add_v4(dst + g4 * 4, a, b, c, d);
-                                else *reinterpret_cast<float4*>(dst + g4 * 4) = make_float4(a, b, c, d);
-                            }
-                        }
-                    }
+                    for (int j = 0; j < 4; ++j) q[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    slab_store(&tmO0, n0 + c0, row0, q, p.use_atomics != 0);
                 }
             } else if constexpr (EPI == EPI_GELU_BWD) {
-#pragma unroll 1
-                for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int c0 = cb + ci * 32;
+                    uint4 zq[4];
+                    in_take(zq);
+                    half_bar();                                       // everybody has read the slab: refill it
+                    if (slab_leader && ci + 2 < N_IN) in_issue(&tmI0, n0 + c0 + 64, row0);
                     uint32_t v[32];
                     tc_ld32(acc_addr + c0, v);
                     float cs[32];
+                    uint4 dq[4];
 #pragma unroll
                     for (int g8 = 0; g8 < 4; ++g8) {
-                        const int col = n0 + c0 + g8 * 8;
+                        const float2 z01 = unpack_bf16(zq[g8].x), z23 = unpack_bf16(zq[g8].y), z45 = unpack_bf16(zq[g8].z), z67 = unpack_bf16(zq[g8].w);
+                        const float z8[8] = {z01.x, z01.y, z23.x, z23.y, z45.x, z45.y, z67.x, z67.y};
                         float f[8];
-                        if (row_ok && col < p.N) {
-                            float z8[8];
-                            load_bf16x8(static_cast<const bf16*>(p.aux0) + row * p.ldaux0 + col, z8);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                float val, grad;
-                                gelu_fast_both(z8[e], val, grad);
-                                f[e] = __uint_as_float(v[g8 * 8 + e]) * grad;
-                            }
-                            store_bf16x8(static_cast<bf16*>(p.out0) + row * p.ld0 + col, f);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) cs[g8 * 8 + e] = round_bf16(f[e]);      // sum what was stored
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) cs[g8 * 8 + e] = 0.f;
+                        for (int e = 0; e < 8; ++e) {
+                            float val, grad;
+                            gelu_fast_both(z8[e], val, grad);
+                            f[e] = __uint_as_float(v[g8 * 8 + e]) * grad;
                         }
+                        dq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                        const bool ok = row_ok && n0 + c0 + g8 * 8 < p.N;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) cs[g8 * 8 + e] = ok ? round_bf16(f[e]) : 0.f;      // sum what is stored
                     }
+                    slab_store(&tmO0, n0 + c0, row0, dq, false);
                     const float tot = warp_col_reduce32(cs, lane);
                     atomicAdd(&s_cs[c0 + lane], tot);
                 }
@@ -373,39 +442,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else if constexpr (EPI == EPI_DROPRES_LN) {
                 const int xpar = it & 1;
                 float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-                for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
+#pragma unroll 2
+                for (int ci = 0; ci < 2 * NCH; ++ci) {
+                    const int c0 = cb + ci * 16;
+                    uint4 rq[4];
+                    in_take(rq);                                      // 16 fp32 of the residual row
+                    half_bar();
+                    if (slab_leader && ci + 2 < N_IN) in_issue(&tmI0, n0 + c0 + 32, row0);
                     uint32_t v[32];
-                    tc_ld32(acc_addr + c0, v);
+                    tc_ld16(acc_addr + c0, v);
+                    uint4 oq[4];
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
+                    for (int g4 = 0; g4 < 4; ++g4) {
                         const int col = n0 + c0 + g4 * 4;
-                        float o[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (row_ok && col < p.N) {
-                            const uint2 bu = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
-                            const float2 b01 = unpack_bf16(bu.x), b23 = unpack_bf16(bu.y);
-                            float a[4] = {__uint_as_float(v[g4 * 4]) + b01.x, __uint_as_float(v[g4 * 4 + 1]) + b01.y,
-                                          __uint_as_float(v[g4 * 4 + 2]) + b23.x, __uint_as_float(v[g4 * 4 + 3]) + b23.y};
+                        const float4 b4 = *reinterpret_cast<const float4*>(sv + c0 + g4 * 4);
+                        float a[4] = {__uint_as_float(v[g4 * 4]) + b4.x, __uint_as_float(v[g4 * 4 + 1]) + b4.y,
+                                      __uint_as_float(v[g4 * 4 + 2]) + b4.z, __uint_as_float(v[g4 * 4 + 3]) + b4.w};
+                        if (p.thresh16) {
                             const long long idx = row * p.N + col;
-                            if (p.thresh16) {
-                                const uint32_t h0 = ew_bits(key, (unsigned long long)idx), h1 = ew_bits(key, (unsigned long long)idx + 2);
-                                a[0] = rng_keep(h0, 0, p.thresh16) ? a[0] * p.keep_scale : 0.f;
-                                a[1] = rng_keep(h0, 1, p.thresh16) ? a[1] * p.keep_scale : 0.f;
-                                a[2] = rng_keep(h1, 0, p.thresh16) ? a[2] * p.keep_scale : 0.f;
-                                a[3] = rng_keep(h1, 1, p.thresh16) ? a[3] * p.keep_scale : 0.f;
-                            }
-                            const float4 x4 = *reinterpret_cast<const float4*>(p.res + idx);
-                            o[0] = x4.x + a[0]; o[1] = x4.y + a[1]; o[2] = x4.z + a[2]; o[3] = x4.w + a[3];
-                            *reinterpret_cast<float4*>(p.xo + idx) = make_float4(o[0], o[1], o[2], o[3]);
+                            const uint32_t h0 = ew_bits(key, (unsigned long long)idx), h1 = ew_bits(key, (unsigned long long)idx + 2);
+                            a[0] = rng_keep(h0, 0, p.thresh16) ? a[0] * p.keep_scale : 0.f;
+                            a[1] = rng_keep(h0, 1, p.thresh16) ? a[1] * p.keep_scale : 0.f;
+                            a[2] = rng_keep(h1, 0, p.thresh16) ? a[2] * p.keep_scale : 0.f;
+                            a[3] = rng_keep(h1, 1, p.thresh16) ? a[3] * p.keep_scale : 0.f;
                         }
+                        float o[4] = {__uint_as_float(rq[g4].x) + a[0], __uint_as_float(rq[g4].y) + a[1], __uint_as_float(rq[g4].z) + a[2],
+                                      __uint_as_float(rq[g4].w) + a[3]};
+                        if (col >= p.N) { o[0] = o[1] = o[2] = o[3] = 0.f; }        // columns beyond the matrix do not enter the row statistics
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             s1 += o[e];
                             s2 = fmaf(o[e], o[e], s2);
                             v[g4 * 4 + e] = __float_as_uint(o[e]);
                         }
+                        oq[g4] = make_uint4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
                     }
-                    if (p.ln_w) tc_st32(acc_addr + c0, v);            // parked for the normalisation pass
+                    if (p.ln_w) tc_st16(acc_addr + c0, v);            // parked for the normalisation pass
+                    slab_store(&tmO0, n0 + c0, row0, oq, false);      // xo
                 }
                 if (p.ln_w) {
                     // per-row sums: 2 column halves x NCTA column blocks -> every CTA of the cluster gets all partials
@@ -427,82 +500,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         S2 += t.y;
                     }
                     const float inv_n = 1.f / (float)p.N;
-                    const float mu = S1 * inv_n;
-                    const float rs = rsqrtf(fmaxf(fmaf(-mu, mu, S2 * inv_n), 0.f) + p.eps);
-                    if (row_ok && slot == 0) { p.mean[row] = mu; p.rstd[row] = rs; }
-#pragma unroll 1
-                    for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
+                    const float mean = S1 * inv_n;
+                    const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, S2 * inv_n), 0.f) + p.eps);
+                    if (row_ok && slot == 0) { p.mean[row] = mean; p.rstd[row] = rstd; }
+#pragma unroll
+                    for (int ci = 0; ci < NCH; ++ci) {
+                        const int c0 = cb + ci * 32;
                         uint32_t v[32];
                         tc_ld32(acc_addr + c0, v);
-                        if (row_ok) {
+                        uint4 yq[4];
 #pragma unroll
-                            for (int g8 = 0; g8 < 4; ++g8) {
-                                const int col = n0 + c0 + g8 * 8;
-                                if (col < p.N) {
-                                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col)), w1 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col + 4));
-                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.ln_b + col + 4));
-                                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                                    float f[8];
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const float4 w0 = *reinterpret_cast<const float4*>(sv + BN + c0 + g8 * 8), w1 = *reinterpret_cast<const float4*>(sv + BN + c0 + g8 * 8 + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(sv + 2 * BN + c0 + g8 * 8), b1 = *reinterpret_cast<const float4*>(sv + 2 * BN + c0 + g8 * 8 + 4);
+                            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                            float f[8];
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] = fmaf((__uint_as_float(v[g8 * 8 + e]) - mu) * rs, wv[e], bv[e]);
-                                    store_bf16x8(static_cast<bf16*>(p.out0) + row * p.ld0 + col, f);
-                                }
-                            }
+                            for (int e = 0; e < 8; ++e) f[e] = fmaf((__uint_as_float(v[g8 * 8 + e]) - mean) * rstd, wv[e], bv[e]);
+                            yq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
+                        slab_store(&tmO1, n0 + c0, row0, yq, false);  // LayerNorm output
                     }
                 }
             } else if constexpr (EPI == EPI_LNBWD_DROP) {
+                // 16-column chunks: dy, xhat and the two column-sum operands stay in registers
+                constexpr int CW = 16, NCW = HC / CW;
                 const int xpar = it & 1;
                 const uint32_t scr_addr = lane_addr + BN;             // scratch columns [256, 512)
-                float mu = 0.f, rs = 0.f;
-                if (row_ok) { mu = p.mean[row]; rs = p.rstd[row]; }
-                float c1 = 0.f, c2 = 0.f;
-#pragma unroll 1
-                for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld32(acc_addr + c0, v);
-                    float xh[32], aw[32], ab[32];
+                const bool has_add = p.xo != nullptr;                 // dx_add present
+                // column sums of 16 columns over the warp's 32 rows: lane l < 16 ends with the total of column l
+                auto col_reduce16 = [&](float (&a)[16]) -> float {
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const int col = n0 + c0 + g4 * 4;
-                        if (row_ok && col < p.N) {
-                            const float4 x4 = *reinterpret_cast<const float4*>(p.res + row * p.N + col);
-                            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.ln_w + col));
-                            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                    for (int sft = 8; sft >= 1; sft >>= 1) {
+                        const bool up = (lane & sft) != 0;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int i = g4 * 4 + e;
-                                const float dy = __uint_as_float(v[i]);
-                                const float h = (xv[e] - mu) * rs;
-                                const float g = dy * wv[e];
-                                xh[i] = h;
-                                aw[i] = dy * h;                       // -> d ln_w
-                                ab[i] = dy;                           // -> d ln_b
-                                c1 += g;
-                                c2 = fmaf(g, h, c2);
-                                v[i] = __float_as_uint(g);            // the accumulator slot now holds g = dy * w
-                            }
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int i = g4 * 4 + e;
-                                xh[i] = 0.f; aw[i] = 0.f; ab[i] = 0.f;
-                                v[i] = 0u;
-                            }
+                        for (int i = 0; i < sft; ++i) {
+                            const float keep = up ? a[i + sft] : a[i];
+                            const float send = up ? a[i] : a[i + sft];
+                            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
                         }
                     }
-                    tc_st32(acc_addr + c0, v);
+                    return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);
+                };
+                float c1 = 0.f, c2 = 0.f;
+#pragma unroll 2
+                for (int ci = 0; ci < NCW; ++ci) {
+                    const int c0 = cb + ci * CW;
+                    uint4 xq[4];
+                    in_take(xq);                                      // 16 fp32 of the LayerNorm input row
+                    half_bar();
+                    if (slab_leader) {
+                        if (ci + 2 < NCW) in_issue(&tmI0, n0 + c0 + 2 * CW, row0);
+                        else if (has_add) in_issue(&tmI1, n0 + cb + (ci + 2 - NCW) * CW, row0);      // dx_add travels during the exchange
+                    }
+                    uint32_t v[32];
+                    tc_ld16(acc_addr + c0, v);
+                    float xh[CW], aw[CW], ab[CW];
+#pragma unroll
+                    for (int g4 = 0; g4 < CW / 4; ++g4) {
+                        const bool ok = row_ok && n0 + c0 + g4 * 4 < p.N;
+                        const float4 w4 = *reinterpret_cast<const float4*>(sv + BN + c0 + g4 * 4);
+                        const float xv[4] = {__uint_as_float(xq[g4].x), __uint_as_float(xq[g4].y), __uint_as_float(xq[g4].z), __uint_as_float(xq[g4].w)};
+                        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = g4 * 4 + e;
+                            const float dy = ok ? __uint_as_float(v[i]) : 0.f;
+                            const float h = ok ? (xv[e] - mu) * rs : 0.f;
+                            const float g = dy * wv[e];
+                            xh[i] = h;
+                            aw[i] = dy * h;                           // -> d ln_w
+                            ab[i] = dy;                               // -> d ln_b
+                            c1 += g;
+                            c2 = fmaf(g, h, c2);
+                            v[i] = __float_as_uint(g);                // the accumulator slot now holds g = dy * w
+                        }
+                    }
+                    tc_st16(acc_addr + c0, v);
                     {
                         uint32_t xu[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) xu[i] = __float_as_uint(xh[i]);
-                        tc_st32(scr_addr + c0, xu);
+                        for (int i = 0; i < CW; ++i) xu[i] = __float_as_uint(xh[i]);
+                        tc_st16(scr_addr + c0, xu);
                     }
-                    const float t_w = warp_col_reduce32(aw, lane);
-                    const float t_b = warp_col_reduce32(ab, lane);
-                    atomicAdd(&s_cs[c0 + lane], t_w);
-                    atomicAdd(&s_cs[BN + c0 + lane], t_b);
+                    const float t_w = col_reduce16(aw);
+                    const float t_b = col_reduce16(ab);
+                    if (lane < CW) {
+                        atomicAdd(&s_cs[c0 + lane], t_w);
+                        atomicAdd(&s_cs[BN + c0 + lane], t_b);
+                    }
                 }
                 // per-row c1, c2 across the column halves and the cluster
                 const int slot = (int)crank * 2 + half;
@@ -526,27 +613,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 C1 *= inv_n;
                 C2 *= inv_n;
 #pragma unroll 1
-                for (int c0 = half * HC; c0 < (half + 1) * HC; c0 += 32) {
-                    uint32_t gv[32], hv[32];
-                    tc_ld32(acc_addr + c0, gv);
-                    tc_ld32(scr_addr + c0, hv);
-                    float ad[32];
+                for (int cj = 0; cj < NCW / 2; ++cj) {
+                    uint4 daq[4];
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const int col = n0 + c0 + g4 * 4;
-                        if (row_ok && col < p.N) {
-                            const long long idx = row * p.N + col;
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int ci = cj * 2 + sub;
+                        const int c0 = cb + ci * CW;
+                        uint4 aq[4];
+                        if (has_add) {
+                            in_take(aq);
+                            half_bar();
+                            if (slab_leader && ci + 2 < NCW) in_issue(&tmI1, n0 + c0 + 2 * CW, row0);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) aq[j] = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        uint32_t gv[32], hv[32];
+                        tc_ld16(acc_addr + c0, gv);
+                        tc_ld16(scr_addr + c0, hv);
+                        float ad[CW];
+                        uint4 dxq[4];
+#pragma unroll
+                        for (int g4 = 0; g4 < CW / 4; ++g4) {
+                            const int col = n0 + c0 + g4 * 4;
+                            const bool ok = row_ok && col < p.N;
+                            const float addv[4] = {__uint_as_float(aq[g4].x), __uint_as_float(aq[g4].y), __uint_as_float(aq[g4].z), __uint_as_float(aq[g4].w)};
                             float o[4];
-                            float4 add4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (p.xo) add4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.xo) + idx);      // dx_add
-                            const float addv[4] = {add4.x, add4.y, add4.z, add4.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const int i = g4 * 4 + e;
                                 o[e] = addv[e] + rs * (__uint_as_float(gv[i]) - C1 - __uint_as_float(hv[i]) * C2);
                             }
-                            *reinterpret_cast<float4*>(static_cast<float*>(p.out1) + idx) = make_float4(o[0], o[1], o[2], o[3]);      // dx
+                            dxq[g4] = make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]));
                             if (p.thresh16) {
+                                const long long idx = row * p.N + col;
                                 const uint32_t h0 = ew_bits(key, (unsigned long long)idx), h1 = ew_bits(key, (unsigned long long)idx + 2);
                                 o[0] = rng_keep(h0, 0, p.thresh16) ? o[0] * p.keep_scale : 0.f;
                                 o[1] = rng_keep(h0, 1, p.thresh16) ? o[1] * p.keep_scale : 0.f;
@@ -554,16 +654,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 o[3] = rng_keep(h1, 1, p.thresh16) ? o[3] * p.keep_scale : 0.f;
                             }
                             const uint32_t u0 = pack_bf16(o[0], o[1]), u1 = pack_bf16(o[2], o[3]);
-                            *reinterpret_cast<uint2*>(static_cast<bf16*>(p.out0) + row * p.ld0 + col) = make_uint2(u0, u1);      // da
+                            if (g4 & 1) { daq[sub * 2 + (g4 >> 1)].z = u0; daq[sub * 2 + (g4 >> 1)].w = u1; }
+                            else { daq[sub * 2 + (g4 >> 1)].x = u0; daq[sub * 2 + (g4 >> 1)].y = u1; }
                             const float2 f0 = unpack_bf16(u0), f1 = unpack_bf16(u1);
-                            ad[g4 * 4] = f0.x; ad[g4 * 4 + 1] = f0.y; ad[g4 * 4 + 2] = f1.x; ad[g4 * 4 + 3] = f1.y;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) ad[g4 * 4 + e] = 0.f;
+                            ad[g4 * 4] = ok ? f0.x : 0.f; ad[g4 * 4 + 1] = ok ? f0.y : 0.f; ad[g4 * 4 + 2] = ok ? f1.x : 0.f; ad[g4 * 4 + 3] = ok ? f1.y : 0.f;
                         }
+                        slab_store(&tmO0, n0 + c0, row0, dxq, false);                 // dx (fp32, 16 columns)
+                        const float t_d = col_reduce16(ad);
+                        if (lane < CW) atomicAdd(&s_cs[2 * BN + c0 + lane], t_d);
                     }
-                    const float t_d = warp_col_reduce32(ad, lane);
-                    atomicAdd(&s_cs[2 * BN + c0 + lane], t_d);
+                    slab_store(&tmO1, n0 + cb + cj * 2 * CW, row0, daq, false);       // da (bf16, 32 columns)
                 }
                 epi_bar();
                 if (n0 + et < p.N) {
@@ -578,6 +678,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_arrive(&tempty[buf]);
         }
     }
+    if (warp >= 2 && ((threadIdx.x - 64) & 127) == 0) bulk_wait_all<0>();      // outstanding TMA stores of this column half
     __syncthreads();
     __syncwarp();
     if (NCTA > 1) cluster_sync_all();          // nobody leaves while the peer may still address this CTA's shared memory
@@ -606,8 +707,14 @@ inline void drop_params(float p, uint32_t& thresh16, float& keep_scale) {
 // that fused and unfused kernels draw the same mask for a given seed
 inline uint32_t ew_key(uint64_t seed) { return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x165667B1U)); }
 
+// output maps of the slab stores: bf16 (32 x 128) or fp32 (16 x 128) boxes, 64-byte swizzle
+int make_out_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, bool fp32) {
+    return make_map_2d(map, base, rows, cols, ld, fp32 ? 4 : 2, fp32 ? 16 : 32, BM, 64);
+}
+
 template <int AMN, int BMN, int EPI, int NCTA>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st, const CUtensorMap* tmO0 = nullptr,
+           const CUtensorMap* tmO1 = nullptr, const CUtensorMap* tmI0 = nullptr, const CUtensorMap* tmI1 = nullptr) {
     p.tiles_m = (p.M + BM - 1) / BM;
     p.tiles_n = (p.N + BN - 1) / BN;
     p.kchunks = (p.K + BK - 1) / BK;
@@ -617,7 +724,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaSt
     p.ksplit = (p.kchunks + p.kchunks_per_split - 1) / p.kchunks_per_split;
     if (p.ksplit > 1) p.use_atomics = 1;
     auto kern = gemm_tc_kernel<AMN, BMN, EPI, NCTA>;
-    const int smem_bytes = (int)Smem::total + 1024;
+    const int smem_bytes = (int)SmemT<epi_stages(EPI)>::total + 1024;
     MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int sms = num_sms();
     cudaLaunchConfig_t cfg = {};
@@ -641,7 +748,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaSt
         cfg.attrs = attr;
         cfg.numAttrs = 1;
     }
-    MMDTI_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+    const CUtensorMap& o0 = tmO0 ? *tmO0 : tmA;      // unused maps: any valid descriptor
+    const CUtensorMap& o1 = tmO1 ? *tmO1 : o0;
+    const CUtensorMap& i0 = tmI0 ? *tmI0 : tmA;
+    const CUtensorMap& i1 = tmI1 ? *tmI1 : i0;
+    MMDTI_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, o0, o1, i0, i1, p));
     return MMDTI_OK;
 }
 
@@ -672,11 +783,13 @@ extern "C" int mmdti_gemm_bias(const void* X, int64_t ldx, const void* W, int64_
     if (int rc = make_map_bf16(&tmB, W, N, K, ldw, BN)) return rc;
     GemmParams p = base_params(M, N, K);
     p.out0 = Y; p.ld0 = ldy; p.bias = static_cast<const bf16*>(bias);
+    CUtensorMap tmY;
+    if (int rc = make_out_map(&tmY, Y, M, N, ldy, false)) return rc;
     if (bias) {
         MMDTI_REQUIRE(mmdti_aligned(bias, 16), "gemm_bias: bias must be 16-byte aligned");
-        return launch<0, 0, EPI_BIAS, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+        return launch<0, 0, EPI_BIAS, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmY);
     }
-    return launch<0, 0, EPI_STORE, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    return launch<0, 0, EPI_STORE, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmY);
 }
 
 extern "C" int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* Z, int64_t ldz,
@@ -692,7 +805,10 @@ extern "C" int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, i
     if (int rc = make_map_bf16(&tmB, W, N, K, ldw, BN)) return rc;
     GemmParams p = base_params(M, N, K);
     p.out0 = Z; p.ld0 = ldz; p.out1 = U; p.ld1 = ldu; p.bias = static_cast<const bf16*>(bias);
-    return launch<0, 0, EPI_BIAS_GELU, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    CUtensorMap tmZ, tmU;
+    if (int rc = make_out_map(&tmZ, Z, M, N, ldz, false)) return rc;
+    if (int rc = make_out_map(&tmU, U, M, N, ldu, false)) return rc;
+    return launch<0, 0, EPI_BIAS_GELU, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmZ, &tmU);
 }
 
 extern "C" int mmdti_gemm_dropres_ln(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, const float* res,
@@ -715,8 +831,13 @@ extern "C" int mmdti_gemm_dropres_ln(const void* X, int64_t ldx, const void* W, 
     p.key = ew_key(seed);
     p.seed_off = mmdti_seed_offset_ptr();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (N > BN) return launch<0, 0, EPI_DROPRES_LN, 2>(tmA, tmB, p, st);
-    return launch<0, 0, EPI_DROPRES_LN, 1>(tmA, tmB, p, st);
+    CUtensorMap tmXo, tmY, tmRes;
+    if (int rc = make_out_map(&tmXo, xo, M, N, N, true)) return rc;
+    if (int rc = make_out_map(&tmRes, res, M, N, N, true)) return rc;
+    if (ln_w) { if (int rc = make_out_map(&tmY, Y, M, N, N, false)) return rc; }
+    else tmY = tmXo;
+    if (N > BN) return launch<0, 0, EPI_DROPRES_LN, 2>(tmA, tmB, p, st, &tmXo, &tmY, &tmRes);
+    return launch<0, 0, EPI_DROPRES_LN, 1>(tmA, tmB, p, st, &tmXo, &tmY, &tmRes);
 }
 
 extern "C" int mmdti_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX, int64_t lddx, int M, int N, int K,
@@ -730,7 +851,9 @@ extern "C" int mmdti_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int
     if (int rc = make_map_bf16(&tmB, W, N, K, ldw, BK)) return rc;           // B = W (N x K): rows = reduction, MN-major
     GemmParams p = base_params(M, K, N);
     p.out0 = dX; p.ld0 = lddx;
-    return launch<0, 1, EPI_STORE, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    CUtensorMap tmX;
+    if (int rc = make_out_map(&tmX, dX, M, K, lddx, false)) return rc;
+    return launch<0, 1, EPI_STORE, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmX);
 }
 
 extern "C" int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* Z, int64_t ldz, void* dZ,
@@ -745,7 +868,10 @@ extern "C" int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W
     if (int rc = make_map_bf16(&tmB, W, N, K, ldw, BK)) return rc;
     GemmParams p = base_params(M, K, N);
     p.out0 = dZ; p.ld0 = lddz; p.aux0 = Z; p.ldaux0 = ldz; p.colsum0 = dbias;
-    return launch<0, 1, EPI_GELU_BWD, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    CUtensorMap tmDZ, tmZ;
+    if (int rc = make_out_map(&tmDZ, dZ, M, K, lddz, false)) return rc;
+    if (int rc = make_out_map(&tmZ, Z, M, K, ldz, false)) return rc;
+    return launch<0, 1, EPI_GELU_BWD, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmDZ, nullptr, &tmZ);
 }
 
 extern "C" int mmdti_gemm_dgrad_lnbwd(const void* dY, int64_t lddy, const void* W, int64_t ldw, const float* x, const float* mean,
@@ -770,8 +896,14 @@ extern "C" int mmdti_gemm_dgrad_lnbwd(const void* dY, int64_t lddy, const void* 
     p.key = ew_key(seed);
     p.seed_off = mmdti_seed_offset_ptr();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (K > BN) return launch<0, 1, EPI_LNBWD_DROP, 2>(tmA, tmB, p, st);
-    return launch<0, 1, EPI_LNBWD_DROP, 1>(tmA, tmB, p, st);
+    CUtensorMap tmDx, tmDa, tmX, tmAdd;
+    if (int rc = make_out_map(&tmDx, dx, M, K, K, true)) return rc;
+    if (int rc = make_out_map(&tmDa, da, M, K, K, false)) return rc;
+    if (int rc = make_out_map(&tmX, x, M, K, K, true)) return rc;
+    if (dx_add) { if (int rc = make_out_map(&tmAdd, dx_add, M, K, K, true)) return rc; }
+    else tmAdd = tmX;
+    if (K > BN) return launch<0, 1, EPI_LNBWD_DROP, 2>(tmA, tmB, p, st, &tmDx, &tmDa, &tmX, &tmAdd);
+    return launch<0, 1, EPI_LNBWD_DROP, 1>(tmA, tmB, p, st, &tmDx, &tmDa, &tmX, &tmAdd);
 }
 
 extern "C" int mmdti_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw, int M, int N, int K,
@@ -799,5 +931,7 @@ extern "C" int mmdti_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int
         if (lddw == K) MMDTI_CUDA_OK(cudaMemsetAsync(dW, 0, (size_t)N * K * sizeof(float), st));
         else MMDTI_CUDA_OK(cudaMemset2DAsync(dW, (size_t)lddw * sizeof(float), 0, (size_t)K * sizeof(float), (size_t)N, st));
     }
-    return launch<1, 1, EPI_WGRAD, 1>(tmA, tmB, p, st);
+    CUtensorMap tmW;
+    if (int rc = make_out_map(&tmW, dW, N, K, lddw, true)) return rc;
+    return launch<1, 1, EPI_WGRAD, 1>(tmA, tmB, p, st, &tmW);
 }

@@ -30,6 +30,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// TMA tile store / reduce-add shared -> global (bulk async-group); the box and swizzle come from the tensor map, rows and
+// columns outside the tensor are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(map), "r"(smem_u32(src)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -76,6 +88,15 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout; version 1).  K-major operand, 128-byte swizzle:
 // lbo = 16 (unused), sbo = 1024 (8 rows of 128 bytes).  MN-major operand, 128-byte swizzle (smem rows = K, 64 MN
 // elements per 128-byte row): lbo = byte distance between successive 64-element MN chunks, sbo = 1024 (8 K rows).
@@ -109,9 +130,10 @@ inline EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-// (rows, cols) bf16 row-major with a row stride of ld elements -> 2-D map with a (64 x box_rows) box, 128-byte swizzle,
-// zero OOB fill.  ld * 2 must be a multiple of 16 bytes.
-inline int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+// (rows, cols) row-major matrix with a row stride of ld elements -> 2-D map with a (box_cols x box_rows) box, zero OOB
+// fill.  elem_bytes = 2 (bf16) or 4 (fp32); swizzle_bytes = 128 or 64 = box_cols * elem_bytes; ld * elem_bytes % 16 == 0.
+inline int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int elem_bytes, int box_cols,
+                       int box_rows, int swizzle_bytes) {
     // the driver entry point needs the primary context bound to THIS thread (autograd runs the backward
     // on its own thread, which may not have made a runtime call yet)
     static thread_local bool bound = false;
@@ -119,14 +141,19 @@ inline int make_map_bf16(CUtensorMap* map, const void* base, long long rows, lon
     EncodeTiledFn fn = encode_fn();
     if (!fn) { mmdti_set_error("cuTensorMapEncodeTiled is not available from the driver"); return MMDTI_ERR_CUDA; }
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    const CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                          const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { mmdti_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return MMDTI_ERR_CUDA; }
     return MMDTI_OK;
+}
+// bf16 operand map: (64 x box_rows) box, 128-byte swizzle
+inline int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+    return make_map_2d(map, base, rows, cols, ld, 2, 64, box_rows, 128);
 }
 
 }  // namespace tc

@@ -52,6 +52,9 @@ class GraphedStep:
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(warmup):
+                if params is not None:
+                    for p in params:          # every warm-up step is a proper step: no accumulation onto the previous one's gradients
+                        p.grad = None
                 body()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)

@@ -7,7 +7,7 @@ import os
 
 import torch
 
-from . import _lib, config
+from . import _lib, config, ops_gemm
 from ._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
 
 _seed_lock = threading.Lock()
@@ -336,6 +336,31 @@ def _mm_f32(a, b):
         return torch.mm(a, b).float()
 
 
+# Which dense projections of the encoder layer run on the own tcgen05 GEMMs with fused epilogues (csrc/gemm_tc.cu)
+# instead of library GEMMs + separate elementwise kernels.  MMDTI_FUSED=all | none | comma list of:
+#   in    in_proj forward (+bias)                         out   out_proj forward + dropout + residual + LayerNorm-2
+#   fc1   fc1 forward + bias + GELU                       fc2   fc2 forward + dropout + residual (+ next LayerNorm-1)
+#   dfc2  fc2 dgrad + GELU backward + db_fc1              dfc1  fc1 dgrad + LayerNorm-2 backward + dropout backward
+#   dout  out_proj dgrad                                  din   in_proj dgrad
+#   wgrad the four weight gradients
+FUSED_ALL = ("in", "out", "fc1", "fc2", "dfc2", "dfc1", "dout", "din", "wgrad")
+
+
+def _parse_fused(spec):
+    spec = spec.strip().lower()
+    if spec in ("all", "1", ""):
+        return frozenset(FUSED_ALL)
+    if spec in ("none", "0"):
+        return frozenset()
+    names = frozenset(x.strip() for x in spec.split(",") if x.strip())
+    bad = names - frozenset(FUSED_ALL)
+    if bad:
+        raise ValueError("MMDTI_FUSED: unknown entries %s (known: %s)" % (sorted(bad), ", ".join(FUSED_ALL)))
+    return names
+
+
+fused_gemms = _parse_fused(os.environ.get("MMDTI_FUSED", "all"))
+
 _side_streams = {}
 overlap_wgrad = True      # run weight-gradient GEMMs / bias column sums of a layer on a side stream (off the critical path)
 
@@ -436,36 +461,51 @@ class EncoderLayerFn(torch.autograd.Function):
             h1, st1 = h1_in.detach(), st1_in.detach()
         else:
             h1, st1 = layernorm_fwd(x2d, ln1_wd, ln1_bd, dt)
-        qkv = torch.addmm(b_in_l, h1, w_in_l.t())
+        # own tcgen05 GEMMs with fused epilogues where the shapes allow it (bf16, feature dims multiples of 64, D <= 512)
+        fz = fused_gemms if (dt == torch.bfloat16 and ops_gemm.supported(D, w_fc1_l.shape[0])) else frozenset()
+        qkv = ops_gemm.gemm_bias(h1, w_in_l, b_in_l) if "in" in fz else torch.addmm(b_in_l, h1, w_in_l.t())
         o = torch.empty((rows, D), device=x.device, dtype=dt)
         pair_out = torch.empty_like(pair_in)
         call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_in, pair_out, o, i64(D),
              i32(B), i32(H), i32(L), f32(scale), f32(p_attn), u64(seeds[0]), i32(code), i32(DTYPE_CODE[pair_in.dtype]), sp)
-        a = torch.addmm(b_out_l, o, w_out_l.t())
-        x1 = torch.empty_like(x2d)
-        h2 = torch.empty((rows, D), device=x.device, dtype=dt)
-        st2 = torch.empty((2, rows), device=x.device, dtype=torch.float32)
-        call("mmdti_dropres_layernorm_fwd", x2d, a, x1, ln2_wd, ln2_bd, h2, st2[0], st2[1], i32(rows), i32(D), f32(1e-5),
-             f32(p_drop), u64(seeds[1]), i32(code), i32(code), sp)
-        z = torch.addmm(b_fc1_l, h2, w_fc1_l.t())
-        u = torch.empty_like(z)
-        call("mmdti_gelu_fwd", z, u, i64(z.numel()), i32(code), sp)
-        f = torch.addmm(b_fc2_l, u, w_fc2_l.t())
-        x2 = torch.empty_like(x2d)
+        if "out" in fz:
+            # out_proj + bias + dropout + residual + LayerNorm-2 in one kernel (same dropout stream as the unfused kernel)
+            x1, h2, st2 = ops_gemm.gemm_dropres_ln(o, w_out_l, b_out_l, x2d, ln2_wd, ln2_bd, p_drop, seeds[1])
+        else:
+            a = torch.addmm(b_out_l, o, w_out_l.t())
+            x1 = torch.empty_like(x2d)
+            h2 = torch.empty((rows, D), device=x.device, dtype=dt)
+            st2 = torch.empty((2, rows), device=x.device, dtype=torch.float32)
+            call("mmdti_dropres_layernorm_fwd", x2d, a, x1, ln2_wd, ln2_bd, h2, st2[0], st2[1], i32(rows), i32(D), f32(1e-5),
+                 f32(p_drop), u64(seeds[1]), i32(code), i32(code), sp)
+        if "fc1" in fz:
+            z, u = ops_gemm.gemm_bias_gelu(h2, w_fc1_l, b_fc1_l)
+        else:
+            z = torch.addmm(b_fc1_l, h2, w_fc1_l.t())
+            u = torch.empty_like(z)
+            call("mmdti_gelu_fwd", z, u, i64(z.numel()), i32(code), sp)
         chain_out = nxt_w is not None
+        nxt_wd = h_next = st_next = None
         if chain_out:
             nxt_wd, nxt_bd = nxt_w.detach().float().contiguous(), nxt_b.detach().float().contiguous()
-            h_next = torch.empty((rows, D), device=x.device, dtype=dt)
-            st_next = torch.empty((2, rows), device=x.device, dtype=torch.float32)
-            call("mmdti_dropres_layernorm_fwd", x1, f, x2, nxt_wd, nxt_bd, h_next, st_next[0], st_next[1], i32(rows), i32(D),
-                 f32(1e-5), f32(p_drop), u64(seeds[2]), i32(code), i32(code), sp)
+        if "fc2" in fz:
+            x2, h_next, st_next = ops_gemm.gemm_dropres_ln(u, w_fc2_l, b_fc2_l, x1, nxt_wd, nxt_bd if chain_out else None,
+                                                           p_drop, seeds[2])
         else:
-            nxt_wd = h_next = st_next = None
-            call("mmdti_dropout_residual_fwd", x1, f, x2, i64(rows * D), f32(p_drop), u64(seeds[2]), i32(code), sp)
+            f = torch.addmm(b_fc2_l, u, w_fc2_l.t())
+            x2 = torch.empty_like(x2d)
+            if chain_out:
+                h_next = torch.empty((rows, D), device=x.device, dtype=dt)
+                st_next = torch.empty((2, rows), device=x.device, dtype=torch.float32)
+                call("mmdti_dropres_layernorm_fwd", x1, f, x2, nxt_wd, nxt_bd, h_next, st_next[0], st_next[1], i32(rows), i32(D),
+                     f32(1e-5), f32(p_drop), u64(seeds[2]), i32(code), i32(code), sp)
+            else:
+                call("mmdti_dropout_residual_fwd", x1, f, x2, i64(rows * D), f32(p_drop), u64(seeds[2]), i32(code), sp)
         ctx.save_for_backward(x2d, pair_out, st1, h1, qkv, o, x1, st2, h2, z, u, ln1_wd, ln2_wd, w_in_l, w_out_l,
                               w_fc1_l, w_fc2_l, *((x2, st_next, nxt_wd) if chain_out else ()))
         ctx.cfg = cfg
         ctx.chain = (chain_in, chain_out)
+        ctx.fz = fz
         ctx.set_materialize_grads(False)
         if chain_out:
             ctx.mark_non_differentiable(st_next)
@@ -526,19 +566,27 @@ class EncoderLayerFn(torch.autograd.Function):
         else:
             call("mmdti_dropout_bwd", dx2, df, db_fc2, i32(rows), i32(D), f32(p_drop), u64(seeds[2]), i32(code), sp)
             g_nxt = (None, None)
-        dW_fc2 = off_path(lambda: _mm_f32(df.t(), u))
-        du = torch.mm(df, w_fc2_l)
-        dz = torch.empty_like(z)
-        call("mmdti_gelu_bwd", du, z, dz, db_fc1, i32(rows), i32(F_), i32(code), sp)
-        dW_fc1 = off_path(lambda: _mm_f32(dz.t(), h2))
-        dh2 = torch.mm(dz, w_fc1_l)
-        dx1 = torch.empty_like(x2d)
+        fz = ctx.fz
+        wgrad = (lambda dy, xin: ops_gemm.gemm_wgrad(dy, xin)) if "wgrad" in fz else (lambda dy, xin: _mm_f32(dy.t(), xin))
+        dW_fc2 = off_path(lambda: wgrad(df, u))
+        if "dfc2" in fz:
+            dz = ops_gemm.gemm_dgrad_gelu(df, w_fc2_l, z, db_fc1)          # fc2 dgrad + GELU' + db_fc1 column sums
+        else:
+            du = torch.mm(df, w_fc2_l)
+            dz = torch.empty_like(z)
+            call("mmdti_gelu_bwd", du, z, dz, db_fc1, i32(rows), i32(F_), i32(code), sp)
+        dW_fc1 = off_path(lambda: wgrad(dz, h2))
         # ---- attention block (LayerNorm-2 backward fused with the dropout backward of the attention output)
-        da = torch.empty((rows, D), device=dev, dtype=dt)
-        call("mmdti_layernorm_bwd_dropout", dh2, x1, ln2_w, st2[0], st2[1], dx2, dx1, dw_ln2, db_ln2, da, db_out, i32(rows),
-             i32(D), f32(p_drop), u64(seeds[1]), i32(code), sp)
-        dW_out = off_path(lambda: _mm_f32(da.t(), o))
-        d_o = torch.mm(da, w_out_l)
+        if "dfc1" in fz:
+            dx1, da = ops_gemm.gemm_dgrad_lnbwd(dz, w_fc1_l, x1, st2, ln2_w, dx2, dw_ln2, db_ln2, db_out, p_drop, seeds[1])
+        else:
+            dh2 = torch.mm(dz, w_fc1_l)
+            dx1 = torch.empty_like(x2d)
+            da = torch.empty((rows, D), device=dev, dtype=dt)
+            call("mmdti_layernorm_bwd_dropout", dh2, x1, ln2_w, st2[0], st2[1], dx2, dx1, dw_ln2, db_ln2, da, db_out, i32(rows),
+                 i32(D), f32(p_drop), u64(seeds[1]), i32(code), sp)
+        dW_out = off_path(lambda: wgrad(da, o))
+        d_o = ops_gemm.gemm_dgrad(da, w_out_l) if "dout" in fz else torch.mm(da, w_out_l)
         dqkv = torch.empty_like(qkv)
         dpair_in = torch.empty_like(pair_out)
         call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair_out, o, d_o, i64(D),
@@ -547,10 +595,10 @@ class EncoderLayerFn(torch.autograd.Function):
              i32(DTYPE_CODE[pair_out.dtype]), sp)
         def in_proj_grads():
             call("mmdti_colsum", dqkv, db_in, i32(rows), i32(3 * D), i32(code), stream_ptr())
-            return _mm_f32(dqkv.t(), h1)
+            return wgrad(dqkv, h1)
 
         dW_in = off_path(in_proj_grads)
-        dh1 = torch.mm(dqkv, w_in_l)
+        dh1 = ops_gemm.gemm_dgrad(dqkv, w_in_l) if "din" in fz else torch.mm(dqkv, w_in_l)
         if chain_in:
             # LayerNorm-1 belongs to the previous layer's fused kernel: hand it dh1, return the residual gradient alone
             dx, g_ln1, g_h1 = dx1, (None, None), dh1

@@ -2,9 +2,9 @@
 golden fixtures generated from the reference's own models/infonce.py and models/contrastive.py
 (oracle/make_golden.py) and against the oracle restatement at larger sizes.
 
-Tolerances.  fp32 validation mode: loss 1e-5, gradients 2e-5 (relative to the max |reference|).
+Tolerances (tests/tolerances.py).  fp32 validation mode: loss 5e-6, gradients 1e-5 (relative to the max |reference|).
 bf16 tensor-core mode: operands are bf16 unit vectors (2^-9 relative rounding), logits are scaled by
-1/t = 10..14.3 before the exponential, so loss 2e-3 and gradients 2e-2 in the norm sense."""
+1/t = 10..14.3 before the exponential, so loss 1e-3 (north_star's bf16 bound: met) and gradients 1.2e-2 in the norm sense (observed 4.4e-3: not met)."""
 import pytest
 import torch
 
@@ -17,7 +17,9 @@ from mmdti_b200.models import infonce as infm
 from oracle import restate
 
 pytestmark = pytest.mark.gpu
-MODES = [("fp32", 1e-5, 2e-5), ("bf16", 2e-3, 2e-2)]
+from tolerances import TOL as _T
+
+MODES = [("fp32",) + _T["sim.fp32"], ("bf16",) + _T["sim.bf16"]]
 
 
 def _tol(a, b, mode):
@@ -109,7 +111,7 @@ def test_losses_vs_oracle_ragged_sizes(N, D, mode, ltol, gtol, report):
         if name == "infonce":
             e.append(_tol(bc.grad, b.grad, mode))
         report("sim-vs-oracle", name, N, D, mode, *("%.2e" % v for v in e))
-        assert e[0] < ltol * 2 and all(v < gtol * 2 for v in e[1:]), (name, e)
+        assert e[0] < ltol and all(v < gtol for v in e[1:]), (name, e)
 
 
 @pytest.mark.parametrize("N,D", [(4096, 512), (4396, 136)])
@@ -136,7 +138,7 @@ def test_large_n_tensor_core_tiles_match_fp32_kernels(N, D, report):
     for (name, l32, g32, gb32), (_, l16, g16, gb16) in zip(out["fp32"], out["bf16"]):
         e = [rel_err(l16, l32), norm_err(g16, g32)] + ([norm_err(gb16, gb32)] if gb32 is not None else [])
         report("sim-large-n", name, N, D, *("%.2e" % v for v in e))
-        assert e[0] < 4e-3 and all(v < 4e-2 for v in e[1:]), (name, e)
+        assert e[0] < _T["sim.bf16"][0] and all(v < _T["sim.bf16"][1] for v in e[1:]), (name, e)      # observed 1.1e-5 / 3.8e-3
 
 
 def test_fused_and_two_step_backward_agree(monkeypatch):

@@ -69,7 +69,7 @@ def test_unimol_encoder_15_layers_golden(tag, act, pair, report):
            "x_by_layer=" + ",".join("%.1e" % e for e in x_growth), "pair_by_layer=" + ",".join("%.1e" % e for e in p_growth),
            "grad_norm=" + str({k: "%.1e" % v for k, v in gerr.items()}),
            "grad_max=" + str({k[5:]: "%.1e" % v for k, v in errs.items() if k.startswith("dmax_")}))
-    key = "enc15." + ("fp32" if act == "fp32" else "bf16.pair_" + pair)
+    key = "enc15." + ("fp32" if act == "fp32" else "bf16." + tag)
     t = TOL[key]
     assert errs["rep"] < t["rep_max"] and errs["rep_norm"] < t["rep_norm"], (errs["rep"], errs["rep_norm"])
     assert errs["x_layer_max"] < t["x_layer_norm"] and errs["pair_layer_max"] < t["pair_layer_norm"], (x_growth, p_growth)

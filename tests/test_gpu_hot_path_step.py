@@ -17,6 +17,8 @@ from mmdti_b200.models.fds import FDS
 from mmdti_b200.models.infonce import InfoNCE
 from oracle import restate
 
+from tolerances import TOL
+
 pytestmark = pytest.mark.gpu
 
 
@@ -25,7 +27,7 @@ def _fds_state(nb, D, gen):
             "smoothed_mean": torch.randn(nb, D, generator=gen) * 0.1, "smoothed_var": torch.rand(nb, D, generator=gen) + 0.5}
 
 
-@pytest.mark.parametrize("mode,ltol,gtol", [("fp32", 2e-5, 2e-4), ("bf16", 2e-3, 3e-2)])
+@pytest.mark.parametrize("mode,ltol,gtol", [("fp32",) + TOL["step.fp32"], ("bf16",) + TOL["step.bf16"]])
 def test_hot_path_training_step_matches_oracle(mode, ltol, gtol, report):
     B, n_atoms, S, nl, nb = 12, 20, 9, 2, 10
     gen = torch.Generator().manual_seed(77)

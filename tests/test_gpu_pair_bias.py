@@ -35,12 +35,10 @@ def test_pair_bias_golden(tag, act, pair, report):
     grads.update({"gbf_proj." + k: v.grad for k, v in proj.named_parameters()})
     e_g = {k: rel_err(grads[k].float(), g["grad." + k]) for k in grads}
     report("pair_bias", tag, act, pair, "out=%.2e" % e_out, {k: "%.1e" % v for k, v in e_g.items()})
-    if act == "fp32":
-        assert e_out < 2e-5
-        assert max(e_g.values()) < 2e-4, e_g
-    else:
-        assert e_out < 2e-2
-        assert max(e_g.values()) < 6e-2, e_g
+    from tolerances import TOL
+    t = TOL["k1." + act]
+    assert e_out < t["out"], e_out
+    assert max(e_g.values()) < t["grad"], e_g
 
 
 @pytest.mark.parametrize("B,n_atoms", [(128, 64), (8, 256)])
