@@ -188,6 +188,10 @@ int mmdti_gemm_dgrad_lnbwd(const void* dY, int64_t lddy, const void* W, int64_t 
 /* dW (N,K) fp32 (row stride lddw) = dY^T X, or += when accumulate != 0.                 [weight gradients] */
 int mmdti_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw, int M, int N,
                      int K, int accumulate, void* stream);
+/* C (M,N) fp32 = A (M,K) bf16 @ B (K,N) bf16, both row-major.  The second step of the two-step contrastive backward
+ * (dA = H . B over the key dimension, models/infonce.py:70-98 / models/contrastive.py gradients), replacing a library GEMM. */
+int mmdti_gemm_nn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                      void* stream);
 
 /* padded (B,H,L,Lp) pair_dtype -> dense (B,L,L,H) f32 "pair" and "delta pair" outputs of
  * TransformerEncoderWithPair.forward (models/transformers.py:163-172): pair_last permuted, and

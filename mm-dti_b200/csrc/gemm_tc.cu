@@ -935,3 +935,18 @@ extern "C" int mmdti_gemm_wgrad(const void* dY, int64_t lddy, const void* X, int
     if (int rc = make_out_map(&tmW, dW, N, K, lddw, true)) return rc;
     return launch<1, 1, EPI_WGRAD, 1>(tmA, tmB, p, st, &tmW);
 }
+
+extern "C" int mmdti_gemm_nn_f32(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+                                 void* stream) {
+    MMDTI_REQUIRE(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0 && C && mmdti_aligned(C, 16) && ldc % 4 == 0,
+                  "gemm_nn_f32: need M, N, K > 0, N, K multiples of 8, a 16-byte aligned C with ldc %% 4 == 0");
+    if (int rc = check_ld(A, lda, "A")) return rc;
+    if (int rc = check_ld(B, ldb, "B")) return rc;
+    CUtensorMap tmA, tmB, tmC;
+    if (int rc = make_map_bf16(&tmA, A, M, K, lda, BM)) return rc;           // A (M x K): reduction K, K-major
+    if (int rc = make_map_bf16(&tmB, B, K, N, ldb, BK)) return rc;           // B (K x N): rows = reduction, MN-major
+    if (int rc = make_out_map(&tmC, C, M, N, ldc, true)) return rc;
+    GemmParams p = base_params(M, N, K);
+    p.out0 = C; p.ld0 = ldc;
+    return launch<0, 1, EPI_WGRAD, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmC);
+}

@@ -114,16 +114,20 @@ class TransformerEncoderWithPair(nn.Module):
         # cross-layer fusion: the final dropout+residual of layer i and LayerNorm-1 of layer i+1 run as one kernel
         # (forward and backward) whenever both layers take the fused path; `chain` carries (h1, statistics)
         chain = None
+        link = None                  # dict shared by two adjacent layers of the chain (see ops.EncoderLayerFn)
         n_layers = len(self.layers)
         for i, layer in enumerate(self.layers):
             nxt = self.layers[i + 1] if i + 1 < n_layers else None
             fuse_next = (self.chain_layers and nxt is not None and layer._fusable(x, pair, None, True)
                          and isinstance(nxt.self_attn_layer_norm, torch.nn.LayerNorm))
+            link_next = {} if fuse_next else None
             out = layer(x, padding_mask=None, attn_bias=pair, return_attn=True,
                         lowp=None if lowp is None else lowp[8 * i:8 * i + 8],
-                        chain_in=chain, next_ln=nxt.self_attn_layer_norm if fuse_next else None)
+                        chain_in=chain, next_ln=nxt.self_attn_layer_norm if fuse_next else None,
+                        link_in=link if chain is not None else None, link_out=link_next)
             x, pair = out[0], out[1]
             chain = out[3] if len(out) > 3 else None
+            link = link_next
 
         if not self.pair_outputs:
             if self.final_layer_norm is not None:

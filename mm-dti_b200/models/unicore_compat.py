@@ -177,7 +177,7 @@ class TransformerEncoderLayer(nn.Module):
                                             self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)]
 
     def forward(self, x, attn_bias=None, padding_mask=None, return_attn=False, inplace_pair=False, lowp=None,
-                chain_in=None, next_ln=None):
+                chain_in=None, next_ln=None, link_in=None, link_out=None):
         """chain_in / next_ln (fused path only, used by TransformerEncoderWithPair): ``chain_in`` = (h1, stats) of this
         layer's LayerNorm-1 already computed by the previous layer, ``next_ln`` = the next layer's LayerNorm-1 module;
         with next_ln the result is (x, scores, None, (h_next, stats_next))."""
@@ -199,7 +199,7 @@ class TransformerEncoderLayer(nn.Module):
                 sa.in_proj.weight, sa.in_proj.bias, sa.out_proj.weight, sa.out_proj.bias,
                 self.final_layer_norm.weight, self.final_layer_norm.bias, self.fc1.weight, self.fc1.bias,
                 self.fc2.weight, self.fc2.bias, lowp, cfg, h1_in, st1_in,
-                None if next_ln is None else next_ln.weight, None if next_ln is None else next_ln.bias)
+                None if next_ln is None else next_ln.weight, None if next_ln is None else next_ln.bias, link_in, link_out)
             if next_ln is not None:
                 return out[0], out[1], None, (out[2], out[3])
             return out[0], out[1], None

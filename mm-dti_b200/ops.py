@@ -439,11 +439,14 @@ class EncoderLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pair_in, ln1_w, ln1_b, w_in, b_in, w_out, b_out, ln2_w, ln2_b, w_fc1, b_fc1, w_fc2, b_fc2,
-                lowp, cfg, h1_in=None, st1_in=None, nxt_w=None, nxt_b=None):
+                lowp, cfg, h1_in=None, st1_in=None, nxt_w=None, nxt_b=None, link_in=None, link_out=None):
         """Cross-layer chaining (optional): ``h1_in, st1_in`` = this layer's LayerNorm-1 output and statistics, already
         produced by the PREVIOUS layer; ``nxt_w, nxt_b`` = the NEXT layer's LayerNorm-1 parameters, in which case the
         final dropout+residual is fused with that LayerNorm (one kernel instead of two, forward and backward) and the
-        function returns (x2, pair_out, h_next, st_next)."""
+        function returns (x2, pair_out, h_next, st_next).  ``link_in`` / ``link_out``: plain dicts shared with the previous /
+        next layer of the chain; the forward leaves the dropout stream of this layer's final dropout in ``link_out`` so
+        that the NEXT layer's backward can fuse its in_proj dgrad + LayerNorm-1 backward with that dropout's backward
+        (one GEMM epilogue, csrc/gemm_tc.cu EPI_LNBWD_DROP) and hand the results back through the same dict."""
         B, H, L, scale, p_attn, p_drop, seeds, dt = cfg
         _lib.require_cuda(x, pair_in)
         D = x.shape[-1]
@@ -506,6 +509,9 @@ class EncoderLayerFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.chain = (chain_in, chain_out)
         ctx.fz = fz
+        ctx.links = (link_in if chain_in else None, link_out if chain_out else None)
+        if chain_out and link_out is not None:
+            link_out["p"], link_out["seed"] = p_drop, seeds[2]
         ctx.set_materialize_grads(False)
         if chain_out:
             ctx.mark_non_differentiable(st_next)
@@ -554,7 +560,14 @@ class EncoderLayerFn(torch.autograd.Function):
 
         # ---- feed-forward block
         df = torch.empty((rows, D), device=dev, dtype=dt)
-        if chain_out and dh_next is not None:
+        link_in, link_out = ctx.links
+        if chain_out and dh_next is not None and link_out is not None and link_out.pop("fused", False):
+            # the next layer's backward already ran in_proj dgrad + LayerNorm-1 backward + THIS layer's final dropout
+            # backward in one GEMM epilogue: dx2 is the total gradient at x2, dh_next carries df, the dict db_fc2
+            df = dh_next.contiguous()
+            db_fc2 = link_out.pop("db_fc2")
+            g_nxt = (None, None)
+        elif chain_out and dh_next is not None:
             # the NEXT layer's LayerNorm-1 backward fused with this layer's final dropout backward:
             # dxt = dx2 + dLN(dh_next) is the total gradient at x2, df = dropout'(dxt)
             x2, st_next, nxt_w = saved[17:20]
@@ -598,18 +611,27 @@ class EncoderLayerFn(torch.autograd.Function):
             return wgrad(dqkv, h1)
 
         dW_in = off_path(in_proj_grads)
-        dh1 = ops_gemm.gemm_dgrad(dqkv, w_in_l) if "din" in fz else torch.mm(dqkv, w_in_l)
-        if chain_in:
+        if chain_in and "din" in fz and link_in is not None and "seed" in link_in:
+            # in_proj dgrad + this layer's LayerNorm-1 backward + the PREVIOUS layer's final dropout backward in one GEMM
+            # epilogue: dx = total gradient at the previous layer's x2, g_h1 = df of the previous layer, its db_fc2 in the dict
+            db_fc2_prev = torch.zeros(D, device=dev, dtype=torch.float32)
+            dx, g_h1 = ops_gemm.gemm_dgrad_lnbwd(dqkv, w_in_l, x2d, st1, ln1_w, dx1, dw_ln1, db_ln1, db_fc2_prev,
+                                                 link_in["p"], link_in["seed"])
+            link_in["db_fc2"], link_in["fused"] = db_fc2_prev, True
+            g_ln1 = (dw_ln1, db_ln1)
+        elif chain_in:
+            dh1 = ops_gemm.gemm_dgrad(dqkv, w_in_l) if "din" in fz else torch.mm(dqkv, w_in_l)
             # LayerNorm-1 belongs to the previous layer's fused kernel: hand it dh1, return the residual gradient alone
             dx, g_ln1, g_h1 = dx1, (None, None), dh1
         else:
+            dh1 = ops_gemm.gemm_dgrad(dqkv, w_in_l) if "din" in fz else torch.mm(dqkv, w_in_l)
             dx = dx1          # in place: dx = dx1 + dLN1
             call("mmdti_layernorm_bwd", dh1, x2d, ln1_w, st1[0], st1[1], dx1, dx, dw_ln1, db_ln1, i32(rows), i32(D), i32(code), sp)
             g_ln1, g_h1 = (dw_ln1, db_ln1), None
         if side is not None:
             main.wait_stream(side)
         return (dx.view(B, L, D), dpair_in, g_ln1[0], g_ln1[1], dW_in, db_in, dW_out, db_out, dw_ln2, db_ln2, dW_fc1, db_fc1,
-                dW_fc2, db_fc2, None, None, g_h1, None, g_nxt[0], g_nxt[1])
+                dW_fc2, db_fc2, None, None, g_h1, None, g_nxt[0], g_nxt[1], None, None)
 
 
 def dropout_mask(n, p, seed, device="cuda"):

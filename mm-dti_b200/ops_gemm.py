@@ -99,3 +99,37 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
     call("mmdti_gemm_wgrad", dy, i64(dy.stride(0)), x, i64(x.stride(0)), dw, i64(dw.stride(0)), i32(M), i32(N), i32(K),
          i32(1 if accumulate else 0), stream_ptr())
     return dw
+
+
+class LinearGeluFn(torch.autograd.Function):
+    """u = gelu(x W^T + b) on the tcgen05 GEMMs: x (M,K) any float dtype, W (N,K), b (N) fp32 parameters -> u (M,N) bf16.
+    Forward = mmdti_gemm_bias_gelu; backward = GELU' (+ bias column sums) and the two gradient GEMMs.  Used by the InfoNCE
+    projection heads (models/infonce.py:24-33: Linear -> GELU -> Linear over every token)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _lib.require_cuda(x, w)
+        xb = x.detach().to(torch.bfloat16).contiguous()
+        wb = w.detach().to(torch.bfloat16).contiguous()
+        bb = b.detach().to(torch.bfloat16).contiguous()
+        z, u = gemm_bias_gelu(xb, wb, bb)
+        ctx.save_for_backward(xb, wb, z)
+        ctx.x_dtype = x.dtype
+        ctx.needs = (x.requires_grad, w.requires_grad, b.requires_grad)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        xb, wb, z = ctx.saved_tensors
+        M, N = z.shape
+        du = du.contiguous().to(torch.bfloat16)
+        dz = torch.empty_like(z)
+        db = torch.zeros(N, device=z.device, dtype=torch.float32)
+        call("mmdti_gelu_bwd", du, z, dz, db, i32(M), i32(N), i32(_lib.BF16), stream_ptr())
+        dw = gemm_wgrad(dz, xb) if ctx.needs[1] else None
+        dx = gemm_dgrad(dz, wb).to(ctx.x_dtype) if ctx.needs[0] else None
+        return dx, dw, db if ctx.needs[2] else None
+
+
+def linear_gelu(x, w, b):
+    return LinearGeluFn.apply(x, w, b)

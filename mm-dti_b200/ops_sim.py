@@ -98,7 +98,17 @@ def _sim_grad_two_step(mode, A, B, row_offset, temperature, lab, rs_row, rs_col)
         m = min(rb, M - r0)
         call("mmdti_sim_coef_tc", A.bf16[r0:], B.bf16, i32(m), i32(N), i32(A.Dp), i32(row_offset + r0), i32(mode),
              f32(temperature), *_label_args(mode, lab), rs_row[r0:], rs_col, hbuf, i64(ldh), stream_ptr())
-        blk = torch.mm(hbuf[:m, :N], B.bf16, out_dtype=torch.float32)            # (m, Dp), fp32 accumulate and result
+        # dA block = H (m, N) @ B (N, Dp) on the own tcgen05 GEMM (fp32 accumulate and result); columns of H beyond N
+        # are never written by the coefficient kernel and are not read here (K = N, row stride ldh)
+        blk = torch.empty((m, A.Dp), device=dev, dtype=torch.float32)
+        if N % 8 == 0:
+            call("mmdti_gemm_nn_f32", hbuf, i64(ldh), B.bf16, i64(A.Dp), blk, i64(A.Dp), i32(m), i32(A.Dp), i32(N), stream_ptr())
+        else:
+            # N not a multiple of 8: the padding columns [N, ldh) of H are zeroed and the key matrix is padded with zero rows
+            hbuf[:m, N:].zero_()
+            bpad = torch.zeros((ldh, A.Dp), device=dev, dtype=torch.bfloat16)
+            bpad[:N] = B.bf16
+            call("mmdti_gemm_nn_f32", hbuf, i64(ldh), bpad, i64(A.Dp), blk, i64(A.Dp), i32(m), i32(A.Dp), i32(ldh), stream_ptr())
         if m == M:
             out = blk
         else:

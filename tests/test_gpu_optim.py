@@ -118,8 +118,12 @@ def test_graphed_step_prefetch_pipeline():
 
 def test_graphed_training_step_matches_eager(report):
     """N replays of a graphed forward + backward + FusedAdam step == the same number of eager steps with zero_grad
-    between them (dropout off): parameters AND Adam moments.  Guards against the captured backward recording
-    ``grad += new`` onto gradients the warm-up left defined (each replay would then see the sum of all previous steps)."""
+    between them (dropout off).  Guards against the captured backward recording ``grad += new`` onto gradients the
+    warm-up left defined: every replay would then hand the optimizer the SUM of all previous steps' gradients.
+    Run with lr = 0 so that the parameters stay put and the comparison is exact up to the summation order of the atomics
+    (with lr > 0 Adam turns the round-off noise of analytically-zero gradients -- key bias, per-head pair-bias constant
+    -- into +-lr steps, and the two runs drift apart for reasons unrelated to the graph): the optimizer's first and
+    second moments then are pure functions of the gradient history, (1 - beta^n) g and (1 - beta2^n) g^2."""
     import mmdti_b200
     from mmdti_b200.data import synthetic_molecules
     from mmdti_b200.graph import GraphedStep
@@ -129,12 +133,12 @@ def test_graphed_training_step_matches_eager(report):
     inputs = [tokens.to(dev), dist.to(dev), et.to(dev)]
     g = torch.randn(4, 16, 512, generator=torch.Generator().manual_seed(1)).to(dev)
     n_warm, n_steps = 3, 4
-    for act, pair, tol in (("fp32", "fp32", 1e-5), ("bf16", "bf16", 1e-5)):
+    for act, pair in (("fp32", "fp32"), ("bf16", "bf16")):
         out = []
         for graphed in (False, True):
             torch.manual_seed(0)
             m = UnimolEncoder(encoder_layers=2).to(dev).eval()
-            opt = FusedAdam(m.parameters(), lr=1e-3, eps=1e-6, shadows=m.encoder.use_external_lowp())
+            opt = FusedAdam(m.parameters(), lr=0.0, eps=1e-6, shadows=m.encoder.use_external_lowp())
 
             def step(*inp):
                 loss = (m(*inp).float() * g).sum()
@@ -151,14 +155,13 @@ def test_graphed_training_step_matches_eager(report):
                     gs.close()
                 else:
                     for _ in range(n_warm + n_steps):
-                        step(*inputs)
                         opt.zero_grad(set_to_none=True)
+                        step(*inputs)
             torch.cuda.synchronize()
             assert int(opt.step_count.item()) == n_warm + n_steps
-            out.append(([p.detach().clone() for p in m.parameters()], opt.exp_avg.clone(), opt.exp_avg_sq.clone()))
-        (pe, me, ve), (pg, mg, vg) = out
-        e_p = max(rel_err(a, b) for a, b in zip(pg, pe))
-        e_m, e_v = rel_err(mg, me), rel_err(vg, ve)
-        report("graphed_vs_eager", act, "param=%.1e exp_avg=%.1e exp_avg_sq=%.1e" % (e_p, e_m, e_v))
-        # same kernels, same inputs, same order: only the atomics' summation order differs
-        assert e_p < tol and e_m < 1e-3 and e_v < 1e-3, (act, e_p, e_m, e_v)
+            out.append((torch.cat([p.grad.detach().reshape(-1) for p in m.parameters()]), opt.exp_avg.clone(), opt.exp_avg_sq.clone()))
+        (ge, me, ve), (gg, mg, vg) = out
+        e_g, e_m, e_v = rel_err(gg, ge), rel_err(mg, me), rel_err(vg, ve)
+        report("graphed_vs_eager", act, "last grad=%.1e exp_avg=%.1e exp_avg_sq=%.1e" % (e_g, e_m, e_v))
+        # an accumulating graph would be off by a factor of n_steps in the gradient and ~4x / ~16x in the moments
+        assert e_g < 1e-4 and e_m < 1e-4 and e_v < 1e-4, (act, e_g, e_m, e_v)
