@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <algorithm>
 
 namespace {
@@ -452,6 +453,11 @@ int num_sms() {
 
 }  // namespace
 
+// tcgen05 forward (pair_bias_tc5.cu)
+int mmdti_pair_bias_fwd_tc5(const float* dist, const long long* et, const float* means, const float* stds, const float* mul,
+                            const float* bias, const float* w1, const float* b1, const float* w2, const float* b2,
+                            const unsigned char* key_pad, void* out, int B, int L, int Lp, int E, int pair_dtype, cudaStream_t st);
+
 extern "C" int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, const float* means, const float* stds,
                                    const float* mul, const float* bias, const float* w1, const float* b1,
                                    const float* w2, const float* b2, const uint8_t* key_pad, void* out, int B, int L,
@@ -480,6 +486,10 @@ extern "C" int mmdti_pair_bias_fwd(const float* dist, const int64_t* edge_type, 
         else { mmdti_set_error("pair_bias_fwd: bad pair_dtype %d", pair_dtype); return MMDTI_ERR_ARG; }
 #undef LAUNCH_F32
     } else {
+        // production path: tcgen05 kernel (MMDTI_K1_TC5=0 selects the previous mma.sync kernel, kept for A/B comparison)
+        const char* e5 = getenv("MMDTI_K1_TC5");
+        if (!e5 || atoi(e5) != 0)
+            return mmdti_pair_bias_fwd_tc5(dist, p.et, means, stds, mul, bias, w1, b1, w2, b2, key_pad, out, B, L, p.Lp, E, pair_dtype, st);
         const size_t esz = pair_dtype == MMDTI_F32 ? 4 : 2;
         const size_t smem = (size_t)(KB + NH) * WS * sizeof(bf16) + (size_t)(KB * 4 + NH + 2 * E) * sizeof(float) +
                             (size_t)2 * TM * sizeof(int) + (size_t)NH * OT_STRIDE * esz + TM + 16 + (size_t)TM * sizeof(long long) + 8;
