@@ -28,7 +28,8 @@ namespace {
 constexpr int KB = 128;          // Gaussian kernels
 constexpr int NH = 64;           // heads
 constexpr int TQ = 128;          // positions per work item (= UMMA M)
-constexpr int NT = 256;          // threads: 2 per position (kernel halves / column halves)
+constexpr int NT = 512;          // threads: 4 per position (quarters of the kernels / columns / heads)
+constexpr int NPART = NT / TQ;
 constexpr int CHUNK_A = TQ * 128;        // one 64-wide K chunk of a 128-row operand tile: 16 KB
 constexpr int CHUNK_W2 = NH * 128;       // 64 rows: 8 KB
 constexpr uint32_t TMEM_COLS = 256;      // z: columns [0,128), o: [128,192)
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(NT, 2) pair_bias_fwd_tc5_kernel(const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int quad = warp & 3, hf = warp >> 2;            // TMEM lane quadrant of this warp; which half of the columns
+    const int quad = warp & 3, hf = warp >> 2;            // TMEM lane quadrant of this warp; which quarter of the columns
     const int r = quad * 32 + lane;                       // position (accumulator row) of this thread inside the item
 
     // ---- one-time: weights to bf16 swizzled operand tiles, per-kernel constants, tables, barriers, TMEM
@@ -165,8 +166,8 @@ __global__ void __launch_bounds__(NT, 2) pair_bias_fwd_tc5_kernel(const __grid_c
         const Gather nxt = gather(item + gridDim.x);          // in flight during this item's stages
         if (tid == 0) bulk_wait_read<0>();                    // the previous item's store has drained the store tile
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) {
-            const int k0 = hf * 64 + k8 * 8;
+        for (int k8 = 0; k8 < KB / NPART / 8; ++k8) {
+            const int k0 = hf * (KB / NPART) + k8 * 8;
             float g[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 4) {
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(NT, 2) pair_bias_fwd_tc5_kernel(const __grid_c
         tc_fence_after();
         // ---- stage 2: h = gelu(z + b1), columns [hf*64, hf*64 + 64) -> A tile (MMA 1 has finished reading it)
 #pragma unroll
-        for (int c32 = 0; c32 < 2; ++c32) {
-            const int c0 = hf * 64 + c32 * 32;
+        for (int c32 = 0; c32 < KB / NPART / 32; ++c32) {
+            const int c0 = hf * (KB / NPART) + c32 * 32;
             uint32_t v[32];
             tc_ld32(lane_addr + c0, v);
 #pragma unroll
@@ -229,25 +230,27 @@ __global__ void __launch_bounds__(NT, 2) pair_bias_fwd_tc5_kernel(const __grid_c
         tc_fence_after();
         // ---- stage 3: heads [hf*32, hf*32 + 32) of this position -> store tile [head][position]
         {
+            constexpr int HPT = NH / NPART;               // heads per thread
             uint32_t v[32];
-            tc_ld32(lane_addr + KB + hf * 32, v);
+            if (HPT == 32) tc_ld32(lane_addr + KB + hf * HPT, v);
+            else tc_ld16(lane_addr + KB + hf * HPT, v);
             if constexpr (sizeof(TP) == 2) {
                 // lanes l, l^1 hold adjacent positions: the even lane stores head e of both, the odd lane head e + 1 of both,
                 // as one 32-bit word each (no sub-word bank conflicts, half the store instructions)
                 const bool odd = lane & 1;
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const float a0 = neg ? -INFINITY : __uint_as_float(v[e]) + s_b2[hf * 32 + e];
-                    const float a1 = neg ? -INFINITY : __uint_as_float(v[e + 1]) + s_b2[hf * 32 + e + 1];
+                for (int e = 0; e < HPT; e += 2) {
+                    const float a0 = neg ? -INFINITY : __uint_as_float(v[e]) + s_b2[hf * HPT + e];
+                    const float a1 = neg ? -INFINITY : __uint_as_float(v[e + 1]) + s_b2[hf * HPT + e + 1];
                     const float got = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);      // partner's value of the head this lane stores
-                    const int h = hf * 32 + e + (odd ? 1 : 0);
+                    const int h = hf * HPT + e + (odd ? 1 : 0);
                     const float lo = odd ? got : a0, hi = odd ? a1 : got;                  // positions (r & ~1), (r | 1)
                     *reinterpret_cast<uint32_t*>(sOt + h * TQ + (r & ~1)) = pack2<TP>(lo, hi);
                 }
             } else {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int h = hf * 32 + e;
+                for (int e = 0; e < HPT; ++e) {
+                    const int h = hf * HPT + e;
                     sOt[h * TQ + r] = from_f<TP>(neg ? -INFINITY : __uint_as_float(v[e]) + s_b2[h]);
                 }
             }
