@@ -163,9 +163,12 @@ int mmdti_pair_attn_dropout_mask(uint8_t* keep, int B, int H, int L, float dropo
 /* Y = X W^T + bias (bias (N) bf16, may be NULL).                                        [in_proj forward] */
 int mmdti_gemm_bias(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* Y,
                     int64_t ldy, int M, int N, int K, void* stream);
-/* Z = X W^T + bias;  U = gelu(Z) (exact-erf GELU of the stored, bf16-rounded Z).         [fc1 forward] */
+/* Z = X W^T + bias;  U = gelu(Z) (exact-erf GELU).  store_grad == 0: Z is stored (bf16) and U is the GELU of the stored,
+ * rounded Z (what a backward that re-evaluates gelu'(Z) needs).  store_grad != 0: the Z buffer receives gelu'(z) instead
+ * (bf16), U = gelu(z) of the fp32 z: the backward then is one multiply per element (pass z_is_grad to
+ * mmdti_gemm_dgrad_gelu).                                                                [fc1 forward] */
 int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* Z,
-                         int64_t ldz, void* U, int64_t ldu, int M, int N, int K, void* stream);
+                         int64_t ldz, void* U, int64_t ldu, int M, int N, int K, int store_grad, void* stream);
 /* xo = res + dropout(X W^T + bias) (fp32, dense (M,N));  Y = LayerNorm(xo; ln_w, ln_b, eps) (bf16, dense (M,N)),
  * mean/rstd (M) saved.  ln_w == NULL: no LayerNorm (Y/mean/rstd unused).  N <= 512 (whole rows per CTA pair).
  * Dropout mask = the flat-tensor mask of mmdti_dropout_mask(seed) over (M*N).           [out_proj / fc2 forward] */
@@ -175,9 +178,10 @@ int mmdti_gemm_dropres_ln(const void* X, int64_t ldx, const void* W, int64_t ldw
 /* dX (M,K) = dY (M,N) W (N,K).                                                          [out_proj backward] */
 int mmdti_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX, int64_t lddx, int M, int N,
                      int K, void* stream);
-/* dZ (M,K) = (dY W) * gelu'(Z);  dbias (K) += column sums of the stored dZ.             [fc2 backward -> fc1 output] */
+/* dZ (M,K) = (dY W) * gelu'(Z)  (z_is_grad != 0: the Z buffer already holds gelu'(z), see mmdti_gemm_bias_gelu);
+ * dbias (K) += column sums of the stored dZ.                                             [fc2 backward -> fc1 output] */
 int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* Z, int64_t ldz,
-                          void* dZ, int64_t lddz, float* dbias, int M, int N, int K, void* stream);
+                          void* dZ, int64_t lddz, float* dbias, int M, int N, int K, int z_is_grad, void* stream);
 /* dh = dY W (M,K), K <= 512: gradient at the output of LayerNorm(x; ln_w) whose statistics are mean/rstd;
  * dx = dx_add + LayerNorm'(dh) (fp32 dense (M,K); dx_add may be NULL);  da = dropout'(dx) (bf16 dense (M,K), mask of
  * `seed` over (M*K));  dw (K) += sum_rows dh*xhat, db (K) += sum_rows dh, dbias (K) += sum_rows da.

@@ -62,6 +62,7 @@ struct GemmParams {
     uint32_t key, thresh16; float keep_scale;
     const unsigned long long* seed_off;
     int use_atomics;                         // EPI_WGRAD with ksplit > 1
+    int gelu_grad;                           // EPI_BIAS_GELU: out0 = gelu'(z) instead of z;  EPI_GELU_BWD: aux0 holds gelu'(z)
 };
 
 // keep decision of flat element idx: identical to elementwise.cu (pairs of consecutive elements share one hash)
@@ -134,8 +135,9 @@ __host__ __device__ constexpr int epi_stages(int epi) { return epi_has_input(epi
 template <int NST>
 struct SmemT {
     static constexpr uint32_t stages = 0;
-    static constexpr uint32_t ostage = NST * STAGE_BYTES;             // output slab, one per column half
-    static constexpr uint32_t istage = ostage + 2 * SLAB_BYTES;       // input slabs, two per column half (NST == 3 only)
+    static constexpr int n_out = NST == 3 ? 2 : 1;                     // output slabs per column half (double-buffered when there is room)
+    static constexpr uint32_t ostage = NST * STAGE_BYTES;
+    static constexpr uint32_t istage = ostage + 2 * n_out * SLAB_BYTES;      // input slabs, two per column half (NST == 3 only)
     static constexpr uint32_t bars = istage + (NST == 3 ? 4 * SLAB_BYTES : 0);      // mbarriers + tmem slot (256 bytes)
     static constexpr uint32_t cs = bars + 256;                        // column-sum scratch: 3 x 256 floats
     static constexpr uint32_t xchg = cs + 3 * BN * 4;                 // [2 parities][4 slots][128 rows] float2
@@ -292,12 +294,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // Coalesced output: the 128 threads of a column half write their 64-byte row segments into a swizzled shared-memory
         // slab (conflict-free), one elected thread hands the slab to the TMA (tile store, or fp32 reduce-add for the
         // split wgrad); rows / columns beyond the matrix are clipped by the TMA.
-        unsigned char* slab = smem + Smem::ostage + half * SLAB_BYTES;
+        constexpr int NOUT = Smem::n_out;
+        unsigned char* slab0 = smem + Smem::ostage + half * NOUT * SLAB_BYTES;
         const bool slab_leader = (et & 127) == 0;
+        uint32_t out_cnt = 0;                             // stores issued by this column half (uniform over its threads)
         auto half_bar = [&]() { asm volatile("bar.sync %0, 128;\n" ::"r"(2 + half) : "memory"); };
-        auto slab_store = [&](const CUtensorMap* tm, int col, int row0, const uint4 (&d)[4], bool reduce) {
-            if (slab_leader) bulk_wait_read<0>();         // the previous store has drained the slab
-            half_bar();
+        // leader: the slab the NEXT store will use (last used NOUT stores ago) has been drained by the TMA
+        auto out_acquire = [&]() { if (slab_leader) bulk_wait_read<NOUT - 1>(); };
+        // pre_synced: the caller ran out_acquire() and a half_bar() since the previous store
+        auto slab_store = [&](const CUtensorMap* tm, int col, int row0, const uint4 (&d)[4], bool reduce, bool pre_synced = false) {
+            if (!pre_synced) {
+                out_acquire();
+                half_bar();
+            }
+            unsigned char* slab = slab0 + (NOUT > 1 ? (out_cnt & 1) * SLAB_BYTES : 0);
+            ++out_cnt;
             unsigned char* rowp = slab + r * 64;
             const int sw = (r >> 1) & 3;
 #pragma unroll
@@ -384,9 +395,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         zq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         if (EPI == EPI_BIAS_GELU) {
-                            // u = gelu(z) of the ROUNDED z, the value the backward reads back
+                            if (p.gelu_grad) {
+                                // u = gelu(z) and gelu'(z) of the fp32 z: the backward multiplies by the stored derivative
+                                float gd[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = gelu_fast_val(round_bf16(f[e]));
+                                for (int e = 0; e < 8; ++e) gelu_fast_both(f[e], f[e], gd[e]);
+                                zq[g8] = make_uint4(pack_bf16(gd[0], gd[1]), pack_bf16(gd[2], gd[3]), pack_bf16(gd[4], gd[5]), pack_bf16(gd[6], gd[7]));
+                            } else {
+                                // u = gelu(z) of the ROUNDED z, the value a backward that re-evaluates gelu'(z) reads back
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = gelu_fast_val(round_bf16(f[e]));
+                            }
                             uq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
                         }
                     }
@@ -408,6 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int ci = 0; ci < NCH; ++ci) {
                     const int c0 = cb + ci * 32;
                     uint4 zq[4];
+                    out_acquire();
                     in_take(zq);
                     half_bar();                                       // everybody has read the slab: refill it
                     if (slab_leader && ci + 2 < N_IN) in_issue(&tmI0, n0 + c0 + 64, row0);
@@ -422,8 +442,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            float val, grad;
-                            gelu_fast_both(z8[e], val, grad);
+                            float val, grad = z8[e];
+                            if (!p.gelu_grad) gelu_fast_both(z8[e], val, grad);
                             f[e] = __uint_as_float(v[g8 * 8 + e]) * grad;
                         }
                         dq[g8] = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -431,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < 8; ++e) cs[g8 * 8 + e] = ok ? round_bf16(f[e]) : 0.f;      // sum what is stored
                     }
-                    slab_store(&tmO0, n0 + c0, row0, dq, false);
+                    slab_store(&tmO0, n0 + c0, row0, dq, false, true);
                     const float tot = warp_col_reduce32(cs, lane);
                     atomicAdd(&s_cs[c0 + lane], tot);
                 }
@@ -446,6 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int ci = 0; ci < 2 * NCH; ++ci) {
                     const int c0 = cb + ci * 16;
                     uint4 rq[4];
+                    out_acquire();
                     in_take(rq);                                      // 16 fp32 of the residual row
                     half_bar();
                     if (slab_leader && ci + 2 < N_IN) in_issue(&tmI0, n0 + c0 + 32, row0);
@@ -478,7 +499,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         oq[g4] = make_uint4(v[g4 * 4], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
                     }
                     if (p.ln_w) tc_st16(acc_addr + c0, v);            // parked for the normalisation pass
-                    slab_store(&tmO0, n0 + c0, row0, oq, false);      // xo
+                    slab_store(&tmO0, n0 + c0, row0, oq, false, true);      // xo
                 }
                 if (p.ln_w) {
                     // per-row sums: 2 column halves x NCTA column blocks -> every CTA of the cluster gets all partials
@@ -621,6 +642,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int c0 = cb + ci * CW;
                         uint4 aq[4];
                         if (has_add) {
+                            out_acquire();
                             in_take(aq);
                             half_bar();
                             if (slab_leader && ci + 2 < NCW) in_issue(&tmI1, n0 + c0 + 2 * CW, row0);
@@ -659,7 +681,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float2 f0 = unpack_bf16(u0), f1 = unpack_bf16(u1);
                             ad[g4 * 4] = ok ? f0.x : 0.f; ad[g4 * 4 + 1] = ok ? f0.y : 0.f; ad[g4 * 4 + 2] = ok ? f1.x : 0.f; ad[g4 * 4 + 3] = ok ? f1.y : 0.f;
                         }
-                        slab_store(&tmO0, n0 + c0, row0, dxq, false);                 // dx (fp32, 16 columns)
+                        slab_store(&tmO0, n0 + c0, row0, dxq, false, has_add);        // dx (fp32, 16 columns)
                         const float t_d = col_reduce16(ad);
                         if (lane < CW) atomicAdd(&s_cs[2 * BN + c0 + lane], t_d);
                     }
@@ -793,7 +815,7 @@ extern "C" int mmdti_gemm_bias(const void* X, int64_t ldx, const void* W, int64_
 }
 
 extern "C" int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* bias, void* Z, int64_t ldz,
-                                    void* U, int64_t ldu, int M, int N, int K, void* stream) {
+                                    void* U, int64_t ldu, int M, int N, int K, int store_grad, void* stream) {
     MMDTI_REQUIRE(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0 && bias && mmdti_aligned(bias, 16),
                   "gemm_bias_gelu: need M, N, K > 0, N, K multiples of 8 and a 16-byte aligned bias");
     if (int rc = check_ld(X, ldx, "X")) return rc;
@@ -805,6 +827,7 @@ extern "C" int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, i
     if (int rc = make_map_bf16(&tmB, W, N, K, ldw, BN)) return rc;
     GemmParams p = base_params(M, N, K);
     p.out0 = Z; p.ld0 = ldz; p.out1 = U; p.ld1 = ldu; p.bias = static_cast<const bf16*>(bias);
+    p.gelu_grad = store_grad ? 1 : 0;
     CUtensorMap tmZ, tmU;
     if (int rc = make_out_map(&tmZ, Z, M, N, ldz, false)) return rc;
     if (int rc = make_out_map(&tmU, U, M, N, ldu, false)) return rc;
@@ -857,7 +880,7 @@ extern "C" int mmdti_gemm_dgrad(const void* dY, int64_t lddy, const void* W, int
 }
 
 extern "C" int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* Z, int64_t ldz, void* dZ,
-                                     int64_t lddz, float* dbias, int M, int N, int K, void* stream) {
+                                     int64_t lddz, float* dbias, int M, int N, int K, int z_is_grad, void* stream) {
     MMDTI_REQUIRE(M > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0 && dbias, "gemm_dgrad_gelu: need M, N, K > 0, N, K multiples of 8, dbias");
     if (int rc = check_ld(dY, lddy, "dY")) return rc;
     if (int rc = check_ld(W, ldw, "W")) return rc;
@@ -868,6 +891,7 @@ extern "C" int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W
     if (int rc = make_map_bf16(&tmB, W, N, K, ldw, BK)) return rc;
     GemmParams p = base_params(M, K, N);
     p.out0 = dZ; p.ld0 = lddz; p.aux0 = Z; p.ldaux0 = ldz; p.colsum0 = dbias;
+    p.gelu_grad = z_is_grad ? 1 : 0;
     CUtensorMap tmDZ, tmZ;
     if (int rc = make_out_map(&tmDZ, dZ, M, K, lddz, false)) return rc;
     if (int rc = make_out_map(&tmZ, Z, M, K, ldz, false)) return rc;

@@ -481,8 +481,11 @@ class EncoderLayerFn(torch.autograd.Function):
             st2 = torch.empty((2, rows), device=x.device, dtype=torch.float32)
             call("mmdti_dropres_layernorm_fwd", x2d, a, x1, ln2_wd, ln2_bd, h2, st2[0], st2[1], i32(rows), i32(D), f32(1e-5),
                  f32(p_drop), u64(seeds[1]), i32(code), i32(code), sp)
+        # with both fc1 and its backward on the fused GEMMs the forward stores gelu'(z) in place of z: the backward
+        # epilogue then is one multiply per element instead of re-evaluating erf / exp on every element
+        z_is_grad = "fc1" in fz and "dfc2" in fz
         if "fc1" in fz:
-            z, u = ops_gemm.gemm_bias_gelu(h2, w_fc1_l, b_fc1_l)
+            z, u = ops_gemm.gemm_bias_gelu(h2, w_fc1_l, b_fc1_l, store_grad=z_is_grad)
         else:
             z = torch.addmm(b_fc1_l, h2, w_fc1_l.t())
             u = torch.empty_like(z)
@@ -509,6 +512,7 @@ class EncoderLayerFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.chain = (chain_in, chain_out)
         ctx.fz = fz
+        ctx.z_is_grad = z_is_grad
         ctx.links = (link_in if chain_in else None, link_out if chain_out else None)
         if chain_out and link_out is not None:
             link_out["p"], link_out["seed"] = p_drop, seeds[2]
@@ -583,7 +587,7 @@ class EncoderLayerFn(torch.autograd.Function):
         wgrad = (lambda dy, xin: ops_gemm.gemm_wgrad(dy, xin)) if "wgrad" in fz else (lambda dy, xin: _mm_f32(dy.t(), xin))
         dW_fc2 = off_path(lambda: wgrad(df, u))
         if "dfc2" in fz:
-            dz = ops_gemm.gemm_dgrad_gelu(df, w_fc2_l, z, db_fc1)          # fc2 dgrad + GELU' + db_fc1 column sums
+            dz = ops_gemm.gemm_dgrad_gelu(df, w_fc2_l, z, db_fc1, z_is_grad=ctx.z_is_grad)      # fc2 dgrad + GELU' + db_fc1 column sums
         else:
             du = torch.mm(df, w_fc2_l)
             dz = torch.empty_like(z)

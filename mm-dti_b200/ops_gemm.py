@@ -29,14 +29,15 @@ def gemm_bias(x, w, bias, out=None):
     return y
 
 
-def gemm_bias_gelu(x, w, bias):
-    """-> (z, u): z = x w^T + bias, u = gelu(z)"""
+def gemm_bias_gelu(x, w, bias, store_grad=False):
+    """-> (z, u): z = x w^T + bias, u = gelu(z); store_grad=True: the first result is gelu'(z) instead of z"""
     _chk(x, w, bias)
     M, K = x.shape
     N = w.shape[0]
     z = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
     u = torch.empty_like(z)
-    call("mmdti_gemm_bias_gelu", x, i64(x.stride(0)), w, i64(w.stride(0)), bias, z, i64(N), u, i64(N), i32(M), i32(N), i32(K), stream_ptr())
+    call("mmdti_gemm_bias_gelu", x, i64(x.stride(0)), w, i64(w.stride(0)), bias, z, i64(N), u, i64(N), i32(M), i32(N), i32(K),
+         i32(1 if store_grad else 0), stream_ptr())
     return z, u
 
 
@@ -67,14 +68,14 @@ def gemm_dgrad(dy, w, out=None):
     return dx
 
 
-def gemm_dgrad_gelu(dy, w, z, dbias):
-    """dz = (dy @ w) * gelu'(z); dbias += colsum(dz)"""
+def gemm_dgrad_gelu(dy, w, z, dbias, z_is_grad=False):
+    """dz = (dy @ w) * gelu'(z); dbias += colsum(dz).  z_is_grad=True: ``z`` already holds gelu'(z)"""
     _chk(dy, w, z)
     M, N = dy.shape
     K = w.shape[1]
     dz = torch.empty((M, K), device=dy.device, dtype=torch.bfloat16)
     call("mmdti_gemm_dgrad_gelu", dy, i64(dy.stride(0)), w, i64(w.stride(0)), z, i64(z.stride(0)), dz, i64(K), dbias, i32(M), i32(N), i32(K),
-         stream_ptr())
+         i32(1 if z_is_grad else 0), stream_ptr())
     return dz
 
 

@@ -1,5 +1,3 @@
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_hotpath_n1.json 2> gpurun_out/r2_bench_hotpath_n1.err; echo "hotpath rc=$? $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_hotpath_n1.json'));print(d['ms_per_step'], d['value'], d['e2e']['value'])")"
-python bench.py --workload encoder --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_encoder_n1.json 2> gpurun_out/r2_bench_encoder_n1.err; echo "encoder rc=$? $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_encoder_n1.json'));print(d['ms_per_step'], d['value'])")"
-python bench.py --workload config4 --steps 10 --warmup 3 --cpu-sample 4 > gpurun_out/r2_bench_config4_n1.json 2> gpurun_out/r2_bench_config4_n1.err; echo "config4 rc=$? $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_config4_n1.json'));print(d['ms_per_step'], d['value'])")"
-python bench.py --workload config5 --steps 10 --warmup 3 > gpurun_out/r2_bench_config5.json 2> gpurun_out/r2_bench_config5.err; echo "config5 rc=$? $(python -c "import json;d=json.load(open('gpurun_out/r2_bench_config5.json'));print(d['value'], d['roofline']['frac'])")"
+timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_elementwise.py tests/test_gpu_encoder.py -x -q 2>&1 | tail -3
+timeout 200 python scripts/probe_gemm.py --only "fc" 2>&1 | tail -8
+python bench.py --workload encoder --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b_all.json 2> gpurun_out/b_all.err; echo "encoder rc=$? $(python -c "import json;d=json.load(open('gpurun_out/b_all.json'));print(d['ms_per_step'])")"

@@ -65,6 +65,8 @@ cases = {
     "fc2+dropres+LN (8448x512x2048)": (lambda: ops_gemm.gemm_dropres_ln(u, w2, b2, res, ln_w, ln_b, 0.1, 5), lambda: torch.addmm(b2, u, w2.t()), 2 * M * D * Fd),
     "dgrad out      (8448x512x512)": (lambda: ops_gemm.gemm_dgrad(x, w_out), lambda: torch.mm(x, w_out), 2 * M * D * D),
     "dgrad fc2+gelu'(8448x2048x512)": (lambda: ops_gemm.gemm_dgrad_gelu(x, w2, z, dbf), lambda: torch.mm(x, w2), 2 * M * D * Fd),
+    "dgrad fc2 * stored gelu'      ": (lambda: ops_gemm.gemm_dgrad_gelu(x, w2, z, dbf, z_is_grad=True), lambda: torch.mm(x, w2), 2 * M * D * Fd),
+    "fc1+gelu+gelu' fwd            ": (lambda: ops_gemm.gemm_bias_gelu(x, w1, b1, store_grad=True), lambda: torch.addmm(b1, x, w1.t()), 2 * M * Fd * D),
     "dgrad fc1+LN'  (8448x512x2048)": (lambda: ops_gemm.gemm_dgrad_lnbwd(u, w1, res, stats, ln_w, res, dw, db, dbias, 0.1, 5), lambda: torch.mm(u, w1), 2 * M * D * Fd),
     "dgrad in+LN'   (8448x512x1536)": (lambda: ops_gemm.gemm_dgrad_lnbwd(dqkv, w_in, res, stats, ln_w, res, dw, db, dbias, 0.1, 5), lambda: torch.mm(dqkv, w_in), 2 * M * D * D3),
     "wgrad fc2      (512x2048x8448)": (lambda: ops_gemm.gemm_wgrad(x, u), lambda: torch.mm(x.t(), u, out_dtype=torch.float32), 2 * M * D * Fd),

@@ -45,7 +45,13 @@ def test_forward_gemms(M, D, D3, Fd, report):
     zw = x.float() @ w1.float().t() + b1.float()
     e2 = _close(z, zw, 6e-3, "fc1.z")
     e3 = _close(u, F.gelu(z.float()), 6e-3, "fc1.u (gelu of the stored z)")
-    report("gemm_fwd", (M, D, D3, Fd), "bias=%.1e z=%.1e u=%.1e" % (e1, e2, e3))
+    # store_grad: the first buffer receives gelu'(z) (what the fused backward multiplies by), u = gelu of the fp32 z
+    gp, u2 = ops_gemm.gemm_bias_gelu(x, w1, b1, store_grad=True)
+    zr = zw.clone().requires_grad_(True)
+    F.gelu(zr).sum().backward()
+    e4 = _close(gp, zr.grad, 6e-3, "fc1.gelu'")
+    e5 = _close(u2, F.gelu(zw), 6e-3, "fc1.u (gelu of the fp32 z)")
+    report("gemm_fwd", (M, D, D3, Fd), "bias=%.1e z=%.1e u=%.1e gelu'=%.1e u2=%.1e" % (e1, e2, e3, e4, e5))
 
 
 @pytest.mark.parametrize("p", [0.0, 0.1])
@@ -93,6 +99,14 @@ def test_backward_gemms(M, D, D3, Fd, report):
     F.gelu(zf).backward(df.float() @ w2.float())
     e2 = _close(dz, zf.grad, 6e-3, "dgrad_gelu")
     e3 = _close(dbias, dz.float().sum(0), 2e-4, "dgrad_gelu.dbias == colsum of the stored dz")
+    # z_is_grad: the buffer already holds gelu'(z)
+    gp = zf.grad.new_tensor(0)          # placeholder
+    zg = z.float().clone().requires_grad_(True)
+    F.gelu(zg).sum().backward()
+    dbias2 = torch.zeros(Fd, device="cuda")
+    dz2 = ops_gemm.gemm_dgrad_gelu(df, w2, zg.grad.bfloat16(), dbias2, z_is_grad=True)
+    _close(dz2, (df.float() @ w2.float()) * zg.grad.bfloat16().float(), 6e-3, "dgrad_gelu with the stored derivative")
+    _close(dbias2, dz2.float().sum(0), 2e-4, "dgrad_gelu(z_is_grad).dbias")
     # wgrad: fp32, split over the tokens; plain and accumulating
     h = _rand((M, D), 26).bfloat16()
     dw = ops_gemm.gemm_wgrad(dz, h)
