@@ -304,6 +304,8 @@ def run_ours(args, rank, local_rank, world):
     model = UnimolEncoder().to(dev).train()
     step_model = model
     use_graph = not args.no_graph
+    # gradients travel as bf16 by default (MMDTI_GRAD_COMM=fp32 keeps fp32 buckets)
+    COMM_DTYPE = None if os.environ.get("MMDTI_GRAD_COMM", "bf16") == "fp32" else torch.bfloat16
     if dist_on and not use_graph:
         from torch.nn.parallel import DistributedDataParallel as DDP
         step_model = DDP(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=64)
@@ -319,7 +321,8 @@ def run_ours(args, rank, local_rank, world):
             + list(model.encoder.emb_layer_norm.parameters())
         if task is None:
             reducer = OverlappedGradReducer(model.parameters(), average=True, tail_params=late, keep_flat=not args.torch_adam,
-                                            bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
+                                            bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20,
+                                            comm_dtype=COMM_DTYPE)
 
     hot = task is not None
     extra_params = []
@@ -350,7 +353,8 @@ def run_ours(args, rank, local_rank, world):
         if dist_on and use_graph:
             reducer = OverlappedGradReducer(list(model.parameters()) + extra_params, average=True, tail_params=late,
                                             keep_flat=not args.torch_adam,
-                                            bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20)
+                                            bucket_bytes=int(os.environ.get("MMDTI_BUCKET_MB", "32")) << 20,
+                                            comm_dtype=COMM_DTYPE)
         elif dist_on:
             raise SystemExit("--workload hotpath at N > 1 needs the graphed step (drop --no-graph)")
 
@@ -524,7 +528,8 @@ def run_ours(args, rank, local_rank, world):
                        "inputs": ("src_tokens + src_distance + src_edge_type (reference batch format)" if args.inputs == "pair"
                                   else "src_tokens + src_coord (pair features computed on the device, mmdti_featurise)"),
                        "parallelism": "dp%d" % world,
-                       "grad_exchange": (None if world == 1 else ("bucketed NCCL all-reduce (32 MB) overlapped with the backward, inside the graph" if use_graph
+                       "grad_exchange": (None if world == 1 else (("bucketed NCCL all-reduce (32 MB of parameters per bucket, %s on the wire) overlapped with the backward, inside the graph"
+                                                                   % os.environ.get("MMDTI_GRAD_COMM", "bf16")) if use_graph
                                                                   else "DistributedDataParallel (NCCL)")),
                        "l2": "no flush: the per-step working set (15 x %.0f MB pair tensors + activations) exceeds the 126 MB L2"
                              % (nel * esz / 1e6)},

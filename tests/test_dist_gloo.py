@@ -101,6 +101,19 @@ def _worker(rank, world, port, q):
             assert torch.allclose(red3.reduced_grad(prm) * red3.grad_scale, t_ / world, atol=1e-6)
             assert torch.equal(prm.grad, lg)
             assert red3.reduced_grad(prm).data_ptr() % 16 == 0
+        red3.remove()
+        # bf16 wire format: the bucket travels as bf16 (half the bytes), the reduced gradient comes back as fp32 and equals
+        # the sum of the bf16-rounded local gradients up to one bf16 rounding of the sum
+        red4 = OverlappedGradReducer(net3.parameters(), average=True, bucket_bytes=256, keep_flat=True, comm_dtype=torch.bfloat16)
+        for prm in net3.parameters():
+            prm.grad = None
+        net3(x).sum().backward()
+        red4.finish()
+        for t_, prm in zip(tot, net3.parameters()):
+            got = red4.reduced_grad(prm) * red4.grad_scale
+            assert got.dtype == torch.float32
+            assert torch.allclose(got, t_ / world, rtol=2e-2, atol=2e-2 * float(t_.abs().max() / world) + 1e-6)
+        red4.remove()
         q.put((rank, "ok"))
     except Exception as e:                                       # noqa: BLE001
         q.put((rank, "fail: %r" % (e,)))
