@@ -138,16 +138,45 @@ def _rownorm_bwd(g, op, dx, scale, gscale, accumulate=False):
          f32(EPS), i32(1 if accumulate else 0), stream_ptr())
 
 
-def _gather_operand(op, dp):
-    """all-gather a normalised operand over the data-parallel group (rank-major rows)."""
+def _gather_packed(dp, tensors):
+    """ONE all-gather for several per-row tensors (M, ...) of any dtypes: their rows are packed side by side into a byte
+    matrix, gathered rank-major, and unpacked again.  Exchange 1 is latency-bound (a few MB over NVSwitch), so the number
+    of collectives, not their size, is what the step pays for.  None entries pass through."""
+    live = [(i, t) for i, t in enumerate(tensors) if t is not None]
+    M = live[0][1].shape[0]
+    parts, meta = [], []
+    for i, t in live:
+        t2 = t.contiguous().view(M, -1)
+        b = t2.view(torch.uint8)
+        pad = (-b.shape[1]) % 16                      # 16-byte aligned columns: every unpacked view is aligned
+        parts.append(b if pad == 0 else torch.nn.functional.pad(b, (0, pad)))
+        meta.append((i, t.dtype, tuple(t.shape[1:]), b.shape[1]))
+    packed = torch.cat(parts, dim=1)
+    gathered = dp.all_gather_rows(packed)
+    out = [None] * len(tensors)
+    off = 0
+    for (i, dt, tail, nbytes), part in zip(meta, parts):
+        col = gathered[:, off:off + nbytes].contiguous().view(dt)
+        out[i] = col.view((gathered.shape[0],) + tail)
+        off += part.shape[1]
+    return out
+
+
+def _gather_operands(ops, dp, extra=()):
+    """all-gather normalised operands (and extra per-row tensors) over the data-parallel group in ONE collective."""
     if dp is None or dp.world == 1:
-        return op
-    g = _Operand()
-    g.N, g.D, g.Dp = op.N * dp.world, op.D, op.Dp
-    g.f32 = dp.all_gather_rows(op.f32) if op.f32 is not None else None
-    g.bf16 = dp.all_gather_rows(op.bf16) if op.bf16 is not None else None
-    g.inv_norm = dp.all_gather_rows(op.inv_norm)
-    return g
+        return list(ops), list(extra)
+    flat = []
+    for op in ops:
+        flat += [op.f32, op.bf16, op.inv_norm]
+    got = _gather_packed(dp, flat + list(extra))
+    res = []
+    for k, op in enumerate(ops):
+        g = _Operand()
+        g.N, g.D, g.Dp = op.N * dp.world, op.D, op.Dp
+        g.f32, g.bf16, g.inv_norm = got[3 * k], got[3 * k + 1], got[3 * k + 2]
+        res.append(g)
+    return res, got[3 * len(ops):]
 
 
 def _use_tc(D):
@@ -175,7 +204,7 @@ class InfoNCEFn(torch.autograd.Function):
         off = 0 if dp is None else dp.rank * M
         qo = normalize_rows(q, True, use_tc)
         po = normalize_rows(p, True, use_tc)
-        qg, pg = _gather_operand(qo, dp), _gather_operand(po, dp)
+        (qg, pg), _ = _gather_operands([qo, po], dp)          # exchange 1: one collective for both modalities
         st_r = sim_stats(INFONCE, qo, pg, off, temperature, {}, use_tc)      # rows of  q̂ p̂ᵀ
         st_c = sim_stats(INFONCE, po, qg, off, temperature, {}, use_tc)      # rows of  p̂ q̂ᵀ  = columns of the above
         coef = (0.5 / N) if reduction == "mean" else 0.5
@@ -184,8 +213,10 @@ class InfoNCEFn(torch.autograd.Function):
         call("mmdti_infonce_finalize", st_r, lse[0], loss, i32(M), f32(temperature), f32(coef), stream_ptr())
         call("mmdti_infonce_finalize", st_c, lse[1], loss, i32(M), f32(temperature), f32(coef), stream_ptr())
         if world > 1:
-            lse_g = torch.stack([dp.all_gather_rows(lse[0]), dp.all_gather_rows(lse[1])])
-            loss = dp.all_reduce_sum(loss)
+            # one collective for both log-sum-exp vectors and the loss partials (third column, constant per rank)
+            got = dp.all_gather_rows(torch.stack([lse[0], lse[1], loss.expand(M)], dim=1).contiguous())
+            lse_g = got[:, :2].t().contiguous()
+            loss = got[:, 2].view(world, M)[:, 0].sum()
         else:
             lse_g = lse
         ctx.ops = (qo, po, qg, pg)
@@ -231,19 +262,21 @@ class ContrastiveFn(torch.autograd.Function):
         N = M * world
         off = 0 if dp is None else dp.rank * M
         fo = normalize_rows(f, True, use_tc)
-        fg = _gather_operand(fo, dp)
         lab = dict(lab_local)
+        names = ("y", "yhat", "key", "wrow", "wcol")
+        (fg,), extra = _gather_operands([fo], dp, [lab.get(k) for k in names])      # features + labels: one collective
         if world > 1:
-            for k in ("y", "yhat", "key", "wrow", "wcol"):
-                if lab.get(k) is not None:
-                    lab[k] = dp.all_gather_rows(lab[k])
+            for k, v in zip(names, extra):
+                if v is not None:
+                    lab[k] = v
         st = sim_stats(mode, fo, fg, off, temperature, lab, use_tc)
         rowstat = torch.empty((M, 2), device=f.device, dtype=torch.float32)
         loss = torch.zeros((), device=f.device, dtype=torch.float32)
         call("mmdti_ct_finalize", st, rowstat, loss, i32(M), i32(N), i32(mode), f32(lab.get("w", 0.0)), stream_ptr())
         if world > 1:
-            rowstat_g = dp.all_gather_rows(rowstat)
-            loss = dp.all_reduce_sum(loss)
+            got = dp.all_gather_rows(torch.cat([rowstat, loss.expand(M, 1)], dim=1).contiguous())
+            rowstat_g = got[:, :2].contiguous()
+            loss = got[:, 2].view(world, M)[:, 0].sum()
         else:
             rowstat_g = rowstat
         ctx.ops = (fo, fg, lab)
