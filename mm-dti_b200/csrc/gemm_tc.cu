@@ -63,6 +63,7 @@ struct GemmParams {
     const unsigned long long* seed_off;
     int use_atomics;                         // EPI_WGRAD with ksplit > 1
     int gelu_grad;                           // EPI_BIAS_GELU: out0 = gelu'(z) instead of z;  EPI_GELU_BWD: aux0 holds gelu'(z)
+    int* sched;                              // NCTA == 1: {next item, CTAs done} of the dynamic tile scheduler (self-resetting)
 };
 
 // keep decision of flat element idx: identical to elementwise.cu (pairs of consecutive elements share one hash)
@@ -162,7 +163,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty = tfull + 2;             // [2]
     uint64_t* xbar = tempty + 2;              // [2]
     uint64_t* inbar = xbar + 2;               // [2 halves][2 buffers]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 4);
+    uint64_t* sfull = inbar + 4;              // [4] tile-scheduler ring: item published
+    uint64_t* sempty = sfull + 4;             // [4] item consumed by the MMA thread and every epilogue thread
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 4);
+    volatile int* s_item = reinterpret_cast<volatile int*>(tmem_slot + 1);      // [4]
     float* s_cs = reinterpret_cast<float*>(smem + Smem::cs);
     float2* s_x = reinterpret_cast<float2*>(smem + Smem::xchg);
     float* s_vec = reinterpret_cast<float*>(smem + Smem::vec);
@@ -178,7 +182,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&tempty[i], NUM_EPI_THREADS);
             mbar_init(&xbar[i], NCTA * NUM_EPI_THREADS);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(&inbar[i], 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&inbar[i], 1);
+            mbar_init(&sfull[i], 1);
+            mbar_init(&sempty[i], 1 + NUM_EPI_THREADS);
+        }
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < 3 * BN; i += NUM_THREADS) s_cs[i] = 0.f;
@@ -193,11 +201,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (NCTA > 1) cluster_sync_all();      // the peer's barriers exist before anybody arrives on them remotely
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- work items of this CTA.  NCTA == 1: item = (tile, k split), tile = m_blk * tiles_n + n_blk, strided over the
-    // grid.  NCTA == 2: the cluster walks row stripes, CTA rank = column half.
+    // ---- work items.  NCTA == 1: item = (tile, k split), tile = m_blk * tiles_n + n_blk, handed out DYNAMICALLY: the
+    // producer thread takes the next item from a global counter and publishes it to the MMA and epilogue warps through a
+    // 4-slot ring, so CTAs that start late (SMs held by a kernel of another stream: the weight-gradient GEMMs, NCCL) simply
+    // take fewer items instead of delaying the whole kernel.  NCTA == 2: the cluster walks row stripes statically, CTA rank
+    // = column half.
     const int n_items = NCTA == 1 ? p.tiles_m * p.tiles_n * p.ksplit : p.tiles_m;
-    const int item0 = NCTA == 1 ? (int)blockIdx.x : (int)(blockIdx.x / NCTA);
-    const int item_step = NCTA == 1 ? (int)gridDim.x : (int)(gridDim.x / NCTA);
+    const int item0 = (int)(blockIdx.x / NCTA);
+    const int item_step = (int)(gridDim.x / NCTA);
+    // consumer side of the scheduler ring: item of iteration `it` (or >= n_items: no more work)
+    auto next_item = [&](int it) -> int {
+        if (NCTA != 1) return item0 + it * item_step;
+        const int sl = it & 3;
+        mbar_wait_g(&sfull[sl], (it >> 2) & 1);
+        const int item = s_item[sl];
+        mbar_arrive(&sempty[sl]);
+        return item;
+    };
     auto decode = [&](int item, int& m_blk, int& n_blk, int& kc0, int& kc1) {
         if (NCTA == 1) {
             const int tile = item / p.ksplit, ks = item - tile * p.ksplit;
@@ -218,7 +238,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int st = 0, par = 1;
             bool wrapped = false;
-            for (int item = item0; item < n_items; item += item_step) {
+            for (int it = 0;; ++it) {
+                int item;
+                if (NCTA == 1) {
+                    const int sl = it & 3;
+                    if (it >= 4) mbar_wait_g(&sempty[sl], ((it >> 2) - 1) & 1);
+                    item = atomicAdd(p.sched, 1);
+                    s_item[sl] = item;
+                    mbar_arrive(&sfull[sl]);                  // release: the item is visible to whoever acquires the barrier
+                } else {
+                    item = item0 + it * item_step;
+                }
+                if (item >= n_items) break;
                 int m_blk, n_blk, kc0, kc1;
                 decode(item, m_blk, n_blk, kc0, kc1);
                 for (int kc = kc0; kc < kc1; ++kc) {
@@ -253,8 +284,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr uint32_t b_kstep = BMN ? (16 * 128) >> 4 : 32 >> 4;
             int st = 0;
             uint32_t par = 0;
-            int it = 0;
-            for (int item = item0; item < n_items; item += item_step, ++it) {
+            for (int it = 0;; ++it) {
+                const int item = next_item(it);
+                if (item >= n_items) break;
                 int m_blk, n_blk, kc0, kc1;
                 decode(item, m_blk, n_blk, kc0, kc1);
                 const int buf = DOUBLE_ACC ? (it & 1) : 0;
@@ -341,8 +373,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 4; ++j) d[j] = *reinterpret_cast<const uint4*>(rowp + ((j ^ sw) << 4));
             ++in_read;
         };
-        int it = 0;
-        for (int item = item0; item < n_items; item += item_step, ++it) {
+        for (int it = 0;; ++it) {
+            const int item = next_item(it);
+            if (item >= n_items) break;
             int m_blk, n_blk, kc0, kc1;
             decode(item, m_blk, n_blk, kc0, kc1);
             const int buf = DOUBLE_ACC ? (it & 1) : 0;
@@ -702,6 +735,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp >= 2 && ((threadIdx.x - 64) & 127) == 0) bulk_wait_all<0>();      // outstanding TMA stores of this column half
     __syncthreads();
+    if (NCTA == 1 && threadIdx.x == 0) {
+        // the last CTA to finish re-arms the scheduler counters for the next launch that uses this slot
+        if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+    }
     __syncwarp();
     if (NCTA > 1) cluster_sync_all();          // nobody leaves while the peer may still address this CTA's shared memory
     if (warp == 1) {
@@ -734,6 +771,21 @@ int make_out_map(CUtensorMap* map, const void* base, long long rows, long long c
     return make_map_2d(map, base, rows, cols, ld, fp32 ? 4 : 2, fp32 ? 16 : 32, BM, 64);
 }
 
+// Scheduler counters: a zero-initialised ring of {next item, CTAs done} pairs in device memory, one pair per launch.  The
+// kernel re-arms its pair when its last CTA retires, so a CUDA-graph replay (which re-runs the same launch with the same
+// pair) finds it zeroed; the ring is long enough that a pair is never shared by two launches in flight.
+int* sched_slot() {
+    constexpr int SLOTS = 16384;
+    static int* base[MMDTI_MAX_DEVICES] = {};
+    static unsigned next[MMDTI_MAX_DEVICES] = {};
+    const int dev = mmdti_device_slot();
+    if (!base[dev]) {
+        if (cudaMalloc(&base[dev], SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(base[dev], 0, SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    }
+    return base[dev] + 2 * (next[dev]++ % SLOTS);
+}
+
 template <int AMN, int BMN, int EPI, int NCTA>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st, const CUtensorMap* tmO0 = nullptr,
            const CUtensorMap* tmO1 = nullptr, const CUtensorMap* tmI0 = nullptr, const CUtensorMap* tmI1 = nullptr) {
@@ -758,6 +810,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaSt
         const long long items = (long long)p.tiles_m * p.tiles_n * p.ksplit;
         cfg.gridDim = dim3((unsigned)std::min<long long>(items, sms));
         cfg.numAttrs = 0;
+        p.sched = sched_slot();
+        MMDTI_REQUIRE(p.sched != nullptr, "gemm_tc: could not allocate the scheduler counters");
     } else {
         MMDTI_REQUIRE(p.tiles_n == NCTA, "gemm_tc: the LayerNorm epilogue needs N = %d..%d columns for a %d-CTA cluster (N = %d)",
                       (NCTA - 1) * BN + 1, NCTA * BN, NCTA, p.N);
