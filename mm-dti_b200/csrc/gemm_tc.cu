@@ -67,7 +67,12 @@ struct GemmParams {
 };
 
 // keep decision of flat element idx: identical to elementwise.cu (pairs of consecutive elements share one hash)
-__device__ __forceinline__ uint32_t ew_bits(uint32_t key, unsigned long long idx) {
+//   bits(idx) = mix32(key ^ lo32(idx >> 1) ^ mix32(hi32(idx >> 1) + 0x27d4eb2f))
+// Tensors of fewer than 2^33 elements (every case of this model) have hi32 == 0: the inner hash is a constant that is
+// folded into the key once per thread (ew_fold_key), one avalanche hash per element pair instead of two.
+__device__ __forceinline__ uint32_t ew_fold_key(uint32_t key) { return key ^ mix32(0x27d4eb2fU); }
+__device__ __forceinline__ uint32_t ew_bits_folded(uint32_t fkey, unsigned long long idx) { return mix32(fkey ^ (uint32_t)(idx >> 1)); }
+__device__ __forceinline__ uint32_t ew_bits_full(uint32_t key, unsigned long long idx) {
     const unsigned long long pr = idx >> 1;
     return mix32(key ^ (uint32_t)pr ^ mix32((uint32_t)(pr >> 32) + 0x27d4eb2fU));
 }
@@ -321,8 +326,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int HC = BN / 2;                        // columns per epilogue thread
         constexpr int NCH = HC / 32;                      // 32-column chunks per thread
         constexpr bool HAS_VEC = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_DROPRES_LN || EPI == EPI_LNBWD_DROP;
-        uint32_t key = 0;
-        if (EPI == EPI_DROPRES_LN || EPI == EPI_LNBWD_DROP) key = p.thresh16 ? rng_effective_key(p.key, p.seed_off) : 0u;
+        uint32_t key = 0, fkey = 0;
+        if (EPI == EPI_DROPRES_LN || EPI == EPI_LNBWD_DROP) {
+            key = p.thresh16 ? rng_effective_key(p.key, p.seed_off) : 0u;
+            fkey = ew_fold_key(key);
+        }
+        const bool small_idx = (unsigned long long)p.tiles_m * BM * (unsigned long long)p.N < (1ull << 33);      // incl. the clipped rows of the last tile
+        auto ew_bits = [&](uint32_t, unsigned long long idx) -> uint32_t {
+            return small_idx ? ew_bits_folded(fkey, idx) : ew_bits_full(key, idx);
+        };
         // Coalesced output: the 128 threads of a column half write their 64-byte row segments into a swizzled shared-memory
         // slab (conflict-free), one elected thread hands the slab to the TMA (tile store, or fp32 reduce-add for the
         // split wgrad); rows / columns beyond the matrix are clipped by the TMA.

@@ -332,8 +332,9 @@ def ct_single(feature, depth, output=None, weights=None, t=0.07, dp=None):
     if key.shape[1] != 1:
         raise _lib.MMDTIError("CT_Single expects one label per sample (got %d); use CT_Multi" % key.shape[1])
     if key.dtype.is_floating_point:
-        # label equality on floats == equality of the bit patterns except +-0 / NaN; class labels are integral
-        key = key.double().view(torch.int64) if (key != key.round()).any() else key.long()
+        # label equality on floats == equality of the float64 bit patterns once -0.0 is folded into +0.0 (NaN labels, which
+        # the reference's == never matches, are not supported); no host synchronisation: the step must stay graph-capturable
+        key = (key.double() + 0.0).view(torch.int64)
     lab = {"key": key.long().contiguous(), "C": 1}
     lab["wrow"], lab["wcol"] = _weights_factors(weights, n, feature.device)
     return ContrastiveFn.apply(feature, SINGLE, lab, float(t), dp)
@@ -344,7 +345,7 @@ def ct_multi(feature, depth, output=None, weights=None, t=0.07, coef=1, dp=None)
     key = depth.detach().reshape(n, -1)
     C = key.shape[1]
     if key.dtype.is_floating_point:
-        key = key.double().view(torch.int64) if (key != key.round()).any() else key.long()
+        key = (key.double() + 0.0).view(torch.int64)
     lab = {"key": key.long().contiguous(), "C": C, "coef": float(coef)}
     lab["wrow"], lab["wcol"] = _weights_factors(weights, n, feature.device)
     return ContrastiveFn.apply(feature, MULTI, lab, float(t), dp)
