@@ -304,6 +304,12 @@ def run_ours(args, rank, local_rank, world):
     model = UnimolEncoder().to(dev).train()
     step_model = model
     use_graph = not args.no_graph
+    if world == 1 and B_PER_GPU * L > 150000 and use_graph:
+        # config 3 on ONE GPU: 4096 molecules x 66 tokens keep ~120 GB of activations alive for the backward; a captured
+        # graph holds them in its private pool on top of the warm-up's, which does not fit in 180 GB.  At this size every
+        # kernel runs for hundreds of microseconds, so launching from the host costs nothing.
+        use_graph = False
+        print("[bench] per-GPU batch %d: running without CUDA-graph capture (activation memory)" % B_PER_GPU, file=sys.stderr)
     # gradients travel as bf16 by default (MMDTI_GRAD_COMM=fp32 keeps fp32 buckets)
     COMM_DTYPE = None if os.environ.get("MMDTI_GRAD_COMM", "bf16") == "fp32" else torch.bfloat16
     if dist_on and not use_graph:

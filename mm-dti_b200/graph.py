@@ -62,6 +62,7 @@ class GraphedStep:
             for p in params:
                 p.grad = None
         self.params = list(params) if params is not None else None
+        torch.cuda.empty_cache()          # the warm-up's cached blocks would sit next to the graph's private pool
         n0 = _lib.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):

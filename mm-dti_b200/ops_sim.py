@@ -315,7 +315,12 @@ def _weights_factors(weights, n, device):
     (N,) -> along columns, (N,1) -> along rows.  Returns (wrow, wcol, constant)."""
     if weights is None:
         return None, None
-    wt = torch.as_tensor(weights).detach().to(device=device, dtype=torch.float32)
+    wt = torch.as_tensor(weights).detach()
+    if wt.numel() == 1 and not wt.is_cuda:
+        # the reference's default ``weights=tensor([1])`` lives on the host: read it there (no host-to-device copy, which
+        # a CUDA-graph capture would refuse) and fill the constant on the device
+        return torch.full((n,), float(wt.reshape(()).item()), device=device, dtype=torch.float32), None
+    wt = wt.to(device=device, dtype=torch.float32)
     if wt.numel() == 1:
         c = wt.reshape(1).expand(n).contiguous()
         return c, None
