@@ -337,13 +337,16 @@ int mmdti_fds_bin(const float* labels, int64_t ld, int N, float min_value, float
                   int bucket_start, int bucket_num, int32_t* bins, int32_t* present, void* stream);
 /* FDS.smooth (models/fds.py:157-190): x (N,D) f32 row stride ldx, IN PLACE:
  * x = (x - m1[b]) * sqrt(clamp(v2[b]/v1[b], .1, 10)) + m2[b] per calibrate_mean_var's three branches.
- * m1,v1 = running_{mean,var}_last_epoch, m2,v2 = smoothed_{mean,var}_last_epoch (nb, D). */
+ * m1,v1 = running_{mean,var}_last_epoch, m2,v2 = smoothed_{mean,var}_last_epoch (nb, D).
+ * work: optional caller-provided scratch of (3*nb*D + nb) floats, 16-byte aligned (nb = bucket_num - bucket_start): with it
+ * (and D, ldx multiples of 4) the per-bucket factors are tabulated once and the per-sample pass is vectorised; NULL selects
+ * the scalar kernel.  Same results either way. */
 int mmdti_fds_smooth_fwd(float* x, int64_t ldx, const int32_t* bins, const int32_t* present, int N,
                          int D, int bucket_start, int bucket_num, const float* m1, const float* v1,
-                         const float* m2, const float* v2, void* stream);
+                         const float* m2, const float* v2, float* work, void* stream);
 int mmdti_fds_smooth_bwd(const float* dy, float* dx, const int32_t* bins, const int32_t* present,
                          int N, int D, int bucket_start, int bucket_num, const float* v1,
-                         const float* v2, void* stream);
+                         const float* v2, float* work, void* stream);
 /* FDS.update_running_stats (models/fds.py:116-155) in four steps so that data-parallel ranks can
  * all-reduce {count, sum1} and {m2} in between:
  *   group:       rows grouped by bucket -> seg (nb+1) offsets, order (N) row indices, count (nb) f32

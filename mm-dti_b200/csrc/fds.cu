@@ -114,6 +114,137 @@ __global__ void __launch_bounds__(1024) fds_group_kernel(const int* __restrict__
     }
 }
 
+// Parallel, STABLE counting sort (nb <= 256): every warp owns a contiguous row range, counts its rows per bucket,
+// a scan over (bucket, warp) gives each warp its write cursor per bucket, and the warp scatters its rows in ascending
+// order -- lanes of a 32-row step that share a bucket rank themselves with __match_any_sync.  Same `order` as the serial
+// form above (ascending rows inside a bucket), ~200x faster at epoch sizes.
+constexpr int GROUP_WARPS = 32;
+__global__ void __launch_bounds__(GROUP_WARPS * 32) fds_group_par_kernel(const int* __restrict__ bins, const int* __restrict__ present,
+                                                                         int N, int bucket_start, int bucket_num, int nb,
+                                                                         int* __restrict__ seg, int* __restrict__ order,
+                                                                         float* __restrict__ count) {
+    extern __shared__ int sh[];           // wcnt[GROUP_WARPS][nb] | tot[nb] | base[nb]
+    int* wcnt = sh;
+    int* tot = sh + GROUP_WARPS * nb;
+    int* base = tot + nb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < GROUP_WARPS * nb; i += blockDim.x) wcnt[i] = 0;
+    __syncthreads();
+    const int chunk = ((N + GROUP_WARPS - 1) / GROUP_WARPS + 31) & ~31;      // rows per warp, multiple of 32
+    const int r0 = warp * chunk, r1 = min(N, r0 + chunk);
+    for (int i = r0 + lane; i < r1; i += 32) {
+        const int b = fds_bucket(bins[i], present, bucket_start, bucket_num);
+        if (b >= 0) atomicAdd(&wcnt[warp * nb + b], 1);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        int run = 0;
+        for (int w = 0; w < GROUP_WARPS; ++w) {
+            const int c = wcnt[w * nb + b];
+            wcnt[w * nb + b] = run;            // cursor of warp w inside bucket b
+            run += c;
+        }
+        tot[b] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < nb; ++b) {
+            seg[b] = run;
+            base[b] = run;
+            count[b] = (float)tot[b];
+            run += tot[b];
+        }
+        seg[nb] = run;
+    }
+    __syncthreads();
+    for (int i0 = r0; i0 < r1; i0 += 32) {
+        const int i = i0 + lane;
+        const int b = i < r1 ? fds_bucket(bins[i], present, bucket_start, bucket_num) : -1;
+        const unsigned same = __match_any_sync(0xffffffffu, b);
+        const int rank = __popc(same & ((1u << lane) - 1u));
+        if (b >= 0) {
+            const int cur = wcnt[warp * nb + b];
+            order[base[b] + cur + rank] = i;
+        }
+        __syncwarp();
+        if (b >= 0 && rank == 0) wcnt[warp * nb + b] += __popc(same);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ segmented sums over row ranges (D == 512 panels, D % 4 == 0)
+// CTA = RPC consecutive entries of `order` (rows sorted by bucket, so a range spans one or two buckets); every warp sums its
+// rows of the range into register accumulators (NV float4 per lane: one coalesced 2 KB row per warp load), warps of the CTA
+// are folded through shared memory whenever the bucket changes, and the CTA adds its partial to the bucket's row with
+// 16-byte reductions.  Work per CTA is uniform whatever the bucket populations are (the per-bucket grid above serialises
+// on the fullest bucket).
+constexpr int SEG_RPC = 128;
+template <int PASS>
+__global__ void __launch_bounds__(256) fds_segsum_range_kernel(const float* __restrict__ x, long long ldx, const int* __restrict__ seg,
+                                                               const int* __restrict__ order, const float* __restrict__ sum1,
+                                                               const float* __restrict__ count, float* __restrict__ out, int D, int nb) {
+    extern __shared__ float red[];        // [8 warps][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = seg[nb];
+    const int k0 = blockIdx.x * SEG_RPC, k1 = min(total, k0 + SEG_RPC);
+    if (k0 >= k1) return;
+    // bucket of the first entry of the range (seg is ascending: small linear search, nb <= 1024)
+    int b = 0;
+    while (seg[b + 1] <= k0) ++b;
+    int k = k0;
+    while (k < k1) {
+        const int kend = min(k1, seg[b + 1]);             // entries [k, kend) belong to bucket b
+        if (kend > k) {
+            const float invn = PASS == 2 ? 1.f / count[b] : 0.f;
+            for (int c0 = 0; c0 < D; c0 += 512) {
+                float4 acc[4], mu[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int c = c0 + (v * 32 + lane) * 4;
+                    mu[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (PASS == 2 && c < D) {
+                        const float4 s4 = *reinterpret_cast<const float4*>(sum1 + (long long)b * D + c);
+                        mu[v] = make_float4(s4.x * invn, s4.y * invn, s4.z * invn, s4.w * invn);
+                    }
+                }
+                for (int kk = k + warp; kk < kend; kk += 8) {
+                    const float* xr = x + (long long)order[kk] * ldx;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int c = c0 + (v * 32 + lane) * 4;
+                        if (c < D) {
+                            const float4 t = *reinterpret_cast<const float4*>(xr + c);
+                            if (PASS == 1) { acc[v].x += t.x; acc[v].y += t.y; acc[v].z += t.z; acc[v].w += t.w; }
+                            else {
+                                const float dx_ = t.x - mu[v].x, dy_ = t.y - mu[v].y, dz_ = t.z - mu[v].z, dw_ = t.w - mu[v].w;
+                                acc[v].x = fmaf(dx_, dx_, acc[v].x); acc[v].y = fmaf(dy_, dy_, acc[v].y);
+                                acc[v].z = fmaf(dz_, dz_, acc[v].z); acc[v].w = fmaf(dw_, dw_, acc[v].w);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) *reinterpret_cast<float4*>(red + warp * 512 + (v * 32 + lane) * 4) = acc[v];
+                __syncthreads();
+                for (int c = threadIdx.x * 4; c < 512 && c0 + c < D; c += blockDim.x * 4) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const float4 u = *reinterpret_cast<const float4*>(red + w * 512 + c);
+                        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+                    }
+                    red_add_v4(out + (long long)b * D + c0 + c, t.x, t.y, t.z, t.w);
+                }
+                __syncthreads();
+            }
+        }
+        k = kend;
+        ++b;
+    }
+}
+
 // ------------------------------------------------------------------ segmented sums
 // grid (nb, splits).  CTA (b, s) walks rows order[seg[b] + s :: splits]; each warp takes every
 // (nwarps)-th of those rows and holds the row as NV float4 per lane (coalesced 512 B per warp load);
@@ -298,6 +429,66 @@ __global__ void __launch_bounds__(256) fds_smooth_kernel(float* __restrict__ x, 
     }
 }
 
+// ---- table form of the calibration (bandwidth-bound at epoch sizes): per bucket and column the factor
+// sqrt(clamp(v2/v1, 0.1, 10)) and the two means are evaluated ONCE (nb x D values) instead of once per sample, with the
+// identity (f = 1, m1 = 0, m2 = -0) where v1 == 0 and a per-bucket "active" flag (sum(v1) >= 1e-10); the per-sample kernel
+// then is three vector loads and (x - m1) * f + m2 with the reference's three separate roundings.
+// tab: [F | M1 | M2] (3 x nb x D) then active (nb) floats.
+__global__ void __launch_bounds__(256) fds_table_kernel(const float* __restrict__ m1, const float* __restrict__ v1,
+                                                        const float* __restrict__ m2, const float* __restrict__ v2,
+                                                        float* __restrict__ tab, int nb, int D) {
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const long long off = (long long)b * D, plane = (long long)nb * D;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) s += v1[off + c];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        tab[3 * plane + b] = (t < 1e-10f) ? 0.f : 1.f;
+    }
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        const float a = v1[off + c];
+        const bool on = a != 0.f;
+        tab[off + c] = on ? sqrtf(fminf(fmaxf(__fdiv_rn(v2[off + c], a), 0.1f), 10.f)) : 1.f;
+        tab[plane + off + c] = on && m1 ? m1[off + c] : 0.f;
+        tab[2 * plane + off + c] = on && m2 ? m2[off + c] : -0.f;
+    }
+}
+
+template <int BWD>
+__global__ void __launch_bounds__(256) fds_smooth_vec_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ dy,
+                                                             const int* __restrict__ bins, const int* __restrict__ present, int N,
+                                                             int D, int bucket_start, int bucket_num, const float* __restrict__ tab) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const long long plane = (long long)(bucket_num - bucket_start) * D;
+    for (int row = blockIdx.x * wpb + warp; row < N; row += gridDim.x * wpb) {
+        const int b = fds_bucket(bins[row], present, bucket_start, bucket_num);
+        const bool active = b >= 0 && tab[3 * plane + b] != 0.f;
+        float* xr = x + (long long)row * ldx;
+        if (!active) {
+            if (BWD) for (int c = lane * 4; c < D; c += 128) *reinterpret_cast<float4*>(xr + c) = *reinterpret_cast<const float4*>(dy + (long long)row * D + c);
+            continue;
+        }
+        const float* F = tab + (long long)b * D;
+        for (int c = lane * 4; c < D; c += 128) {
+            const float4 f = *reinterpret_cast<const float4*>(F + c);
+            if (BWD) {
+                const float4 g = *reinterpret_cast<const float4*>(dy + (long long)row * D + c);
+                *reinterpret_cast<float4*>(xr + c) = make_float4(g.x * f.x, g.y * f.y, g.z * f.z, g.w * f.w);
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(xr + c);
+                const float4 a = *reinterpret_cast<const float4*>(F + plane + c), o = *reinterpret_cast<const float4*>(F + 2 * plane + c);
+                *reinterpret_cast<float4*>(xr + c) = make_float4(__fadd_rn(__fmul_rn(__fsub_rn(v.x, a.x), f.x), o.x), __fadd_rn(__fmul_rn(__fsub_rn(v.y, a.y), f.y), o.y),
+                                                                 __fadd_rn(__fmul_rn(__fsub_rn(v.z, a.z), f.z), o.z), __fadd_rn(__fmul_rn(__fsub_rn(v.w, a.w), f.w), o.w));
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int mmdti_fds_bin(const float* labels, int64_t ld, int N, float min_value, float bin_width, int bucket_start,
@@ -314,8 +505,17 @@ extern "C" int mmdti_fds_bin(const float* labels, int64_t ld, int N, float min_v
 
 extern "C" int mmdti_fds_smooth_fwd(float* x, int64_t ldx, const int32_t* bins, const int32_t* present, int N, int D,
                                     int bucket_start, int bucket_num, const float* m1, const float* v1, const float* m2,
-                                    const float* v2, void* stream) {
+                                    const float* v2, float* work, void* stream) {
     MMDTI_REQUIRE(x && bins && present && m1 && v1 && m2 && v2 && N > 0 && D > 0 && ldx >= D, "fds_smooth_fwd: bad arguments");
+    if (work && D % 4 == 0 && ldx % 4 == 0 && mmdti_aligned(x, 16) && mmdti_aligned(work, 16)) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int nb = bucket_num - bucket_start;
+        fds_table_kernel<<<nb, 256, 0, st>>>(m1, v1, m2, v2, work, nb, D);
+        fds_smooth_vec_kernel<0><<<std::min((N + 7) / 8, num_sms() * 16), 256, 0, st>>>(x, ldx, nullptr, bins, present, N, D, bucket_start,
+                                                                                       bucket_num, work);
+        MMDTI_LAUNCH_OK();
+        return MMDTI_OK;
+    }
     fds_smooth_kernel<0><<<std::min((N + 7) / 8, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         x, ldx, nullptr, bins, present, N, D, bucket_start, bucket_num, m1, v1, m2, v2);
     MMDTI_LAUNCH_OK();
@@ -323,8 +523,17 @@ extern "C" int mmdti_fds_smooth_fwd(float* x, int64_t ldx, const int32_t* bins, 
 }
 
 extern "C" int mmdti_fds_smooth_bwd(const float* dy, float* dx, const int32_t* bins, const int32_t* present, int N, int D,
-                                    int bucket_start, int bucket_num, const float* v1, const float* v2, void* stream) {
+                                    int bucket_start, int bucket_num, const float* v1, const float* v2, float* work, void* stream) {
     MMDTI_REQUIRE(dy && dx && bins && present && v1 && v2 && N > 0 && D > 0, "fds_smooth_bwd: bad arguments");
+    if (work && D % 4 == 0 && mmdti_aligned(dy, 16) && mmdti_aligned(dx, 16) && mmdti_aligned(work, 16)) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const int nb = bucket_num - bucket_start;
+        fds_table_kernel<<<nb, 256, 0, st>>>(nullptr, v1, nullptr, v2, work, nb, D);
+        fds_smooth_vec_kernel<1><<<std::min((N + 7) / 8, num_sms() * 16), 256, 0, st>>>(dx, D, dy, bins, present, N, D, bucket_start,
+                                                                                       bucket_num, work);
+        MMDTI_LAUNCH_OK();
+        return MMDTI_OK;
+    }
     fds_smooth_kernel<1><<<std::min((N + 7) / 8, num_sms() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dx, D, dy, bins, present, N, D, bucket_start, bucket_num, nullptr, v1, nullptr, v2);
     MMDTI_LAUNCH_OK();
@@ -340,6 +549,12 @@ static int fds_segsum(int pass, const float* x, int64_t ldx, const int32_t* seg,
         const int blocks = (nb * 32 + 127) / 128;
         if (pass == 1) fds_segsum_small_kernel<1><<<blocks, 128, 0, st>>>(x, ldx, seg, order, sum1, count, out, D, DP, nb);
         else fds_segsum_small_kernel<2><<<blocks, 128, 0, st>>>(x, ldx, seg, order, sum1, count, out, D, DP, nb);
+    } else if (D % 4 == 0 && (ldx & 3) == 0 && mmdti_aligned(x, 16) && mmdti_aligned(out, 16) && (!sum1 || mmdti_aligned(sum1, 16))) {
+        // uniform work per CTA: ranges of the bucket-sorted row order (out is zeroed by the caller, partials are added)
+        const size_t smem = 8 * 512 * sizeof(float);
+        const int grid = (N + SEG_RPC - 1) / SEG_RPC;
+        if (pass == 1) fds_segsum_range_kernel<1><<<grid, 256, smem, st>>>(x, ldx, seg, order, sum1, count, out, D, nb);
+        else fds_segsum_range_kernel<2><<<grid, 256, smem, st>>>(x, ldx, seg, order, sum1, count, out, D, nb);
     } else {
         int splits = std::max(1, std::min(64, (2 * num_sms() + nb - 1) / nb));
         splits = std::max(1, std::min(splits, (N / nb + 63) / 64));
@@ -356,8 +571,14 @@ extern "C" int mmdti_fds_group(const int32_t* bins, const int32_t* present, int 
                                int32_t* order, float* count, void* stream) {
     const int nb = bucket_num - bucket_start;
     MMDTI_REQUIRE(bins && present && seg && order && count && N > 0 && nb > 0 && nb <= 4096, "fds_group: bad arguments (nb <= 4096)");
-    fds_group_kernel<<<1, 1024, 2 * nb * sizeof(int), static_cast<cudaStream_t>(stream)>>>(bins, present, N, bucket_start, bucket_num,
-                                                                                         nb, seg, order, count);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nb <= 256) {
+        const size_t smem = (size_t)(GROUP_WARPS * nb + 2 * nb) * sizeof(int);
+        MMDTI_CUDA_OK(cudaFuncSetAttribute(fds_group_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fds_group_par_kernel<<<1, GROUP_WARPS * 32, smem, st>>>(bins, present, N, bucket_start, bucket_num, nb, seg, order, count);
+    } else {
+        fds_group_kernel<<<1, 1024, 2 * nb * sizeof(int), st>>>(bins, present, N, bucket_start, bucket_num, nb, seg, order, count);
+    }
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }

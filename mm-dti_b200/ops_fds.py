@@ -40,8 +40,10 @@ class FDSSmoothFn(torch.autograd.Function):
         if features.dtype != torch.float32 or features.stride(1) != 1:
             raise _lib.MMDTIError("FDS.smooth: features must be f32 with unit column stride (got %s, strides %s)"
                                   % (features.dtype, features.stride()))
+        nb = bucket_num - bucket_start
+        work = torch.empty(3 * nb * D + nb, device=features.device, dtype=torch.float32)      # factor / mean tables
         call("mmdti_fds_smooth_fwd", features, i64(features.stride(0)), bins, present, i32(N), i32(D), i32(bucket_start),
-             i32(bucket_num), m1, v1, m2, v2, stream_ptr())
+             i32(bucket_num), m1, v1, m2, v2, work, stream_ptr())
         ctx.mark_dirty(features)
         ctx.save_for_backward(bins, present, v1.clone(), v2.clone())
         ctx.cfg = (N, D, bucket_start, bucket_num)
@@ -53,7 +55,8 @@ class FDSSmoothFn(torch.autograd.Function):
         N, D, bs, bn = ctx.cfg
         dy = dy.contiguous().float()
         dx = torch.empty_like(dy)
-        call("mmdti_fds_smooth_bwd", dy, dx, bins, present, i32(N), i32(D), i32(bs), i32(bn), v1, v2, stream_ptr())
+        work = torch.empty(3 * (bn - bs) * D + (bn - bs), device=dy.device, dtype=torch.float32)
+        call("mmdti_fds_smooth_bwd", dy, dx, bins, present, i32(N), i32(D), i32(bs), i32(bn), v1, v2, work, stream_ptr())
         return dx, None, None, None, None, None, None, None, None
 
 
@@ -68,8 +71,9 @@ def fds_update_running_stats(features, bins, present, bucket_start, bucket_num, 
     dev = features.device
     seg = torch.empty(nb + 1, device=dev, dtype=torch.int32)
     order = torch.empty(N, device=dev, dtype=torch.int32)
-    acc = torch.empty(nb * (D + 1), device=dev, dtype=torch.float32)       # [count | sum1] one buffer, one all-reduce
-    count, sum1 = acc[:nb], acc[nb:].view(nb, D)
+    nbp = (nb + 3) // 4 * 4                                                  # sum1 starts 16-byte aligned (vector kernels)
+    acc = torch.zeros(nbp + nb * D, device=dev, dtype=torch.float32)         # [count (padded) | sum1] one buffer, one all-reduce
+    count, sum1 = acc[:nb], acc[nbp:].view(nb, D)
     m2 = torch.empty((nb, D), device=dev, dtype=torch.float32)
     sp = stream_ptr()
     call("mmdti_fds_group", bins, present, i32(N), i32(bucket_start), i32(bucket_num), seg, order, count, sp)

@@ -1,5 +1,6 @@
-timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_elementwise.py tests/test_gpu_encoder.py tests/test_gpu_optim.py -x -q 2>&1 | tail -3
-timeout 200 python scripts/probe_gemm.py 2>&1 | tail -14
-python bench.py --workload encoder --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b_all.json 2> gpurun_out/b_all.err; echo "encoder rc=$? $(python -c "import json;d=json.load(open('gpurun_out/b_all.json'));print(d['ms_per_step'])")"
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/b_hot.json 2> gpurun_out/b_hot.err; echo "hotpath rc=$? $(python -c "import json;d=json.load(open('gpurun_out/b_hot.json'));print(d['ms_per_step'])")"
-timeout 300 python bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/b_hot2.json 2> gpurun_out/b_hot2.err; echo "n2 rc=$? $(python -c "import json;d=json.load(open('gpurun_out/b_hot2.json'));print(d['ms_per_step'], d['value'])")"
+mkdir -p gpurun_out/prof
+timeout 300 python -m pytest tests/test_gpu_fds.py tests/test_gpu_edge_cases.py tests/test_gpu_hot_path_step.py -q 2>&1 | tail -3
+python scripts/probe_fds.py > gpurun_out/prof/r2_fds_probe.log 2>&1; cat gpurun_out/prof/r2_fds_probe.log
+python scripts/probe_fds.py --iters 2 > /dev/null 2>&1 && ncu --set full --clock-control none -k regex:"fds_" -s 18 -c 9 -o gpurun_out/r2_fds python scripts/probe_fds.py --iters 2 > gpurun_out/ncu_fds.log 2>&1
+python scripts/ncu_key_metrics.py gpurun_out/r2_fds.ncu-rep > gpurun_out/prof/r2_fds_ncu_full.txt 2>&1; rm -f gpurun_out/r2_fds.ncu-rep
+grep -E "^==|time_duration|dram__bytes|dram_throughput" gpurun_out/prof/r2_fds_ncu_full.txt | cut -c1-120 | head -50
