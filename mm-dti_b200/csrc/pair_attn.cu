@@ -162,6 +162,12 @@ pair_attn_fwd_kernel(const FwdParams p) {
     const int w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
     const size_t tile_elems = (size_t)L * G::STRIDE;
     const FastDiv div_h((uint32_t)p.H), div_c((uint32_t)p.nchunks);
+    // who gathers the q / k / v rows (see prefetch): the last warp alone when its row block is a half block of a
+    // single-chunk tile, everybody otherwise
+    const int nwarps = nthr >> 5;
+    const bool light_last = !CS && p.nchunks == 1 && nwarps > 1 && (L - (nwarps - 1) * 16) <= 8 && (L - (nwarps - 1) * 16) > 0;
+    const int pf_lane0 = light_last ? (warp == nwarps - 1 ? lane : -1) : tid;
+    const int pf_step = light_last ? 32 : nthr;
 
     auto prefetch = [&](int w, int s) {
         const int tile = (int)div_c.div((uint32_t)w);
@@ -177,10 +183,16 @@ pair_attn_fwd_kernel(const FwdParams p) {
         const T* qg = static_cast<const T*>(p.q) + (size_t)b * L * p.ldqkv + h * HD;
         const T* kg = static_cast<const T*>(p.k) + (size_t)b * L * p.ldqkv + h * HD;
         const T* vg = static_cast<const T*>(p.v) + (size_t)b * L * p.ldqkv + h * HD;
-        for (int i = tid; i < 2 * L + nrows; i += nthr) {
-            if (i < L) cp_head_row(stage(s).K + i * HD, kg + (size_t)i * p.ldqkv);
-            else if (i < 2 * L) cp_head_row(stage(s).V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
-            else cp_head_row(stage(s).Q + (i - 2 * L) * HD, qg + (size_t)(row0 + i - 2 * L) * p.ldqkv);
+        // light_last: the CTA's last warp owns a half row block (L = 66: rows 64, 65) and would idle at the barrier for
+        // three quarters of an item; it fetches the q / k / v head rows of the next item ALONE, so that the full-block
+        // warps spend no instruction on the gather
+        const int i0 = pf_lane0, istep = pf_step;
+        if (i0 >= 0) {
+            for (int i = i0; i < 2 * L + nrows; i += istep) {
+                if (i < L) cp_head_row(stage(s).K + i * HD, kg + (size_t)i * p.ldqkv);
+                else if (i < 2 * L) cp_head_row(stage(s).V + (i - L) * HD, vg + (size_t)(i - L) * p.ldqkv);
+                else cp_head_row(stage(s).Q + (i - 2 * L) * HD, qg + (size_t)(row0 + i - 2 * L) * p.ldqkv);
+            }
         }
         cp_async_commit();
     };
@@ -536,6 +548,7 @@ pair_attn_fwd_kernel(const FwdParams p) {
             if (row0 + warp * 16 + 8 < L) row_block(std::true_type{});
             else row_block(std::false_type{});
         }
+        // (tried: every warp bulk-storing its own 16 rows without the CTA barrier -- no gain: 80.3 vs 77 us)
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
