@@ -383,6 +383,34 @@ int mmdti_adam_chunk(void);
 int mmdti_adam_step(const int64_t* table, const int32_t* chunks, int nchunks, const int64_t* step, double lr,
                     double beta1, double beta2, double eps, double grad_scale, void* stream);
 
+/* ---------------------------------------------------------------- cross-modal fusion
+ * BertCoAttention.forward (models/mm_module.py:493-522) as called by CrossAttentionModel.forward
+ * (models/mm_model.py:386-406): queries of one modality attend to keys/values of the other.
+ *   q (B*Lq, ldq), k / v (B*Lk, ldkv): head h occupies columns [h*head_dim, (h+1)*head_dim); act_dtype f32 | bf16
+ *   key_mask (B, Lk) uint8, 1 = attend: the reference's additive mask (1 - mask) * -10000 on the scores
+ *   o (B*Lq, ldo) = dropout(softmax(scale q k^T + mask)) v, act_dtype;  lse (B, H, Lq) f32 = opaque row statistics for
+ *   the backward (log2 domain on the bf16 path, natural log on the f32 path).
+ * bf16: head_dim 32 or 64, mma.sync flash-style kernels; f32: validation path.  Dropout keep decisions are a counter hash
+ * of (seed, b*H+h, query, key): mmdti_cross_attn_dropout_mask exports them as (B, H, Lq, Lk) uint8. */
+int mmdti_cross_attn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const uint8_t* key_mask,
+                         void* o, int64_t ldo, float* lse, int B, int H, int Lq, int Lk, int head_dim, float scale,
+                         float dropout_p, uint64_t seed, int act_dtype, void* stream);
+/* Backward of the above: delta (B, H, Lq) f32 scratch (rowsum(dO * O), written here); dq (B*Lq, lddq), dk / dv
+ * (B*Lk, lddkv) act_dtype, fully overwritten.  Deterministic (no atomics). */
+int mmdti_cross_attn_bwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const uint8_t* key_mask,
+                         const void* o, const void* d_o, int64_t ldo, const float* lse, float* delta, void* dq,
+                         int64_t lddq, void* dk, void* dv, int64_t lddkv, int B, int H, int Lq, int Lk, int head_dim,
+                         float scale, float dropout_p, uint64_t seed, int act_dtype, void* stream);
+int mmdti_cross_attn_dropout_mask(uint8_t* keep, int B, int H, int Lq, int Lk, float dropout_p, uint64_t seed,
+                                  void* stream);
+/* Masked mean pooling over the concatenation of the two fused sequences (models/mm_model.py:572-576):
+ * out (B, D) f32 = (sum of the rows of x1 (B, L1, D) with mask1 + sum of the rows of x2 (B, L2, D) with mask2) /
+ * (count1 + count2); x_dtype f32 | bf16.  Backward: dx1 / dx2 f32, dense (zeros on masked rows). */
+int mmdti_masked_pool_fwd(const void* x1, const uint8_t* mask1, int L1, const void* x2, const uint8_t* mask2, int L2,
+                          float* out, int B, int D, int x_dtype, void* stream);
+int mmdti_masked_pool_bwd(const float* dout, const uint8_t* mask1, int L1, const uint8_t* mask2, int L2, float* dx1,
+                          float* dx2, int B, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -652,7 +652,7 @@ extern "C" int mmdti_dropres_layernorm_fwd(const float* res, const void* a, floa
 extern "C" int mmdti_layernorm_bwd_dropout(const void* dy, const float* x, const float* w, const float* mean, const float* rstd,
                                            const float* dx_add, float* dx, float* dw, float* db, void* da, float* dbias, int rows,
                                            int D, float p, uint64_t seed, int dy_dtype, void* stream) {
-    MMDTI_REQUIRE(dy && x && w && mean && rstd && dx_add && dx && dw && db && da && dbias && rows > 0 && D % 4 == 0 && D <= 1024,
+    MMDTI_REQUIRE(dy && x && w && mean && rstd && dx && dw && db && da && dbias && rows > 0 && D % 4 == 0 && D <= 1024,
                   "layernorm_bwd_dropout: bad arguments (D=%d)", D);
     MMDTI_REQUIRE(dy_dtype == MMDTI_F32 || dy_dtype == MMDTI_BF16, "layernorm_bwd_dropout: dy_dtype must be f32 or bf16");
     MMDTI_REQUIRE(p >= 0.f && p < 1.f, "layernorm_bwd_dropout: p out of range");

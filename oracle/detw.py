@@ -25,7 +25,7 @@ def det_state_dict(shapes, seed=1, std=0.02):
     """shapes: {name: shape}.  LayerNorm weights ~ 1 + U, everything else ~ U(std)."""
     out = {}
     for i, (k, shp) in enumerate(sorted(shapes.items())):
-        if "layer_norm.weight" in k:
+        if "layer_norm.weight" in k or "LayerNorm.weight" in k:
             out[k] = det_tensor(shp, seed * 1000 + i, 0.1, 1.0)
         elif k.endswith("bias") and "gbf.bias" not in k:
             out[k] = det_tensor(shp, seed * 1000 + i, 0.05)

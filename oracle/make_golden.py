@@ -561,6 +561,62 @@ def gold_loss(ref):
     _save("loss", d)
 
 
+def gold_cross_modal(ref):
+    """the reference's CrossAttentionModel (models/mm_model.py:379-406; BertCrossEncoder,
+    models/mm_module.py:663-677) at its own configuration (crossmodal_config: hidden 512, 16 heads, FFN 2048, eps 1e-12),
+    eval mode (dropout off), ragged masks, followed by the masked pooling of models/mm_model.py:572-576.
+    Weights: oracle/detw.py, std 0.05 (6.3 M parameters, not stored).  Stored: both outputs, the pooled features, the
+    gradients of both inputs and 12 parameter gradients (rows [:ROWS] of the matrices)."""
+    from oracle.detw import det_state_dict, det_tensor
+    mm = ref["mm_model"]
+    cfg = mm.crossmodal_config()
+    ROWS = 32
+    net = mm.CrossAttentionModel(cfg, num_layers=1)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=21, std=0.05)
+    net.load_state_dict(sd)
+    net.eval()
+    B, L1, L2, D = 3, 13, 10, cfg.hidden_size
+    x1 = det_tensor((B, L1, D), 901, std=1.0).requires_grad_(True)          # "text_embeddings" slot (the graph tokens in MM_Model)
+    x2 = det_tensor((B, L2, D), 902, std=1.0).requires_grad_(True)
+    m1 = torch.zeros(B, L1, dtype=torch.bool)
+    m2 = torch.zeros(B, L2, dtype=torch.bool)
+    for b, (n1, n2) in enumerate(((13, 4), (7, 10), (1, 6))):
+        m1[b, :n1] = True
+        m2[b, :n2] = True
+    t2g, g2t = net(x1, x2, m1, m2)
+    a, c = t2g.clone(), g2t.clone()
+    a[~m1] = 0.0
+    c[~m2] = 0.0
+    final = torch.cat((a, c), dim=1)
+    pooled = final.sum(dim=1) / (m1.sum(dim=1).view(-1, 1) + m2.sum(dim=1).view(-1, 1))
+    up = det_tensor((B, D), 903, std=1.0)
+    (pooled * up).sum().backward()
+    named = dict(net.named_parameters())
+    gsel = ["text_attention.layer.0.attention.self.query.weight", "text_attention.layer.0.attention.self.key.bias",
+            "text_attention.layer.0.attention.self.value.weight", "text_attention.layer.0.attention.output.dense.weight",
+            "text_attention.layer.0.attention.output.LayerNorm.weight", "text_attention.layer.0.intermediate.dense.bias",
+            "text_attention.layer.0.output.dense.weight", "text_attention.layer.0.output.LayerNorm.bias",
+            "graph_attention.layer.0.attention.self.query.bias", "graph_attention.layer.0.attention.self.key.weight",
+            "graph_attention.layer.0.intermediate.dense.weight", "graph_attention.layer.0.output.LayerNorm.weight"]
+    d = {"in.x1": x1, "in.x2": x2, "in.m1": m1, "in.m2": m2, "in.up": up, "out.t2g": t2g, "out.g2t": g2t, "out.pooled": pooled,
+         "grad.x1": x1.grad, "grad.x2": x2.grad, "cfg": np.array([cfg.num_attention_heads, D, cfg.intermediate_size, 21, ROWS])}
+    for k in gsel:
+        d["grad." + k] = named[k].grad[:ROWS] if named[k].grad.dim() == 2 else named[k].grad
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    y1, y2 = x1.detach().clone().requires_grad_(True), x2.detach().clone().requires_grad_(True)
+    mt2g, mg2t = restate.cross_modal(y1, y2, m1, m2, p, heads=cfg.num_attention_heads, eps=cfg.layer_norm_eps)
+    _close(mt2g, t2g, 2e-6, "cross.t2g")
+    _close(mg2t, g2t, 2e-6, "cross.g2t")
+    mp = restate.fuse_pool(mt2g, mg2t, m1, m2)
+    _close(mp, pooled, 2e-6, "cross.pooled")
+    (mp * up).sum().backward()
+    _close(y1.grad, x1.grad, 2e-5, "cross.grad.x1")
+    _close(y2.grad, x2.grad, 2e-5, "cross.grad.x2")
+    for k in gsel:
+        _close(p[k].grad, named[k].grad, 2e-5, "cross.grad." + k)
+    _save("cross_modal", d)
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
@@ -573,6 +629,7 @@ def main():
     gold_fds(ref)
     gold_featurise(ref)
     gold_loss(ref)
+    gold_cross_modal(ref)
     print("all fixtures written and the restatement reproduces each of them")
 
 

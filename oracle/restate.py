@@ -437,3 +437,51 @@ def fds_update_last_epoch_stats(epoch, st, window):
 def mse_loss(pred, target):
     """nn.MSELoss registered for regression at models/nnmodel.py:27."""
     return F.mse_loss(pred, target)
+
+
+# --------------------------------------------------------------------------- f2 cross-modal fusion
+def _bert_ln(x, w, b, eps):
+    """BertLayerNorm, TF style, epsilon inside the square root (models/mm_module.py:320-333)."""
+    u = x.mean(-1, keepdim=True)
+    s = (x - u).pow(2).mean(-1, keepdim=True)
+    return w * ((x - u) / torch.sqrt(s + eps)) + b
+
+
+def cross_layer(s1, s2, mask2, p, prefix, heads=16, eps=1e-12, keeps=None, attn_dropout=0.0, dropout=0.0):
+    """BertCrossAttentionLayer (models/mm_module.py:607-620): BertCoAttention (:493-522: q from s1, k / v from s2, scores /
+    sqrt(d) + additive mask, softmax, dropout) -> BertSelfOutput (:525-536: dense, dropout, LayerNorm(x + s1)) ->
+    BertIntermediate (:563-575: dense + erf GELU) -> BertOutput (:578-589).  mask2 (B, L2) 1 = attend; the additive form
+    (1 - mask) * -10000 is models/mm_model.py:393-394.  keeps = (attention, attention-output, output) keep masks or None."""
+    B, L1, D = s1.shape
+    L2 = s2.shape[1]
+    hd = D // heads
+    lin = lambda x, n: F.linear(x, p[prefix + n + ".weight"], p[prefix + n + ".bias"])
+    split = lambda t, L: t.view(B, L, heads, hd).permute(0, 2, 1, 3)
+    q, k, v = split(lin(s1, "attention.self.query"), L1), split(lin(s2, "attention.self.key"), L2), split(lin(s2, "attention.self.value"), L2)
+    sc = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(hd)
+    sc = sc + ((1.0 - mask2.to(sc.dtype)) * -10000.0)[:, None, None, :]
+    pr = torch.softmax(sc, dim=-1)
+    pr = _drop(pr, attn_dropout, None if keeps is None else keeps[0])
+    ctx = torch.matmul(pr, v).permute(0, 2, 1, 3).contiguous().view(B, L1, D)
+    a = _drop(lin(ctx, "attention.output.dense"), dropout, None if keeps is None else keeps[1])
+    a = _bert_ln(a + s1, p[prefix + "attention.output.LayerNorm.weight"], p[prefix + "attention.output.LayerNorm.bias"], eps)
+    z = lin(a, "intermediate.dense")
+    u = z * 0.5 * (1.0 + torch.erf(z / math.sqrt(2.0)))                      # models/mm_module.py:204-211
+    o = _drop(lin(u, "output.dense"), dropout, None if keeps is None else keeps[2])
+    return _bert_ln(o + a, p[prefix + "output.LayerNorm.weight"], p[prefix + "output.LayerNorm.bias"], eps)
+
+
+def cross_modal(text_embeddings, graph_embeddings, text_mask, graph_mask, p, heads=16, eps=1e-12, prefix=""):
+    """CrossAttentionModel.forward (models/mm_model.py:386-406) with one layer per direction and dropout off:
+    returns (text_to_graph, graph_to_text)."""
+    g2t = cross_layer(graph_embeddings, text_embeddings, text_mask, p, prefix + "graph_attention.layer.0.", heads, eps)
+    t2g = cross_layer(text_embeddings, graph_embeddings, graph_mask, p, prefix + "text_attention.layer.0.", heads, eps)
+    return t2g, g2t
+
+
+def fuse_pool(cross_txt, cross, img_mask, attention_mask):
+    """models/mm_model.py:572-576: zero the rows outside the masks, concatenate, sum over tokens, divide by the valid counts."""
+    a = cross_txt * img_mask[..., None].to(cross_txt.dtype)
+    b = cross * attention_mask[..., None].to(cross.dtype)
+    final = torch.cat((a, b), dim=1)
+    return final.sum(dim=1) / (img_mask.sum(dim=1).view(-1, 1) + attention_mask.sum(dim=1).view(-1, 1))

@@ -43,6 +43,7 @@ def build(ref, dropin, task="regression", layers=2):
     patch(mm, "molecule_architecture", lambda: _with(arch(), encoder_layers=layers))
     if dropin:
         from mmdti_b200.models import contrastive as dct
+        from mmdti_b200.models import cross_modal as dcm
         from mmdti_b200.models import encoder as denc
         from mmdti_b200.models import fds as dfds
         from mmdti_b200.models import infonce as dinf
@@ -52,6 +53,7 @@ def build(ref, dropin, task="regression", layers=2):
         patch(mm, "NonLinearHead", denc.NonLinearHead)
         patch(mm, "InfoNCE", dinf.InfoNCE)
         patch(mm, "FDS", dfds.FDS)
+        patch(mm, "CrossAttentionModel", dcm.CrossAttentionModel)
         for n in ("CT_Regress", "CT_Single", "CT_Multi"):
             patch(ref["contrastive"], n, getattr(dct, n))
     try:

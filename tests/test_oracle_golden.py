@@ -131,3 +131,25 @@ def test_featurise_restatement_matches_reference_fixture():
     dist, et = restate.featurise(g["in.src_tokens"], g["in.src_coord"], n_dict=31, pad_idx=0)
     assert torch.equal(dist, g["out.src_distance"])
     assert torch.equal(et, g["out.src_edge_type"])
+
+
+def test_cross_modal_golden():
+    """oracle/restate.py:cross_modal + fuse_pool against the fixture made by the reference's CrossAttentionModel."""
+    g = load_golden("cross_modal")
+    H, D, Fd, seed, ROWS = [int(v) for v in g["cfg"]]
+    from tests_util import cross_layer_shapes
+    shapes = {}
+    for side in ("text_attention", "graph_attention"):
+        shapes.update(cross_layer_shapes(D, Fd, side + ".layer.0."))
+    p = {k: v.requires_grad_(True) for k, v in det_state_dict(shapes, seed=seed, std=0.05).items()}
+    x1, x2 = g["in.x1"].clone().requires_grad_(True), g["in.x2"].clone().requires_grad_(True)
+    t2g, g2t = restate.cross_modal(x1, x2, g["in.m1"], g["in.m2"], p, heads=H)
+    assert rel_err(t2g, g["out.t2g"]) < 5e-6 and rel_err(g2t, g["out.g2t"]) < 5e-6
+    pooled = restate.fuse_pool(t2g, g2t, g["in.m1"], g["in.m2"])
+    assert rel_err(pooled, g["out.pooled"]) < 5e-6
+    (pooled * g["in.up"]).sum().backward()
+    assert rel_err(x1.grad, g["grad.x1"]) < 5e-5 and rel_err(x2.grad, g["grad.x2"]) < 5e-5
+    for k, v in g.items():
+        if k.startswith("grad.") and k not in ("grad.x1", "grad.x2") and not k.endswith("key.bias"):
+            got = p[k[5:]].grad
+            assert rel_err(got[:ROWS] if got.dim() == 2 else got, v) < 5e-5, k

@@ -24,3 +24,15 @@ def slice_shapes(H, D, Fd, nl, K=128, n_tok=31):
 def seeded(shape, seed, scale=1.0, device="cpu"):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(device)
+
+
+def cross_layer_shapes(D, Fd, prefix=""):
+    """state_dict shapes of one BertCrossAttentionLayer (models/mm_module.py:607-620)."""
+    s = {}
+    for n in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+        s[prefix + n + ".weight"], s[prefix + n + ".bias"] = (D, D), (D,)
+    s[prefix + "intermediate.dense.weight"], s[prefix + "intermediate.dense.bias"] = (Fd, D), (Fd,)
+    s[prefix + "output.dense.weight"], s[prefix + "output.dense.bias"] = (D, Fd), (D,)
+    for n in ("attention.output.LayerNorm", "output.LayerNorm"):
+        s[prefix + n + ".weight"], s[prefix + n + ".bias"] = (D,), (D,)
+    return s
