@@ -95,12 +95,14 @@ class BertCrossAttentionLayer(nn.Module):
             raise ValueError("cross-modal layer: one hidden dropout rate per layer")
         seeds = (ops.next_seed(), ops.next_seed(), ops.next_seed()) if train else (0, 0, 0)
         cfg = (att.self.num_attention_heads, p_attn, p_hid, seeds, config.act_dtype(), att.output.LayerNorm.variance_epsilon)
-        # fp32 out like the reference under autocast (LayerNorm output), so the caller's pooling / heads see full precision
-        return ops_cross.CrossLayerFn.apply(
+        # fp32 out like the reference under autocast (LayerNorm output), so the caller's pooling / heads see full precision; a
+        # fresh tensor, because the caller zeroes masked rows IN PLACE (models/mm_model.py:572-573)
+        y = ops_cross.CrossLayerFn.apply(
             s1_hidden_states, s2_hidden_states, m, att.self.query.weight, att.self.query.bias, att.self.key.weight, att.self.key.bias,
             att.self.value.weight, att.self.value.bias, att.output.dense.weight, att.output.dense.bias, att.output.LayerNorm.weight,
             att.output.LayerNorm.bias, self.intermediate.dense.weight, self.intermediate.dense.bias, out.dense.weight, out.dense.bias,
-            out.LayerNorm.weight, out.LayerNorm.bias, cfg).float()
+            out.LayerNorm.weight, out.LayerNorm.bias, cfg)
+        return y.float() if y.dtype != torch.float32 else y.clone()
 
 
 class BertCrossEncoder(nn.Module):
