@@ -7,7 +7,8 @@ Default workload `hotpath` = BASELINE.json's metric "train molecules/sec (fwd+bw
 geometry: the Uni-Mol conformer encoder (15 layers, 64 heads, 512-d, per-GPU batch 128 molecules x 64 atoms, L = 66
 tokens, bf16, dropout 0.1) chained the way MM_Model.forward chains the WHOLE hot path of SURVEY.md §8(a)
 (models/mm_model.py:545-591): encoder -> InfoNCE against the second modality (a resident random (B, 64, 512) tensor
-standing in for the out-of-scope ChemBERTa output) -> masked mean pooling -> FDS.smooth (epoch 1, populated statistics)
+standing in for the out-of-scope ChemBERTa output) -> cross-modal fusion (CrossAttentionModel, both directions) + masked
+mean pooling of both token sequences (--no-fusion: pooling of the encoder output alone) -> FDS.smooth (epoch 1, populated statistics)
 -> regression head -> ConR, loss = MSE + 0.1 InfoNCE + 0.1 ConR (tasks/trainer.py:68-69,193), backward, Adam step;
 synthetic molecules, random-init weights.  The step is captured once in a CUDA graph and replayed; at N > 1 the
 contrastive operands are all-gathered (global-batch negatives, exchange 1) and the gradients all-reduced (exchange 2)
@@ -40,9 +41,9 @@ L = N_ATOMS + 2
 METRIC, UNIT = "train_molecules_per_sec", "molecules/s"
 S_SMILES, FDS_BUCKETS = 64, 30
 _NAMES = {"encoder": "unimol_encoder_fwd_bwd_15L_64H_512d_b128x64atoms",
-          "hotpath": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd",
-          "config3": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+supcon_classification_fwd_bwd_global_batch_4096",
-          "config4": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+fds_smooth+conr_fwd_bwd",
+          "hotpath": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+cross_fusion+fds_smooth+conr_fwd_bwd",
+          "config3": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+cross_fusion+supcon_classification_fwd_bwd_global_batch_4096",
+          "config4": "unimol_encoder_15L_64H_512d_b128x64atoms+infonce+cross_fusion+fds_smooth+conr_fwd_bwd",
           "config5": "contrastive_similarity_sweep_infonce_supcon_conr_N1K-64K_x512d"}
 WORKLOADS = dict(_NAMES)
 # per-workload defaults: (molecules per GPU | None = global batch / world, atoms, SMILES length, task, scaling)
@@ -50,6 +51,7 @@ SPECS = {"encoder": (128, 64, 64, None, "weak"), "hotpath": (128, 64, 64, "regre
          "config3": (None, 64, 64, "classification", "strong"), "config4": (32, 256, 256, "regression", "weak"),
          "config5": (128, 64, 64, None, "weak")}
 GLOBAL_BATCH_CONFIG3 = 4096
+FUSION = True          # --no-fusion: pool the encoder output directly (the round-1 step, without SURVEY.md §8 row f2)
 
 
 def set_shape(batch, n_atoms, smiles_len):
@@ -59,6 +61,8 @@ def set_shape(batch, n_atoms, smiles_len):
     L = N_ATOMS + 2
     for k in WORKLOADS:
         WORKLOADS[k] = _NAMES[k].replace("b128x64atoms", "b%dx%datoms" % (batch, n_atoms))
+        if not FUSION:
+            WORKLOADS[k] = WORKLOADS[k].replace("+cross_fusion", "")
 
 
 def peaks():
@@ -138,6 +142,15 @@ def make_head_batch(seed, n=None, task="regression"):
     return smiles, y, w, stats
 
 
+def smiles_mask(seed, n=None):
+    """Attention mask of the second modality: ragged lengths in [S/2, S] (tokenizer padding to the longest of the batch)."""
+    n = B_PER_GPU if n is None else n
+    gen = torch.Generator().manual_seed(seed + 17)
+    lens = torch.randint(max(1, S_SMILES // 2), S_SMILES + 1, (n,), generator=gen)
+    lens[0] = S_SMILES
+    return torch.arange(S_SMILES)[None, :] < lens[:, None]
+
+
 FDS_CFG = dict(min_value=-3.0, bin_width=0.2, bucket_num=FDS_BUCKETS, bucket_start=0, start_smooth=1)
 
 
@@ -215,6 +228,29 @@ def cpu_reference_run(steps, warmup, sample_b=32, workload="hotpath"):
             pi = {"infonce." + k: v for k, v in inf.named_parameters()}
         head_params = list(inf.parameters()) + list(head.parameters())
         mask = tokens.ne(0).float().unsqueeze(-1)
+        if FUSION:
+            # cross-modal fusion + pooling, models/mm_model.py:571-576 (the reference's CrossAttentionModel, else the port)
+            img_mask, txt_mask = tokens.ne(0), smiles_mask(1234, sample_b)
+            if ref is not None:
+                cross = ref["mm_model"].CrossAttentionModel(ref["mm_model"].crossmodal_config(), num_layers=1).train()
+                head_params += list(cross.parameters())
+            else:
+                from tests_util import cross_layer_shapes
+                shp = {}
+                for side in ("text_attention", "graph_attention"):
+                    shp.update(cross_layer_shapes(DIM, 2048, side + ".layer.0."))
+                pc = {k: v.requires_grad_(True) for k, v in det_state_dict(shp, seed=6).items()}
+                head_params += list(pc.values())
+
+            def pool(rep):
+                if ref is not None:
+                    a, c = cross(rep, smiles, img_mask, txt_mask)
+                else:
+                    a, c = restate.cross_modal(rep, smiles, img_mask, txt_mask, pc)
+                return restate.fuse_pool(a, c, img_mask, txt_mask)
+        else:
+            def pool(rep):
+                return (rep * mask).sum(1) / mask.sum(1)
     opt = torch.optim.Adam(enc_params + head_params, lr=1e-4, eps=1e-6)   # tasks/trainer.py:160
     ts = []
     for i in range(warmup + steps):
@@ -224,7 +260,7 @@ def cpu_reference_run(steps, warmup, sample_b=32, workload="hotpath"):
             (rep * g).sum().backward()
         else:
             l_inf = inf(rep, smiles) if ref is not None else restate.infonce_head(rep, smiles, pi)
-            pooled = (rep * mask).sum(1) / mask.sum(1)
+            pooled = pool(rep)
             if task == "regression":
                 feats = restate.fds_smooth(pooled * 1.0, y, 1, stats, FDS_CFG)
                 logits = head(feats)
@@ -348,6 +384,11 @@ def run_ours(args, rank, local_rank, world):
             getattr(fds, k).copy_(v)
         d_smiles = smiles.to(dev)
         extra_params = list(inf.parameters()) + list(head.parameters())
+        if FUSION:
+            from mmdti_b200.models.cross_modal import CrossAttentionModel, crossmodal_config, fuse_and_pool
+            cross = CrossAttentionModel(crossmodal_config(), num_layers=1).to(dev).train()
+            d_txt_mask = smiles_mask(1234 + rank).to(dev)
+            extra_params += list(cross.parameters())
         dp_ctx = None
         if dist_on:
             from mmdti_b200.dist import DataParallelCtx
@@ -397,8 +438,13 @@ def run_ours(args, rank, local_rank, world):
             y_d, w_d = inp[n_enc_in], inp[n_enc_in + 1]
             rep = rep.float()
             l_inf = inf(rep, d_smiles)                                     # a7: InfoNCE against the second modality
-            mk = inp[0].ne(0).unsqueeze(-1).float()
-            pooled = (rep * mk).sum(1) / mk.sum(1)                          # masked mean pooling (mm_model.py:571-576)
+            if FUSION:                                                      # f2: cross-modal fusion + masked pooling (mm_model.py:571-576)
+                img_mask = inp[0].ne(0)
+                t2g, g2t = cross(rep, d_smiles, img_mask, d_txt_mask)
+                pooled = fuse_and_pool(t2g, g2t, img_mask, d_txt_mask)
+            else:
+                mk = inp[0].ne(0).unsqueeze(-1).float()
+                pooled = (rep * mk).sum(1) / mk.sum(1)
             if task == "regression":
                 feats = fds.smooth(pooled * 1.0, y_d, 1)                    # a11: in place on the pooled features
                 logits = head(feats)
@@ -723,12 +769,15 @@ def main():
     ap.add_argument("--smiles-len", type=int, default=None, help="length of the second-modality sequence")
     ap.add_argument("--cpu-sample", type=int, default=32, help="molecules per step of the CPU arm's bounded sample")
     ap.add_argument("--nmax", type=int, default=65536, help="config5: largest N of the sweep")
+    ap.add_argument("--no-fusion", action="store_true", help="leave the cross-modal fusion block (SURVEY.md 8 row f2) out of the step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     n_ranks = max(world, args.gpus)
+    global FUSION
+    FUSION = not args.no_fusion
     b0, a0, s0 = SPECS[args.workload][:3]
     if b0 is None:                                      # config 3: the GLOBAL batch is fixed (strong scaling)
         if GLOBAL_BATCH_CONFIG3 % n_ranks:

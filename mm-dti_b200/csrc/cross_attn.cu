@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) cross_attn_fwd_kernel(CAParams P, bf16* _
     constexpr int LD = HD + 8;
     __shared__ __align__(16) bf16 Qs[64 * LD], Ks[64 * LD], Vs[64 * LD];
     __shared__ float madd[64];
-    const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H, q0 = blockIdx.x * 64;
+    const int bh = blockIdx.x, b = bh / P.H, h = bh % P.H, q0 = blockIdx.y * 64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
     const uint32_t key = ca_bh_key(P.key, P.seed_off, (uint32_t)bh);
     const uint32_t th2 = P.thresh16 * 0x10001U;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_q_kernel(CAParams P, const
     constexpr int LD = HD + 8;
     __shared__ __align__(16) bf16 Qs[64 * LD], Gs[64 * LD], Ks[64 * LD], Vs[64 * LD];
     __shared__ float madd[64];
-    const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H, q0 = blockIdx.x * 64;
+    const int bh = blockIdx.x, b = bh / P.H, h = bh % P.H, q0 = blockIdx.y * 64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
     const uint32_t key = ca_bh_key(P.key, P.seed_off, (uint32_t)bh);
     const bf16* qb = P.q + (long long)b * P.Lq * P.ldq + h * HD;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_kv_kernel(CAParams P, cons
     constexpr int LD = HD + 8;
     __shared__ __align__(16) bf16 Qs[64 * LD], Gs[64 * LD], Ks[64 * LD], Vs[64 * LD];
     __shared__ float lse_s[64], dl_s[64];
-    const int bh = blockIdx.y, b = bh / P.H, h = bh % P.H, k0 = blockIdx.x * 64;
+    const int bh = blockIdx.x, b = bh / P.H, h = bh % P.H, k0 = blockIdx.y * 64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
     const uint32_t key = ca_bh_key(P.key, P.seed_off, (uint32_t)bh);
     const bf16* qb = P.q + (long long)b * P.Lq * P.ldq + h * HD;
@@ -520,7 +520,7 @@ __global__ void cross_attn_mask_kernel(uint8_t* keep, int H, int Lq, int Lk, lon
 template <typename T>
 __global__ void __launch_bounds__(128) masked_pool_fwd_kernel(const T* __restrict__ x1, const uint8_t* __restrict__ m1, int L1, const T* __restrict__ x2,
                                                               const uint8_t* __restrict__ m2, int L2, float* __restrict__ out, int D) {
-    const int b = blockIdx.y, d = blockIdx.x * 128 + threadIdx.x;
+    const int b = blockIdx.x, d = blockIdx.y * 128 + threadIdx.x;
     __shared__ int cnt_s;
     if (threadIdx.x == 0) {
         int c = 0;
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(128) masked_pool_fwd_kernel(const T* __restric
 }
 __global__ void __launch_bounds__(128) masked_pool_bwd_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ m1, int L1,
                                                               const uint8_t* __restrict__ m2, int L2, float* __restrict__ dx1, float* __restrict__ dx2, int D) {
-    const int b = blockIdx.y;
+    const int b = blockIdx.x;
     __shared__ int cnt_s;
     if (threadIdx.x == 0) {
         int c = 0;
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(128) masked_pool_bwd_kernel(const float* __res
     }
     __syncthreads();
     const float inv = 1.f / (float)cnt_s;
-    const int r = blockIdx.x;                                 // row of the concatenation
+    const int r = blockIdx.y;                                 // row of the concatenation
     const bool first = r < L1;
     const bool on = first ? m1[(long long)b * L1 + r] : m2[(long long)b * L2 + (r - L1)];
     float* dst = first ? dx1 + ((long long)b * L1 + r) * D : dx2 + ((long long)b * L2 + (r - L1)) * D;
@@ -586,7 +586,7 @@ extern "C" int mmdti_cross_attn_fwd(const void* q, int64_t ldq, const void* k, c
         MMDTI_REQUIRE(ldo % 8 == 0 && mmdti_aligned(o, 16), "cross_attn_fwd: output rows must be 16-byte aligned");
         CAParams P{static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v), ldq, ldkv, key_mask, H, Lq, Lk,
                    scale, scale * CA_LOG2E, ks, ca_seed_key(seed), th, mmdti_seed_offset_ptr()};
-        const dim3 grid((Lq + 63) / 64, B * H);
+        const dim3 grid(B * H, (Lq + 63) / 64);          // (b, h) on x: B * H may exceed the 65535 limit of y
         if (head_dim == 32) cross_attn_fwd_kernel<32><<<grid, 128, 0, st>>>(P, static_cast<bf16*>(o), ldo, lse);
         else cross_attn_fwd_kernel<64><<<grid, 128, 0, st>>>(P, static_cast<bf16*>(o), ldo, lse);
     } else {
@@ -615,7 +615,7 @@ extern "C" int mmdti_cross_attn_bwd(const void* q, int64_t ldq, const void* k, c
                       "cross_attn_bwd: rows must be 16-byte aligned");
         CAParams P{static_cast<const bf16*>(q), static_cast<const bf16*>(k), static_cast<const bf16*>(v), ldq, ldkv, key_mask, H, Lq, Lk,
                    scale, scale * CA_LOG2E, ks, ca_seed_key(seed), th, mmdti_seed_offset_ptr()};
-        const dim3 gq((Lq + 63) / 64, B * H), gk((Lk + 63) / 64, B * H);
+        const dim3 gq(B * H, (Lq + 63) / 64), gk(B * H, (Lk + 63) / 64);
         if (head_dim == 32) {
             cross_attn_bwd_q_kernel<32><<<gq, 128, 0, st>>>(P, static_cast<const bf16*>(o), static_cast<const bf16*>(d_o), ldo, lse, delta,
                                                             static_cast<bf16*>(dq), lddq);
@@ -656,7 +656,7 @@ extern "C" int mmdti_masked_pool_fwd(const void* x1, const uint8_t* mask1, int L
                                      int D, int x_dtype, void* stream) {
     MMDTI_REQUIRE(x1 && x2 && mask1 && mask2 && out && B > 0 && D > 0 && L1 > 0 && L2 > 0, "masked_pool_fwd: bad arguments");
     MMDTI_REQUIRE(x_dtype == MMDTI_F32 || x_dtype == MMDTI_BF16, "masked_pool_fwd: x_dtype must be f32 or bf16");
-    const dim3 grid((D + 127) / 128, B);
+    const dim3 grid(B, (D + 127) / 128);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x_dtype == MMDTI_F32)
         masked_pool_fwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x1), mask1, L1, static_cast<const float*>(x2), mask2, L2, out, D);
@@ -669,7 +669,7 @@ extern "C" int mmdti_masked_pool_fwd(const void* x1, const uint8_t* mask1, int L
 extern "C" int mmdti_masked_pool_bwd(const float* dout, const uint8_t* mask1, int L1, const uint8_t* mask2, int L2, float* dx1, float* dx2, int B,
                                      int D, void* stream) {
     MMDTI_REQUIRE(dout && mask1 && mask2 && dx1 && dx2 && B > 0 && D > 0 && L1 > 0 && L2 > 0, "masked_pool_bwd: bad arguments");
-    const dim3 grid(L1 + L2, B);
+    const dim3 grid(B, L1 + L2);
     masked_pool_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(dout, mask1, L1, mask2, L2, dx1, dx2, D);
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;

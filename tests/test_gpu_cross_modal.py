@@ -29,7 +29,8 @@ def _ref_attn(q, kv, mask2, B, H, Lq, Lk, keep=None, p=0.0):
     return (pr @ v4).permute(0, 2, 1, 3).reshape(B * Lq, D)
 
 
-@pytest.mark.parametrize("B,H,Lq,Lk,hd", [(2, 4, 13, 10, 32), (3, 16, 66, 70, 32), (2, 8, 130, 200, 64), (1, 2, 64, 64, 32), (2, 2, 5, 129, 64)])
+@pytest.mark.parametrize("B,H,Lq,Lk,hd", [(2, 4, 13, 10, 32), (3, 16, 66, 70, 32), (2, 8, 130, 200, 64), (1, 2, 64, 64, 32), (2, 2, 5, 129, 64),
+                                          (4100, 16, 2, 3, 32)])      # B * H beyond the 65535 grid-y limit (config 3 on one GPU)
 @pytest.mark.parametrize("p", [0.0, 0.2])
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_cross_attention_core(B, H, Lq, Lk, hd, p, mode, report):
@@ -41,7 +42,7 @@ def test_cross_attention_core(B, H, Lq, Lk, hd, p, mode, report):
     kv = (torch.randn(B * Lk, 2 * D, generator=g) * 1.5).cuda().to(dt).requires_grad_(True)
     up = torch.randn(B * Lq, D, generator=g).cuda()
     mask2 = torch.ones(B, Lk, dtype=torch.bool)
-    for b in range(B):
+    for b in range(min(B, 8)):
         mask2[b, max(1, Lk - 3 * b - (Lk // 3 if b else 0)):] = False
     mask2 = mask2.cuda()
     seed = 1234567 + Lk
