@@ -405,11 +405,12 @@ int mmdti_cross_attn_dropout_mask(uint8_t* keep, int B, int H, int Lq, int Lk, f
                                   void* stream);
 /* Masked mean pooling over the concatenation of the two fused sequences (models/mm_model.py:572-576):
  * out (B, D) f32 = (sum of the rows of x1 (B, L1, D) with mask1 + sum of the rows of x2 (B, L2, D) with mask2) /
- * (count1 + count2); x_dtype f32 | bf16.  Backward: dx1 / dx2 f32, dense (zeros on masked rows). */
+ * (count1 + count2); x_dtype f32 | bf16; inv_count (B) f32 = 1 / (count1 + count2), kept for the backward; D % 4 == 0.
+ * Backward: dx1 / dx2 f32, dense (zeros on masked rows). */
 int mmdti_masked_pool_fwd(const void* x1, const uint8_t* mask1, int L1, const void* x2, const uint8_t* mask2, int L2,
-                          float* out, int B, int D, int x_dtype, void* stream);
-int mmdti_masked_pool_bwd(const float* dout, const uint8_t* mask1, int L1, const uint8_t* mask2, int L2, float* dx1,
-                          float* dx2, int B, int D, void* stream);
+                          float* out, float* inv_count, int B, int D, int x_dtype, void* stream);
+int mmdti_masked_pool_bwd(const float* dout, const float* inv_count, const uint8_t* mask1, int L1, const uint8_t* mask2,
+                          int L2, float* dx1, float* dx2, int B, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(128) cross_attn_fwd_kernel(CAParams P, bf16* _
     for (int n = 0; n < HD / 8; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     const int row_g = q0 + warp * 16 + g;
+    const bool active = q0 + warp * 16 < P.Lq;
     for (int k0 = 0; k0 < P.Lk; k0 += 64) {
         if (k0) __syncthreads();
         ca_load_rows<HD>(Ks, kb, P.ldkv, k0, P.Lk, tid);
@@ -118,20 +119,24 @@ __global__ void __launch_bounds__(128) cross_attn_fwd_kernel(CAParams P, bf16* _
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
+        if (!active) continue;                                 // no valid query row in this warp: it only helps loading
         if (k0 == 0) ca_a_frags<HD>(qa, Qs, warp * 16, lane);
+        const int nt = min(8, (P.Lk - k0 + 7) >> 3);             // 8-key tiles of this block that hold valid keys
         float s[8][4];
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-            ca_mma_nt<HD>(s[j], qa, Ks, 8 * j, lane);
-            const float a0 = madd[8 * j + 2 * q4], a1 = madd[8 * j + 2 * q4 + 1];
-            s[j][0] = fmaf(s[j][0], P.scale_log2, a0);
-            s[j][1] = fmaf(s[j][1], P.scale_log2, a1);
-            s[j][2] = fmaf(s[j][2], P.scale_log2, a0);
-            s[j][3] = fmaf(s[j][3], P.scale_log2, a1);
-            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+            if (j < nt) {
+                ca_mma_nt<HD>(s[j], qa, Ks, 8 * j, lane);
+                const float a0 = madd[8 * j + 2 * q4], a1 = madd[8 * j + 2 * q4 + 1];
+                s[j][0] = fmaf(s[j][0], P.scale_log2, a0);
+                s[j][1] = fmaf(s[j][1], P.scale_log2, a1);
+                s[j][2] = fmaf(s[j][2], P.scale_log2, a0);
+                s[j][3] = fmaf(s[j][3], P.scale_log2, a1);
+                mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+                mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+            }
         }
         mx0 = quad_max(mx0);
         mx1 = quad_max(mx1);
@@ -142,12 +147,14 @@ __global__ void __launch_bounds__(128) cross_attn_fwd_kernel(CAParams P, bf16* _
         float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            s[j][0] = fast_ex2(s[j][0] - mn0);
-            s[j][1] = fast_ex2(s[j][1] - mn0);
-            s[j][2] = fast_ex2(s[j][2] - mn1);
-            s[j][3] = fast_ex2(s[j][3] - mn1);
-            ps0 += s[j][0] + s[j][1];
-            ps1 += s[j][2] + s[j][3];
+            if (j < nt) {
+                s[j][0] = fast_ex2(s[j][0] - mn0);
+                s[j][1] = fast_ex2(s[j][1] - mn0);
+                s[j][2] = fast_ex2(s[j][2] - mn1);
+                s[j][3] = fast_ex2(s[j][3] - mn1);
+                ps0 += s[j][0] + s[j][1];
+                ps1 += s[j][2] + s[j][3];
+            }
         }
         l_run[0] = l_run[0] * al0 + ps0;
         l_run[1] = l_run[1] * al1 + ps1;
@@ -160,15 +167,18 @@ __global__ void __launch_bounds__(128) cross_attn_fwd_kernel(CAParams P, bf16* _
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            const uint2 w0 = rng_quad_bits(key, (uint32_t)row_g, (uint32_t)(k0 + 16 * t + 2 * q4));
-            const uint2 w1 = rng_quad_bits(key, (uint32_t)(row_g + 8), (uint32_t)(k0 + 16 * t + 2 * q4));
-            const uint32_t a0 = pack_bf16(s[2 * t][0], s[2 * t][1]) & rng_keep_mask2(w0.x, th2);
-            const uint32_t a1 = pack_bf16(s[2 * t][2], s[2 * t][3]) & rng_keep_mask2(w1.x, th2);
-            const uint32_t a2 = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]) & rng_keep_mask2(w0.y, th2);
-            const uint32_t a3 = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]) & rng_keep_mask2(w1.y, th2);
-            ca_mma_nn<HD>(oacc, a0, a1, a2, a3, Vs, 16 * t, lane);
+            if (2 * t < nt) {                                  // tile 2t+1 beyond nt holds zeros
+                const uint2 w0 = rng_quad_bits(key, (uint32_t)row_g, (uint32_t)(k0 + 16 * t + 2 * q4));
+                const uint2 w1 = rng_quad_bits(key, (uint32_t)(row_g + 8), (uint32_t)(k0 + 16 * t + 2 * q4));
+                const uint32_t a0 = pack_bf16(s[2 * t][0], s[2 * t][1]) & rng_keep_mask2(w0.x, th2);
+                const uint32_t a1 = pack_bf16(s[2 * t][2], s[2 * t][3]) & rng_keep_mask2(w1.x, th2);
+                const uint32_t a2 = pack_bf16(s[2 * t + 1][0], s[2 * t + 1][1]) & rng_keep_mask2(w0.y, th2);
+                const uint32_t a3 = pack_bf16(s[2 * t + 1][2], s[2 * t + 1][3]) & rng_keep_mask2(w1.y, th2);
+                ca_mma_nn<HD>(oacc, a0, a1, a2, a3, Vs, 16 * t, lane);
+            }
         }
     }
+    if (!active) return;
     const float l0 = quad_sum(l_run[0]), l1 = quad_sum(l_run[1]);
     const float i0 = P.keep_scale / l0, i1 = P.keep_scale / l1;
     if (row_g < P.Lq) {
@@ -228,6 +238,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_q_kernel(CAParams P, const
     }
     const float dl0 = __shfl_sync(0xffffffffu, dl, g), dl1 = __shfl_sync(0xffffffffu, dl, g + 8);
     const int row_g = q0 + warp * 16 + g;
+    const bool active = q0 + warp * 16 < P.Lq;
     const float ls0 = row_g < P.Lq ? lse2[(long long)bh * P.Lq + row_g] : INFINITY;
     const float ls1 = row_g + 8 < P.Lq ? lse2[(long long)bh * P.Lq + row_g + 8] : INFINITY;
     uint32_t qa[HD / 16][4], ga[HD / 16][4];
@@ -245,13 +256,17 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_q_kernel(CAParams P, const
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
+        if (!active) continue;
         if (k0 == 0) {
             ca_a_frags<HD>(qa, Qs, warp * 16, lane);
             ca_a_frags<HD>(ga, Gs, warp * 16, lane);
         }
+        const int nt = min(8, (P.Lk - k0 + 7) >> 3);
         float ds[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            ds[j][0] = ds[j][1] = ds[j][2] = ds[j][3] = 0.f;
+            if (j >= nt) continue;
             float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
             ca_mma_nt<HD>(s, qa, Ks, 8 * j, lane);
             ca_mma_nt<HD>(dp, ga, Vs, 8 * j, lane);
@@ -268,8 +283,9 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_q_kernel(CAParams P, const
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-            ca_mma_nn<HD>(acc, pack_bf16(ds[2 * t][0], ds[2 * t][1]), pack_bf16(ds[2 * t][2], ds[2 * t][3]),
-                          pack_bf16(ds[2 * t + 1][0], ds[2 * t + 1][1]), pack_bf16(ds[2 * t + 1][2], ds[2 * t + 1][3]), Ks, 16 * t, lane);
+            if (2 * t < nt)
+                ca_mma_nn<HD>(acc, pack_bf16(ds[2 * t][0], ds[2 * t][1]), pack_bf16(ds[2 * t][2], ds[2 * t][3]),
+                              pack_bf16(ds[2 * t + 1][0], ds[2 * t + 1][1]), pack_bf16(ds[2 * t + 1][2], ds[2 * t + 1][3]), Ks, 16 * t, lane);
     }
     if (row_g < P.Lq) {
         bf16* r = dq + ((long long)b * P.Lq + row_g) * lddq + h * HD + 2 * q4;
@@ -312,6 +328,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_kv_kernel(CAParams P, cons
         dva[n][0] = dva[n][1] = dva[n][2] = dva[n][3] = 0.f;
     }
     const bool hi = g & 1;                                   // halfword of the random word that belongs to this key column
+    const bool active = k0 + warp * 16 < P.Lk;
     for (int q0 = 0; q0 < P.Lq; q0 += 64) {
         if (q0) __syncthreads();
         ca_load_rows<HD>(Qs, qb, P.ldq, q0, P.Lq, tid);
@@ -324,13 +341,18 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_kv_kernel(CAParams P, cons
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
+        if (!active) continue;
         if (q0 == 0) {
             ca_a_frags<HD>(ka, Ks, warp * 16, lane);
             ca_a_frags<HD>(va, Vs, warp * 16, lane);
         }
+        const int nt = min(8, (P.Lq - q0 + 7) >> 3);             // 8-query tiles of this block that hold valid queries
         float pd[8][4], ds[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+            pd[j][0] = pd[j][1] = pd[j][2] = pd[j][3] = 0.f;
+            ds[j][0] = ds[j][1] = ds[j][2] = ds[j][3] = 0.f;
+            if (j >= nt) continue;
             float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
             ca_mma_nt<HD>(s, ka, Qs, 8 * j, lane);             // S^T: rows = keys, cols = queries
             ca_mma_nt<HD>(dp, va, Gs, 8 * j, lane);            // dP^T
@@ -354,6 +376,7 @@ __global__ void __launch_bounds__(128) cross_attn_bwd_kv_kernel(CAParams P, cons
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+            if (2 * t >= nt) continue;
             ca_mma_nn<HD>(dva, pack_bf16(pd[2 * t][0], pd[2 * t][1]), pack_bf16(pd[2 * t][2], pd[2 * t][3]),
                           pack_bf16(pd[2 * t + 1][0], pd[2 * t + 1][1]), pack_bf16(pd[2 * t + 1][2], pd[2 * t + 1][3]), Gs, 16 * t, lane);
             ca_mma_nn<HD>(dka, pack_bf16(ds[2 * t][0], ds[2 * t][1]), pack_bf16(ds[2 * t][2], ds[2 * t][3]),
@@ -517,43 +540,70 @@ __global__ void cross_attn_mask_kernel(uint8_t* keep, int H, int Lq, int Lk, lon
 
 // ------------------------------------------------------------------------------------------------ masked mean pooling
 // pooled[b] = (sum_{valid rows} x1[b] + sum_{valid rows} x2[b]) / (n1 + n2)   (models/mm_model.py:572-576)
+constexpr int POOL_RG = 8;          // row groups per CTA (threadIdx.y)
 template <typename T>
-__global__ void __launch_bounds__(128) masked_pool_fwd_kernel(const T* __restrict__ x1, const uint8_t* __restrict__ m1, int L1, const T* __restrict__ x2,
-                                                              const uint8_t* __restrict__ m2, int L2, float* __restrict__ out, int D) {
-    const int b = blockIdx.x, d = blockIdx.y * 128 + threadIdx.x;
-    __shared__ int cnt_s;
-    if (threadIdx.x == 0) {
-        int c = 0;
-        for (int r = 0; r < L1; ++r) c += m1[(long long)b * L1 + r] ? 1 : 0;
-        for (int r = 0; r < L2; ++r) c += m2[(long long)b * L2 + r] ? 1 : 0;
-        cnt_s = c;
+__global__ void __launch_bounds__(32 * POOL_RG) masked_pool_fwd_kernel(const T* __restrict__ x1, const uint8_t* __restrict__ m1, int L1,
+                                                                      const T* __restrict__ x2, const uint8_t* __restrict__ m2, int L2,
+                                                                      float* __restrict__ out, float* __restrict__ inv_cnt, int D) {
+    // CTA = (molecule b, 128 columns): thread (x, y) owns columns 4x .. 4x+3 of the rows y, y + POOL_RG, ...
+    __shared__ float part[POOL_RG][128];
+    __shared__ int cnt_s[POOL_RG];
+    const int b = blockIdx.x, tx = threadIdx.x, ty = threadIdx.y, d = blockIdx.y * 128 + tx * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+    for (int r = ty; r < L1 + L2; r += POOL_RG) {
+        const bool first = r < L1;
+        const bool on = first ? m1[(long long)b * L1 + r] : m2[(long long)b * L2 + (r - L1)];
+        if (!on) continue;
+        ++cnt;
+        if (d < D) {
+            const T* row = first ? x1 + ((long long)b * L1 + r) * D + d : x2 + ((long long)b * L2 + (r - L1)) * D + d;
+            if constexpr (sizeof(T) == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(row);
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            } else {
+                const uint2 u = *reinterpret_cast<const uint2*>(row);
+                const float2 a = unpack_bf16(u.x), c = unpack_bf16(u.y);
+                acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+            }
+        }
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) part[ty][tx * 4 + e] = acc[e];
+    if (tx == 0) cnt_s[ty] = cnt;
     __syncthreads();
-    if (d >= D) return;
-    float acc = 0.f;
-    for (int r = 0; r < L1; ++r)
-        if (m1[(long long)b * L1 + r]) acc += to_f(x1[((long long)b * L1 + r) * D + d]);
-    for (int r = 0; r < L2; ++r)
-        if (m2[(long long)b * L2 + r]) acc += to_f(x2[((long long)b * L2 + r) * D + d]);
-    out[(long long)b * D + d] = acc / (float)cnt_s;
+    if (ty == 0) {
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < POOL_RG; ++k) c += cnt_s[k];
+        const float inv = 1.f / (float)c;
+        if (tx == 0 && blockIdx.y == 0) inv_cnt[b] = inv;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < POOL_RG; ++k) t += part[k][tx * 4 + e];
+            if (d + e < D) out[(long long)b * D + d + e] = t * inv;
+        }
+    }
 }
-__global__ void __launch_bounds__(128) masked_pool_bwd_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ m1, int L1,
-                                                              const uint8_t* __restrict__ m2, int L2, float* __restrict__ dx1, float* __restrict__ dx2, int D) {
+__global__ void __launch_bounds__(128) masked_pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ inv_cnt,
+                                                              const uint8_t* __restrict__ m1, int L1, const uint8_t* __restrict__ m2, int L2,
+                                                              float* __restrict__ dx1, float* __restrict__ dx2, int D) {
     const int b = blockIdx.x;
-    __shared__ int cnt_s;
-    if (threadIdx.x == 0) {
-        int c = 0;
-        for (int r = 0; r < L1; ++r) c += m1[(long long)b * L1 + r] ? 1 : 0;
-        for (int r = 0; r < L2; ++r) c += m2[(long long)b * L2 + r] ? 1 : 0;
-        cnt_s = c;
-    }
-    __syncthreads();
-    const float inv = 1.f / (float)cnt_s;
+    const float inv = inv_cnt[b];
     const int r = blockIdx.y;                                 // row of the concatenation
     const bool first = r < L1;
     const bool on = first ? m1[(long long)b * L1 + r] : m2[(long long)b * L2 + (r - L1)];
     float* dst = first ? dx1 + ((long long)b * L1 + r) * D : dx2 + ((long long)b * L2 + (r - L1)) * D;
-    for (int d = threadIdx.x; d < D; d += 128) dst[d] = on ? dout[(long long)b * D + d] * inv : 0.f;
+    for (int d = threadIdx.x * 4; d < D; d += 512) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on) {
+            v = *reinterpret_cast<const float4*>(dout + (long long)b * D + d);
+            v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+        }
+        *reinterpret_cast<float4*>(dst + d) = v;
+    }
 }
 
 int ca_check(const void* q, const void* k, const void* v, const uint8_t* kmask, int B, int H, int Lq, int Lk, int hd, int act_dtype, long long ldq,
@@ -652,25 +702,29 @@ extern "C" int mmdti_cross_attn_dropout_mask(uint8_t* keep, int B, int H, int Lq
     return MMDTI_OK;
 }
 
-extern "C" int mmdti_masked_pool_fwd(const void* x1, const uint8_t* mask1, int L1, const void* x2, const uint8_t* mask2, int L2, float* out, int B,
-                                     int D, int x_dtype, void* stream) {
-    MMDTI_REQUIRE(x1 && x2 && mask1 && mask2 && out && B > 0 && D > 0 && L1 > 0 && L2 > 0, "masked_pool_fwd: bad arguments");
+extern "C" int mmdti_masked_pool_fwd(const void* x1, const uint8_t* mask1, int L1, const void* x2, const uint8_t* mask2, int L2, float* out,
+                                     float* inv_count, int B, int D, int x_dtype, void* stream) {
+    MMDTI_REQUIRE(x1 && x2 && mask1 && mask2 && out && inv_count && B > 0 && D > 0 && L1 > 0 && L2 > 0, "masked_pool_fwd: bad arguments");
     MMDTI_REQUIRE(x_dtype == MMDTI_F32 || x_dtype == MMDTI_BF16, "masked_pool_fwd: x_dtype must be f32 or bf16");
-    const dim3 grid(B, (D + 127) / 128);
+    MMDTI_REQUIRE(D % 4 == 0 && mmdti_aligned(x1, 16) && mmdti_aligned(x2, 16), "masked_pool_fwd: D %% 4 == 0 and 16-byte aligned inputs");
+    const dim3 grid(B, (D + 127) / 128), block(32, POOL_RG);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (x_dtype == MMDTI_F32)
-        masked_pool_fwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x1), mask1, L1, static_cast<const float*>(x2), mask2, L2, out, D);
+        masked_pool_fwd_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(x1), mask1, L1, static_cast<const float*>(x2), mask2, L2, out,
+                                                              inv_count, D);
     else
-        masked_pool_fwd_kernel<bf16><<<grid, 128, 0, st>>>(static_cast<const bf16*>(x1), mask1, L1, static_cast<const bf16*>(x2), mask2, L2, out, D);
+        masked_pool_fwd_kernel<bf16><<<grid, block, 0, st>>>(static_cast<const bf16*>(x1), mask1, L1, static_cast<const bf16*>(x2), mask2, L2, out,
+                                                             inv_count, D);
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }
 
-extern "C" int mmdti_masked_pool_bwd(const float* dout, const uint8_t* mask1, int L1, const uint8_t* mask2, int L2, float* dx1, float* dx2, int B,
-                                     int D, void* stream) {
-    MMDTI_REQUIRE(dout && mask1 && mask2 && dx1 && dx2 && B > 0 && D > 0 && L1 > 0 && L2 > 0, "masked_pool_bwd: bad arguments");
+extern "C" int mmdti_masked_pool_bwd(const float* dout, const float* inv_count, const uint8_t* mask1, int L1, const uint8_t* mask2, int L2,
+                                     float* dx1, float* dx2, int B, int D, void* stream) {
+    MMDTI_REQUIRE(dout && inv_count && mask1 && mask2 && dx1 && dx2 && B > 0 && D > 0 && D % 4 == 0 && L1 > 0 && L2 > 0,
+                  "masked_pool_bwd: bad arguments");
     const dim3 grid(B, L1 + L2);
-    masked_pool_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(dout, mask1, L1, mask2, L2, dx1, dx2, D);
+    masked_pool_bwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(dout, inv_count, mask1, L1, mask2, L2, dx1, dx2, D);
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }

@@ -165,11 +165,26 @@ class CrossLayerFn(torch.autograd.Function):
         db_o, db_2, db_q, db_kv = red[4 * D:5 * D], red[5 * D:6 * D], red[6 * D:7 * D], red[7 * D:9 * D]
         db_1 = red[9 * D:]
         if fused:
-            wgrad = ops_gemm.gemm_wgrad
+            wgrad_ = ops_gemm.gemm_wgrad
             dgrad = ops_gemm.gemm_dgrad
         else:
-            wgrad = lambda g, x: torch.mm(g.t(), x).float()
+            wgrad_ = lambda g, x: torch.mm(g.t(), x).float()
             dgrad = lambda g, w: torch.mm(g, w)
+        # weight gradients and bias column sums are off the critical path: side stream (parallel branches of a captured graph),
+        # joined before the function returns -- same scheme as ops.EncoderLayerFn
+        main = torch.cuda.current_stream(dev)
+        side = ops._side_stream(dev) if ops.overlap_wgrad else None
+
+        def off_path(fn):
+            if side is None:
+                return fn()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = fn()
+            out.record_stream(main)
+            return out
+
+        wgrad = lambda g, x: off_path(lambda: wgrad_(g, x))
         # ---- output block: LayerNorm-2 backward + dropout backward of the fc2 output
         dxo2 = torch.empty((R1, D), device=dev, dtype=torch.float32)
         df = torch.empty((R1, D), device=dev, dtype=dt)
@@ -198,12 +213,24 @@ class CrossLayerFn(torch.autograd.Function):
         dWo = wgrad(da, o)
         d_o = dgrad(da, wo_l)
         dq, dkv = _attn_bwd(q, kv, D, mask2, o, d_o, lse, B, H, L1, L2, scale, p_attn, seeds[0])
-        call("mmdti_colsum", dq, db_q, i32(R1), i32(D), i32(code), sp)
-        call("mmdti_colsum", dkv, db_kv, i32(R2), i32(2 * D), i32(code), sp)
-        dWq = wgrad(dq, s1l)
-        dWkv = wgrad(dkv, s2l)
+        def qkv_grads():
+            sps = stream_ptr()
+            call("mmdti_colsum", dq, db_q, i32(R1), i32(D), i32(code), sps)
+            call("mmdti_colsum", dkv, db_kv, i32(R2), i32(2 * D), i32(code), sps)
+            return wgrad_(dq, s1l), wgrad_(dkv, s2l)
+
+        if side is None:
+            dWq, dWkv = qkv_grads()
+        else:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dWq, dWkv = qkv_grads()
+            dWq.record_stream(main)
+            dWkv.record_stream(main)
         ds1 = dxo1 + dgrad(dq, wq_l)
         ds2 = dgrad(dkv, wkv_l).float()
+        if side is not None:
+            main.wait_stream(side)
         return (ds1.view(B, L1, D), ds2.view(B, L2, D), None, dWq, db_q, dWkv[:D], db_kv[:D], dWkv[D:], db_kv[D:], dWo, db_o, dw_ln1, db_ln1,
                 dW1, db_1, dW2, db_2, dw_ln2, db_ln2, None)
 
@@ -222,18 +249,19 @@ class MaskedPoolFn(torch.autograd.Function):
         x1, x2 = x1.detach().contiguous(), x2.detach().contiguous()
         m1, m2 = m1.detach().to(torch.uint8).contiguous(), m2.detach().to(torch.uint8).contiguous()
         out = torch.empty((B, D), device=x1.device, dtype=torch.float32)
-        call("mmdti_masked_pool_fwd", x1, m1, i32(L1), x2, m2, i32(L2), out, i32(B), i32(D), i32(DTYPE_CODE[x1.dtype]), stream_ptr())
-        ctx.save_for_backward(m1, m2)
+        inv = torch.empty(B, device=x1.device, dtype=torch.float32)
+        call("mmdti_masked_pool_fwd", x1, m1, i32(L1), x2, m2, i32(L2), out, inv, i32(B), i32(D), i32(DTYPE_CODE[x1.dtype]), stream_ptr())
+        ctx.save_for_backward(m1, m2, inv)
         ctx.dims = (B, L1, L2, D)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        m1, m2 = ctx.saved_tensors
+        m1, m2, inv = ctx.saved_tensors
         B, L1, L2, D = ctx.dims
         dx1 = torch.empty((B, L1, D), device=dout.device, dtype=torch.float32)
         dx2 = torch.empty((B, L2, D), device=dout.device, dtype=torch.float32)
-        call("mmdti_masked_pool_bwd", dout.contiguous().float(), m1, i32(L1), m2, i32(L2), dx1, dx2, i32(B), i32(D), stream_ptr())
+        call("mmdti_masked_pool_bwd", dout.contiguous().float(), inv, m1, i32(L1), m2, i32(L2), dx1, dx2, i32(B), i32(D), stream_ptr())
         return dx1, None, dx2, None
 
 
