@@ -214,16 +214,24 @@ class UnimolEncoder(nn.Module):
 
 
 class ChembertaEncoder(nn.Module):
-    """models/encoder.py:548-572: the HF SMILES encoder; stock PyTorch (out of the hot path).
-    ``model_name_or_path`` may also be a transformers config object (random init, offline)."""
+    """models/encoder.py:548-572: the HF SMILES encoder.  ``model_name_or_path``: a local checkpoint directory or a
+    transformers config object (random init, offline).  Configurations the fused layer covers (models/chemberta.supported:
+    hidden <= 512, head_dim 32 | 64 -- the 512-d ChemBERTa the reference's heads expect) run on the mmdti kernels with HF's
+    ``state_dict`` names; anything else is the stock HF module, with a warning."""
 
     def __init__(self, model_name_or_path, **params):
         super().__init__()
-        from transformers import AutoModel, PretrainedConfig
-        if isinstance(model_name_or_path, PretrainedConfig):
-            self.bert = AutoModel.from_config(model_name_or_path)
+        from transformers import AutoConfig, AutoModel, PretrainedConfig
+        from . import chemberta
+        is_cfg = isinstance(model_name_or_path, PretrainedConfig)
+        cfg = model_name_or_path if is_cfg else AutoConfig.from_pretrained(model_name_or_path)
+        if params.get("fused", True) and chemberta.supported(cfg):
+            self.bert = chemberta.RobertaModel(cfg) if is_cfg else chemberta.RobertaModel.from_pretrained(model_name_or_path)
         else:
-            self.bert = AutoModel.from_pretrained(model_name_or_path)
+            import warnings
+            warnings.warn("ChembertaEncoder: configuration outside the fused layer's range (hidden %d, %d heads): stock HF module"
+                          % (cfg.hidden_size, cfg.num_attention_heads))
+            self.bert = AutoModel.from_config(cfg) if is_cfg else AutoModel.from_pretrained(model_name_or_path)
 
     def forward(self, input_ids, attention_mask):
         return self.bert(input_ids, attention_mask, return_dict=True)[0]

@@ -617,6 +617,49 @@ def gold_cross_modal(ref):
     _save("cross_modal", d)
 
 
+def gold_chemberta(ref):
+    """the second-modality encoder as the reference runs it -- Hugging Face ``RobertaModel``
+    (models/mm_model.py:475,562), here a random-init 512-d stand-in (2 layers, 8 heads x 64, FFN 1024, vocab 64; the
+    reference's heads expect a 512-d ChemBERTa, models/mm_model.py:493), eval mode, ragged padding.
+    Weights: oracle/detw.py std 0.05 (not stored).  Stored: last_hidden_state, the gradient of the word / position
+    embeddings and 6 layer-parameter gradients (rows [:ROWS])."""
+    from transformers import RobertaConfig, RobertaModel
+    from oracle.detw import det_state_dict, det_tensor
+    ROWS, H, D, Fd, nl, V, P = 32, 8, 512, 1024, 2, 64, 48
+    cfg = RobertaConfig(vocab_size=V, hidden_size=D, num_hidden_layers=nl, num_attention_heads=H, intermediate_size=Fd,
+                        max_position_embeddings=P, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, pad_token_id=1)
+    net = RobertaModel(cfg)
+    sd = det_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=31, std=0.05)
+    net.load_state_dict(sd)
+    net.eval()
+    B, S = 3, 21
+    g = torch.Generator().manual_seed(77)
+    ids = torch.randint(4, V, (B, S), generator=g)
+    am = torch.ones(B, S, dtype=torch.long)
+    for b, n in enumerate((21, 9, 2)):
+        am[b, n:] = 0
+        ids[b, n:] = 1
+    out = net(ids, am, return_dict=True)[0]
+    up = det_tensor((B, S, D), 904, std=1.0) * am[..., None]
+    (out * up).sum().backward()
+    named = dict(net.named_parameters())
+    gsel = ["embeddings.word_embeddings.weight", "embeddings.position_embeddings.weight", "embeddings.LayerNorm.weight",
+            "encoder.layer.0.attention.self.query.weight", "encoder.layer.0.attention.self.value.bias",
+            "encoder.layer.0.output.dense.weight", "encoder.layer.1.attention.output.dense.weight",
+            "encoder.layer.1.intermediate.dense.bias", "encoder.layer.1.output.LayerNorm.weight"]
+    d = {"in.ids": ids, "in.mask": am, "in.up": up, "out.hidden": out, "cfg": np.array([H, D, Fd, nl, V, P, 31, ROWS])}
+    for k in gsel:
+        gr = named[k].grad
+        d["grad." + k] = gr[:ROWS] if (gr.dim() == 2 and "embeddings" not in k) else gr
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    mine = restate.roberta_encoder(ids, am, p, heads=H, n_layers=nl, eps=cfg.layer_norm_eps, pad_idx=1)
+    _close(mine * am[..., None], out * am[..., None], 2e-6, "chemberta.hidden")
+    (mine * up).sum().backward()
+    for k in gsel:
+        _close(p[k].grad, named[k].grad, 2e-5, "chemberta.grad." + k)
+    _save("chemberta", d)
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
@@ -630,6 +673,7 @@ def main():
     gold_featurise(ref)
     gold_loss(ref)
     gold_cross_modal(ref)
+    gold_chemberta(ref)
     print("all fixtures written and the restatement reproduces each of them")
 
 

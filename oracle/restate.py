@@ -485,3 +485,22 @@ def fuse_pool(cross_txt, cross, img_mask, attention_mask):
     b = cross * attention_mask[..., None].to(cross.dtype)
     final = torch.cat((a, b), dim=1)
     return final.sum(dim=1) / (img_mask.sum(dim=1).view(-1, 1) + attention_mask.sum(dim=1).view(-1, 1))
+
+
+# --------------------------------------------------------------------------- f4 ChemBERTa (HF RoBERTa encoder)
+def roberta_encoder(input_ids, attention_mask, p, heads, n_layers, eps=1e-12, pad_idx=1, prefix=""):
+    """``self.bert(input_ids, attention_mask, return_dict=True)[0]`` (models/mm_model.py:475,562): Hugging Face RobertaModel
+    (third-party ``transformers``, unpinned by the reference), dropout off.  Embeddings = word + token-type 0 + position
+    (position id = pad_idx + running count of non-padding tokens) -> LayerNorm; every layer is the post-LN block of
+    ``cross_layer`` with s1 = s2 (self-attention; HF masks padded keys with the dtype minimum instead of -10000: both give
+    exactly zero probability in fp32)."""
+    keep = input_ids.ne(pad_idx).int()
+    pos = (torch.cumsum(keep, dim=1) * keep).long() + pad_idx
+    e = prefix + "embeddings."
+    x = p[e + "word_embeddings.weight"][input_ids] + p[e + "token_type_embeddings.weight"][torch.zeros_like(input_ids)] \
+        + p[e + "position_embeddings.weight"][pos]
+    x = _bert_ln(x, p[e + "LayerNorm.weight"], p[e + "LayerNorm.bias"], eps)
+    for i in range(n_layers):
+        x = cross_layer(x, x, attention_mask, p, prefix + "encoder.layer.%d." % i, heads, eps)
+    return x
+

@@ -54,6 +54,8 @@ def build(ref, dropin, task="regression", layers=2):
         patch(mm, "InfoNCE", dinf.InfoNCE)
         patch(mm, "FDS", dfds.FDS)
         patch(mm, "CrossAttentionModel", dcm.CrossAttentionModel)
+        from mmdti_b200.models import chemberta as dcb
+        patch(mm, "AutoModel", dcb.RobertaModel)             # models/mm_model.py:475: AutoModel.from_pretrained(chemberta_dir)
         for n in ("CT_Regress", "CT_Single", "CT_Multi"):
             patch(ref["contrastive"], n, getattr(dct, n))
     try:

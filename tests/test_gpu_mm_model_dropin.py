@@ -26,7 +26,7 @@ def test_reference_mm_model_with_dropin_modules(task, report):
     m_ref = h.build(ref, dropin=False, task=task).to(dev).train()
     m_new = h.build(ref, dropin=True, task=task).to(dev).train()
     m_new.load_state_dict(m_ref.state_dict(), strict=True)          # identical state_dict names: the drop-in contract
-    assert type(m_new.cross_modal_module).__module__.startswith("mmdti_b200")
+    assert type(m_new.cross_modal_module).__module__.startswith("mmdti_b200") and type(m_new.bert).__module__.startswith("mmdti_b200")
     assert type(m_new.encoder).__module__.startswith("mmdti_b200") and type(m_ref.encoder).__module__ == "models.transformers"
     inp, y, w = h.batch()
     if task == "classification":
@@ -45,7 +45,8 @@ def test_reference_mm_model_with_dropin_modules(task, report):
     names = ["embed_tokens.weight", "gbf.means.weight", "gbf_proj.linear1.weight", "encoder.layers.0.self_attn.in_proj.weight",
              "encoder.layers.1.fc2.weight", "infonce.info_proj_query.0.weight", "cross_modal_module.text_attention.layer.0.attention.self.query.weight",
              "cross_modal_module.graph_attention.layer.0.output.dense.weight", "classification_head.dense.weight",
-             "bert.embeddings.word_embeddings.weight"]
+             "bert.embeddings.word_embeddings.weight", "bert.encoder.layer.0.attention.self.key.weight",
+             "bert.encoder.layer.1.output.dense.weight"]
     g_ref = {k: dict(m_ref.named_parameters())[k].grad.detach().clone() for k in names}
     for act, pair, ltol, gtol in (("fp32", "fp32", 2e-5, 2e-4), ("bf16", "bf16", 2e-2, 6e-2)):
         with mmdti_b200.precision(act=act, pair=pair):

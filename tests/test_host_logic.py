@@ -196,3 +196,31 @@ def test_pair_tensor_leading_dimension_rule():
     assert lib.mmdti_pair_ld(66) == 72 and lib.mmdti_pair_ld(258) == 264
     for L in (265, 512):
         assert lib.mmdti_pair_ld(L) == -1
+
+
+def test_chemberta_encoder_dispatch_and_checkpoint_loading(tmp_path):
+    """models/encoder.py:548-572 mirror: configurations the fused layer covers get mmdti_b200's RobertaModel (same state_dict names
+    as Hugging Face's, checkpoints load strictly), anything else the stock HF module with a warning."""
+    import warnings
+    import torch
+    from transformers import RobertaConfig, RobertaModel
+    from mmdti_b200.models import chemberta
+    from mmdti_b200.models.encoder import ChembertaEncoder
+    cfg = RobertaConfig(vocab_size=64, hidden_size=128, num_hidden_layers=2, num_attention_heads=4, intermediate_size=256,
+                        max_position_embeddings=40, pad_token_id=1)
+    hf = RobertaModel(cfg)
+    hf.save_pretrained(str(tmp_path))
+    enc = ChembertaEncoder(str(tmp_path))
+    assert isinstance(enc.bert, chemberta.RobertaModel)
+    want = hf.state_dict()
+    got = enc.bert.state_dict()
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    big = RobertaConfig(vocab_size=64, hidden_size=768, num_hidden_layers=1, num_attention_heads=12, intermediate_size=3072,
+                        max_position_embeddings=40, pad_token_id=1)
+    assert not chemberta.supported(big)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        stock = ChembertaEncoder(big)
+    assert type(stock.bert).__module__.startswith("transformers") and any("stock HF" in str(x.message) for x in w)

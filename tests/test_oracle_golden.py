@@ -153,3 +153,26 @@ def test_cross_modal_golden():
         if k.startswith("grad.") and k not in ("grad.x1", "grad.x2") and not k.endswith("key.bias"):
             got = p[k[5:]].grad
             assert rel_err(got[:ROWS] if got.dim() == 2 else got, v) < 5e-5, k
+
+
+def test_chemberta_golden():
+    """oracle/restate.py:roberta_encoder against the fixture made by Hugging Face's RobertaModel (the reference's second-modality
+    encoder, models/mm_model.py:475,562)."""
+    g = load_golden("chemberta")
+    H, D, Fd, nl, V, P, seed, ROWS = [int(v) for v in g["cfg"]]
+    from tests_util import cross_layer_shapes
+    shapes = {"embeddings.word_embeddings.weight": (V, D), "embeddings.token_type_embeddings.weight": (2, D),
+              "embeddings.position_embeddings.weight": (P, D), "embeddings.LayerNorm.weight": (D,), "embeddings.LayerNorm.bias": (D,),
+              "pooler.dense.weight": (D, D), "pooler.dense.bias": (D,)}
+    for i in range(nl):
+        shapes.update(cross_layer_shapes(D, Fd, "encoder.layer.%d." % i))
+    p = {k: v.requires_grad_(True) for k, v in det_state_dict(shapes, seed=seed, std=0.05).items()}
+    out = restate.roberta_encoder(g["in.ids"], g["in.mask"], p, heads=H, n_layers=nl)
+    m = g["in.mask"].bool()
+    assert rel_err(out[m], g["out.hidden"][m]) < 5e-6
+    (out * g["in.up"]).sum().backward()
+    for k, v in g.items():
+        if k.startswith("grad."):
+            got = p[k[5:]].grad
+            got = got[:ROWS] if (got.dim() == 2 and "embeddings" not in k) else got
+            assert rel_err(got, v) < 5e-5, k
