@@ -51,6 +51,9 @@ SPECS = {"encoder": (128, 64, 64, None, "weak"), "hotpath": (128, 64, 64, "regre
          "config3": (None, 64, 64, "classification", "strong"), "config4": (32, 256, 256, "regression", "weak"),
          "config5": (128, 64, 64, None, "weak")}
 GLOBAL_BATCH_CONFIG3 = 4096
+CHEMBERTA = False      # --chemberta: the second modality comes from a ChemBERTa-sized RoBERTa encoder in the step
+BERT_SHAPE = dict(vocab_size=600, hidden_size=512, num_hidden_layers=6, num_attention_heads=8, intermediate_size=2048,
+                  max_position_embeddings=515, pad_token_id=1)       # 512-d stand-in: the reference's heads expect 512 (mm_model.py:493)
 FUSION = True          # --no-fusion: pool the encoder output directly (the round-1 step, without SURVEY.md §8 row f2)
 
 
@@ -63,6 +66,8 @@ def set_shape(batch, n_atoms, smiles_len):
         WORKLOADS[k] = _NAMES[k].replace("b128x64atoms", "b%dx%datoms" % (batch, n_atoms))
         if not FUSION:
             WORKLOADS[k] = WORKLOADS[k].replace("+cross_fusion", "")
+        if CHEMBERTA and "+infonce" in WORKLOADS[k] and "chemberta" not in WORKLOADS[k]:
+            WORKLOADS[k] = WORKLOADS[k].replace("+infonce", "+chemberta_6L_512d+infonce")
 
 
 def peaks():
@@ -140,6 +145,15 @@ def make_head_batch(seed, n=None, task="regression"):
              "smoothed_mean_last_epoch": torch.randn(FDS_BUCKETS, DIM, generator=sg) * 0.1,
              "smoothed_var_last_epoch": torch.rand(FDS_BUCKETS, DIM, generator=sg) + 0.5}
     return smiles, y, w, stats
+
+
+def smiles_ids(seed, n=None):
+    """Token ids of the second modality for --chemberta: random ids under the ragged mask of smiles_mask, padding id 1."""
+    n = B_PER_GPU if n is None else n
+    gen = torch.Generator().manual_seed(seed + 19)
+    ids = torch.randint(4, BERT_SHAPE["vocab_size"], (n, S_SMILES), generator=gen)
+    ids[~smiles_mask(seed, n)] = BERT_SHAPE["pad_token_id"]
+    return ids
 
 
 def smiles_mask(seed, n=None):
@@ -228,6 +242,12 @@ def cpu_reference_run(steps, warmup, sample_b=32, workload="hotpath"):
             pi = {"infonce." + k: v for k, v in inf.named_parameters()}
         head_params = list(inf.parameters()) + list(head.parameters())
         mask = tokens.ne(0).float().unsqueeze(-1)
+        if CHEMBERTA:
+            # models/mm_model.py:475,562: the reference's own second-modality encoder = Hugging Face RobertaModel
+            from transformers import RobertaConfig, RobertaModel
+            bert = RobertaModel(RobertaConfig(**BERT_SHAPE)).train()
+            ids_c, am_c = smiles_ids(1234, sample_b), smiles_mask(1234, sample_b).long()
+            head_params += list(bert.parameters())
         if FUSION:
             # cross-modal fusion + pooling, models/mm_model.py:571-576 (the reference's CrossAttentionModel, else the port)
             img_mask, txt_mask = tokens.ne(0), smiles_mask(1234, sample_b)
@@ -259,6 +279,8 @@ def cpu_reference_run(steps, warmup, sample_b=32, workload="hotpath"):
         if task is None:
             (rep * g).sum().backward()
         else:
+            if CHEMBERTA:
+                smiles = bert(ids_c, am_c, return_dict=True)[0]
             l_inf = inf(rep, smiles) if ref is not None else restate.infonce_head(rep, smiles, pi)
             pooled = pool(rep)
             if task == "regression":
@@ -384,10 +406,16 @@ def run_ours(args, rank, local_rank, world):
             getattr(fds, k).copy_(v)
         d_smiles = smiles.to(dev)
         extra_params = list(inf.parameters()) + list(head.parameters())
+        d_txt_mask = smiles_mask(1234 + rank).to(dev)
+        if CHEMBERTA:
+            from transformers import RobertaConfig
+            from mmdti_b200.models.encoder import ChembertaEncoder
+            bert = ChembertaEncoder(RobertaConfig(**BERT_SHAPE)).to(dev).train()
+            ids_h = smiles_ids(1234 + rank)
+            extra_params += list(bert.parameters())
         if FUSION:
             from mmdti_b200.models.cross_modal import CrossAttentionModel, crossmodal_config, fuse_and_pool
             cross = CrossAttentionModel(crossmodal_config(), num_layers=1).to(dev).train()
-            d_txt_mask = smiles_mask(1234 + rank).to(dev)
             extra_params += list(cross.parameters())
         dp_ctx = None
         if dist_on:
@@ -412,6 +440,8 @@ def run_ours(args, rank, local_rank, world):
     n_enc_in = len(host_inputs)
     if hot:
         host_inputs = host_inputs + (y_h, w_h)             # targets and sample weights travel with the batch
+        if CHEMBERTA:
+            host_inputs = host_inputs + (ids_h,)           # and the SMILES token ids
     pin = [t.pin_memory() for t in host_inputs]
     dev_inputs = [t.to(dev) for t in host_inputs]
     d_g = g.to(dev)
@@ -437,10 +467,11 @@ def run_ours(args, rank, local_rank, world):
         if hot:
             y_d, w_d = inp[n_enc_in], inp[n_enc_in + 1]
             rep = rep.float()
-            l_inf = inf(rep, d_smiles)                                     # a7: InfoNCE against the second modality
+            out_bert = bert(inp[n_enc_in + 2], d_txt_mask) if CHEMBERTA else d_smiles      # f4 (mm_model.py:562)
+            l_inf = inf(rep, out_bert)                                     # a7: InfoNCE against the second modality
             if FUSION:                                                      # f2: cross-modal fusion + masked pooling (mm_model.py:571-576)
                 img_mask = inp[0].ne(0)
-                t2g, g2t = cross(rep, d_smiles, img_mask, d_txt_mask)
+                t2g, g2t = cross(rep, out_bert, img_mask, d_txt_mask)
                 pooled = fuse_and_pool(t2g, g2t, img_mask, d_txt_mask)
             else:
                 mk = inp[0].ne(0).unsqueeze(-1).float()
@@ -769,6 +800,8 @@ def main():
     ap.add_argument("--smiles-len", type=int, default=None, help="length of the second-modality sequence")
     ap.add_argument("--cpu-sample", type=int, default=32, help="molecules per step of the CPU arm's bounded sample")
     ap.add_argument("--nmax", type=int, default=65536, help="config5: largest N of the sweep")
+    ap.add_argument("--chemberta", action="store_true", help="run a ChemBERTa-sized RoBERTa encoder (6 layers, 512-d) on SMILES token ids "
+                    "inside the step instead of the resident stand-in tensor (SURVEY.md 8 row f4)")
     ap.add_argument("--no-fusion", action="store_true", help="leave the cross-modal fusion block (SURVEY.md 8 row f2) out of the step")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -776,8 +809,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     n_ranks = max(world, args.gpus)
-    global FUSION
+    global FUSION, CHEMBERTA
     FUSION = not args.no_fusion
+    CHEMBERTA = args.chemberta
     b0, a0, s0 = SPECS[args.workload][:3]
     if b0 is None:                                      # config 3: the GLOBAL batch is fixed (strong scaling)
         if GLOBAL_BATCH_CONFIG3 % n_ranks:
