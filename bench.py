@@ -471,8 +471,7 @@ def run_ours(args, rank, local_rank, world):
             l_inf = inf(rep, out_bert)                                     # a7: InfoNCE against the second modality
             if FUSION:                                                      # f2: cross-modal fusion + masked pooling (mm_model.py:571-576)
                 img_mask = inp[0].ne(0)
-                t2g, g2t = cross(rep, out_bert, img_mask, d_txt_mask)
-                pooled = fuse_and_pool(t2g, g2t, img_mask, d_txt_mask)
+                pooled = cross.forward_pooled(rep, out_bert, img_mask, d_txt_mask)
             else:
                 mk = inp[0].ne(0).unsqueeze(-1).float()
                 pooled = (rep * mk).sum(1) / mk.sum(1)

@@ -236,6 +236,9 @@ int mmdti_dropout_residual_fwd(const float* res, const void* a, float* out, int6
 /* da = dropout'(dx) in da_dtype (rows,C); dbias (C) f32 += column sums of da (NULL to skip). */
 int mmdti_dropout_bwd(const float* dx, void* da, float* dbias, int rows, int C, float p,
                       uint64_t seed, int da_dtype, void* stream);
+/* dst (n) dst_dtype = (float)src (n) src_dtype + (add ? add (n) f32 : 0): dtype conversions and residual adds between fused
+ * GEMMs (the post-LN layers of mm_module.py:525-536,578-589 keep their residual in fp32).  n % 8 == 0, f32 | bf16. */
+int mmdti_convert_add(const void* src, int src_dtype, const float* add, void* dst, int dst_dtype, int64_t n, void* stream);
 /* exact-erf GELU (unicore.utils.get_activation_fn("gelu") = F.gelu) and its backward:
  * dz = du * gelu'(z); dbias (C) f32 += column sums of dz (NULL to skip). */
 int mmdti_gelu_fwd(const void* z, void* u, int64_t n, int dtype, void* stream);   /* n % 8 == 0 */

@@ -572,6 +572,21 @@ inline int rowmap_ctas_per_sm() {
     return v;
 }
 
+// dst = (float)src (+ add): the dtype conversions / residual adds between fused GEMMs that have no epilogue to live in
+// (ops_cross.py: bf16 LayerNorm output -> fp32 residual, bf16 dgrad + fp32 residual gradient).  8 elements per thread.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) convert_add_kernel(const TS* __restrict__ src, const float* __restrict__ add, TD* __restrict__ dst, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        load8(src + i * 8, v);
+        if (add) {
+            const float4 a = *reinterpret_cast<const float4*>(add + i * 8), b = *reinterpret_cast<const float4*>(add + i * 8 + 4);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        store8(dst + i * 8, v);
+    }
+}
+
 inline int ew_grid(long long work_items, int per_block) {
     return (int)std::max<long long>(1, std::min<long long>((work_items + per_block - 1) / per_block, (long long)num_sms() * 8));
 }
@@ -719,6 +734,24 @@ extern "C" int mmdti_dropout_bwd(const float* dx, void* da, float* dbias, int ro
     if (da_dtype == MMDTI_F32) launch_rowmap<float, float, OP_DROPOUT_BWD>(dx, nullptr, da, dbias, rows, C, key, th, ks, st);
     else if (da_dtype == MMDTI_BF16) launch_rowmap<float, bf16, OP_DROPOUT_BWD>(dx, nullptr, da, dbias, rows, C, key, th, ks, st);
     else { mmdti_set_error("dropout_bwd: da_dtype must be f32 or bf16"); return MMDTI_ERR_ARG; }
+    MMDTI_LAUNCH_OK();
+    return MMDTI_OK;
+}
+
+extern "C" int mmdti_convert_add(const void* src, int src_dtype, const float* add, void* dst, int dst_dtype, int64_t n, void* stream) {
+    MMDTI_REQUIRE(src && dst && n > 0 && n % 8 == 0, "convert_add: n must be a positive multiple of 8");
+    MMDTI_REQUIRE(mmdti_aligned(src, 16) && mmdti_aligned(dst, 16) && (!add || mmdti_aligned(add, 16)), "convert_add: 16-byte aligned buffers");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ew_grid(n / 8, 256);
+    if (src_dtype == MMDTI_BF16 && dst_dtype == MMDTI_F32)
+        convert_add_kernel<bf16, float><<<grid, 256, 0, st>>>(static_cast<const bf16*>(src), add, static_cast<float*>(dst), n / 8);
+    else if (src_dtype == MMDTI_F32 && dst_dtype == MMDTI_BF16)
+        convert_add_kernel<float, bf16><<<grid, 256, 0, st>>>(static_cast<const float*>(src), add, static_cast<bf16*>(dst), n / 8);
+    else if (src_dtype == MMDTI_F32 && dst_dtype == MMDTI_F32)
+        convert_add_kernel<float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(src), add, static_cast<float*>(dst), n / 8);
+    else if (src_dtype == MMDTI_BF16 && dst_dtype == MMDTI_BF16)
+        convert_add_kernel<bf16, bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(src), add, static_cast<bf16*>(dst), n / 8);
+    else { mmdti_set_error("convert_add: dtypes must be f32 or bf16"); return MMDTI_ERR_ARG; }
     MMDTI_LAUNCH_OK();
     return MMDTI_OK;
 }

@@ -55,8 +55,8 @@ class RobertaEncoder(nn.Module):
         self.layer = nn.ModuleList([BertCrossAttentionLayer(cfg) for _ in range(cfg.num_hidden_layers)])
 
     def forward(self, x, attention_mask):
-        for layer in self.layer:
-            x = layer(x, x, attention_mask)            # self-attention: queries, keys and values from the same stream
+        for i, layer in enumerate(self.layer):          # self-attention: queries, keys and values from the same stream;
+            x = layer(x, x, attention_mask, out_f32=i == len(self.layer) - 1)      # fp32 only out of the last layer
         return x
 
 

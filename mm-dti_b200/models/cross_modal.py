@@ -81,9 +81,11 @@ class BertCrossAttentionLayer(nn.Module):
         self.intermediate = _Intermediate(cfg)
         self.output = _DenseNorm(cfg.intermediate_size, cfg)
 
-    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask):
+    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask, out_f32=True):
         """``s2_attention_mask``: (B, L2) bool / 0-1 (1 = attend), or the reference's extended additive form
-        (B, 1, 1, L2) with 0 / -10000 (models/mm_model.py:393-394)."""
+        (B, 1, 1, L2) with 0 / -10000 (models/mm_model.py:393-394).  ``out_f32`` (default): fp32 output like the reference
+        under autocast (LayerNorm output), a fresh tensor because the caller zeroes masked rows IN PLACE (mm_model.py:572-573);
+        False: the activation dtype, for consumers that read bf16 (the next layer of a stack, fuse_and_pool)."""
         m = s2_attention_mask
         if m.dim() == 4:
             m = m[:, 0, 0, :] > -5000.0
@@ -94,15 +96,12 @@ class BertCrossAttentionLayer(nn.Module):
         if att.output.dropout.p != out.dropout.p:
             raise ValueError("cross-modal layer: one hidden dropout rate per layer")
         seeds = (ops.next_seed(), ops.next_seed(), ops.next_seed()) if train else (0, 0, 0)
-        cfg = (att.self.num_attention_heads, p_attn, p_hid, seeds, config.act_dtype(), att.output.LayerNorm.variance_epsilon)
-        # fp32 out like the reference under autocast (LayerNorm output), so the caller's pooling / heads see full precision; a
-        # fresh tensor, because the caller zeroes masked rows IN PLACE (models/mm_model.py:572-573)
-        y = ops_cross.CrossLayerFn.apply(
+        cfg = (att.self.num_attention_heads, p_attn, p_hid, seeds, config.act_dtype(), att.output.LayerNorm.variance_epsilon, out_f32)
+        return ops_cross.CrossLayerFn.apply(
             s1_hidden_states, s2_hidden_states, m, att.self.query.weight, att.self.query.bias, att.self.key.weight, att.self.key.bias,
             att.self.value.weight, att.self.value.bias, att.output.dense.weight, att.output.dense.bias, att.output.LayerNorm.weight,
             att.output.LayerNorm.bias, self.intermediate.dense.weight, self.intermediate.dense.bias, out.dense.weight, out.dense.bias,
             out.LayerNorm.weight, out.LayerNorm.bias, cfg)
-        return y.float() if y.dtype != torch.float32 else y.clone()
 
 
 class BertCrossEncoder(nn.Module):
@@ -112,10 +111,12 @@ class BertCrossEncoder(nn.Module):
         for l in self.layer[1:]:                      # the reference deep-copies ONE initialised layer (mm_module.py:666-667)
             l.load_state_dict(self.layer[0].state_dict())
 
-    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask, output_all_encoded_layers=True):
+    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask, output_all_encoded_layers=True, out_f32=True):
         outs = []
-        for layer in self.layer:
-            s1_hidden_states = layer(s1_hidden_states, s2_hidden_states, s2_attention_mask)
+        for i, layer in enumerate(self.layer):
+            last = i == len(self.layer) - 1
+            s1_hidden_states = layer(s1_hidden_states, s2_hidden_states, s2_attention_mask,
+                                     out_f32=out_f32 and (last or output_all_encoded_layers))
             if output_all_encoded_layers:
                 outs.append(s1_hidden_states)
         if not output_all_encoded_layers:
@@ -133,12 +134,17 @@ class CrossAttentionModel(nn.Module):
         self.graph_attention = BertCrossEncoder(cross_cfg, num_layers)
         self.dropout = nn.Dropout(cross_cfg.hidden_dropout_prob)
 
-    def forward(self, text_embeddings, graph_embeddings, text_mask, graph_mask):
+    def forward(self, text_embeddings, graph_embeddings, text_mask, graph_mask, out_f32=True):
         t = ops_cross.flat_dropout(text_embeddings, self.dropout.p, self.training)
         g = ops_cross.flat_dropout(graph_embeddings, self.dropout.p, self.training)
-        graph_to_text = self.graph_attention(g, t, text_mask)[-1]
-        text_to_graph = self.text_attention(t, g, graph_mask)[-1]
+        graph_to_text = self.graph_attention(g, t, text_mask, out_f32=out_f32)[-1]
+        text_to_graph = self.text_attention(t, g, graph_mask, out_f32=out_f32)[-1]
         return text_to_graph, graph_to_text
+
+    def forward_pooled(self, text_embeddings, graph_embeddings, text_mask, graph_mask):
+        """forward + the masked mean pooling of models/mm_model.py:572-576 without the fp32 copies of the two outputs."""
+        t2g, g2t = self.forward(text_embeddings, graph_embeddings, text_mask, graph_mask, out_f32=False)
+        return fuse_and_pool(t2g, g2t, text_mask, graph_mask)
 
 
 def fuse_and_pool(cross_txt_output_layer, cross_output_layer, img_mask, attention_mask):

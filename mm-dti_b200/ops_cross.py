@@ -22,6 +22,17 @@ def cross_attn_dropout_mask(B, H, Lq, Lk, p, seed, device="cuda"):
     return keep.bool()
 
 
+def _convert(src, dst_dtype, add=None, shape=None, copy=False):
+    """dst = float(src) (+ add, fp32) in one vectorised pass (mmdti_convert_add); the no-op cases return src unless ``copy``.
+    ``shape``: shape of the result (same element count) -- a fresh base tensor, not a view."""
+    if add is None and src.dtype == dst_dtype and not copy:
+        return src
+    src = src.contiguous()
+    dst = torch.empty(src.shape if shape is None else shape, device=src.device, dtype=dst_dtype)
+    call("mmdti_convert_add", src, i32(DTYPE_CODE[src.dtype]), add, dst, i32(DTYPE_CODE[dst_dtype]), i64(src.numel()), stream_ptr())
+    return dst
+
+
 def _attn_fwd(q, kv, D, mask2, B, H, Lq, Lk, scale, p, seed):
     o = torch.empty((B * Lq, D), device=q.device, dtype=q.dtype)
     lse = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
@@ -95,7 +106,8 @@ class CrossLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, s1, s2, mask2, wq, bq, wk, bk, wv, bv, wo, bo, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b, cfg):
-        H, p_attn, p_hid, seeds, dt, eps = cfg
+        H, p_attn, p_hid, seeds, dt, eps = cfg[:6]
+        out_f32 = len(cfg) > 6 and cfg[6]            # fp32 copy of the output, made here (a fresh tensor: callers may write into it)
         _lib.require_cuda(s1, s2)
         B, L1, D = s1.shape
         L2 = s2.shape[1]
@@ -107,15 +119,24 @@ class CrossLayerFn(torch.autograd.Function):
         fused = dt == torch.bfloat16 and ops_gemm.supported(D, F_) and (D // H) in (32, 64)
         if dt == torch.bfloat16 and not fused:
             raise _lib.MMDTIError("cross layer: bf16 mode needs hidden %% 64 == 0, hidden <= 512 and head_dim 32 or 64 (got D=%d, H=%d)" % (D, H))
-        s1f = s1.detach().reshape(R1, D).contiguous().float()
-        s2f = s2.detach().reshape(R2, D).contiguous().float()
+        def both(t, rows):
+            """(fp32, activation-dtype) copies of an input stream, each made at most once by the vectorised convert kernel"""
+            t = t.detach().reshape(rows, D).contiguous()
+            if t.dtype == torch.float32:
+                return t, _convert(t, dt)
+            if t.dtype == dt:
+                return _convert(t, torch.float32), t
+            tf = t.float()
+            return tf, _convert(tf, dt)
+
+        s1f, s1l = both(s1, R1)
+        s2f, s2l = (s1f, s1l) if s2 is s1 else both(s2, R2)
         mask2 = mask2.detach().to(torch.uint8).contiguous()
         lw = lambda t: t.detach().to(dt).contiguous()
         wq_l, wo_l, w1_l, w2_l = lw(wq), lw(wo), lw(w1), lw(w2)
         wkv_l = torch.cat([wk.detach(), wv.detach()], 0).to(dt)
         bkv_l = torch.cat([bk.detach(), bv.detach()], 0).to(dt)
         ln1_wd, ln1_bd, ln2_wd, ln2_bd = (t.detach().float().contiguous() for t in (ln1_w, ln1_b, ln2_w, ln2_b))
-        s1l, s2l = s1f.to(dt), s2f.to(dt)
         if fused:
             q = ops_gemm.gemm_bias(s1l, wq_l, lw(bq))
             kv = ops_gemm.gemm_bias(s2l, wkv_l, bkv_l)
@@ -125,7 +146,7 @@ class CrossLayerFn(torch.autograd.Function):
         o, lse = _attn_fwd(q, kv, D, mask2, B, H, L1, L2, scale, p_attn, seeds[0])
         if fused:
             xo1, a, st1 = ops_gemm.gemm_dropres_ln(o, wo_l, lw(bo), s1f, ln1_wd, ln1_bd, p_hid, seeds[1], eps=eps)
-            a_res = a.float()
+            a_res = _convert(a, torch.float32)
             z, u = ops_gemm.gemm_bias_gelu(a, w1_l, lw(b1), store_grad=True)
             xo2, y, st2 = ops_gemm.gemm_dropres_ln(u, w2_l, lw(b2), a_res, ln2_wd, ln2_bd, p_hid, seeds[2], eps=eps)
         else:
@@ -146,12 +167,14 @@ class CrossLayerFn(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.fused = fused
         ctx.dims = (B, L1, L2, D, F_)
+        if out_f32:
+            return _convert(y, torch.float32, shape=(B, L1, D), copy=True)
         return y.view(B, L1, D)
 
     @staticmethod
     def backward(ctx, dy):
         (s1l, s2l, mask2, q, kv, o, lse, xo1, st1, a, z, u, xo2, st2, ln1_w, ln2_w, wq_l, wkv_l, wo_l, w1_l, w2_l) = ctx.saved_tensors
-        H, p_attn, p_hid, seeds, dt, eps = ctx.cfg
+        H, p_attn, p_hid, seeds, dt, eps = ctx.cfg[:6]
         B, L1, L2, D, F_ = ctx.dims
         R1, R2 = B * L1, B * L2
         code = DTYPE_CODE[dt]
@@ -188,7 +211,7 @@ class CrossLayerFn(torch.autograd.Function):
         # ---- output block: LayerNorm-2 backward + dropout backward of the fc2 output
         dxo2 = torch.empty((R1, D), device=dev, dtype=torch.float32)
         df = torch.empty((R1, D), device=dev, dtype=dt)
-        call("mmdti_layernorm_bwd_dropout", dy if dt == torch.float32 else dy.to(dt), xo2, ln2_w, st2[0], st2[1], None, dxo2, dw_ln2, db_ln2,
+        call("mmdti_layernorm_bwd_dropout", _convert(dy, dt), xo2, ln2_w, st2[0], st2[1], None, dxo2, dw_ln2, db_ln2,
              df, db_2, i32(R1), i32(D), f32(p_hid), u64(seeds[2]), i32(code), sp)
         dW2 = wgrad(df, u)
         if fused:
@@ -227,8 +250,8 @@ class CrossLayerFn(torch.autograd.Function):
                 dWq, dWkv = qkv_grads()
             dWq.record_stream(main)
             dWkv.record_stream(main)
-        ds1 = dxo1 + dgrad(dq, wq_l)
-        ds2 = dgrad(dkv, wkv_l).float()
+        ds1 = _convert(dgrad(dq, wq_l), torch.float32, add=dxo1)
+        ds2 = _convert(dgrad(dkv, wkv_l), torch.float32)
         if side is not None:
             main.wait_stream(side)
         return (ds1.view(B, L1, D), ds2.view(B, L2, D), None, dWq, db_q, dWkv[:D], db_kv[:D], dWkv[D:], db_kv[D:], dWo, db_o, dw_ln1, db_ln1,
