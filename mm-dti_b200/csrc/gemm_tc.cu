@@ -77,7 +77,7 @@ __device__ __forceinline__ uint32_t ew_bits_full(uint32_t key, unsigned long lon
     return mix32(key ^ (uint32_t)pr ^ mix32((uint32_t)(pr >> 32) + 0x27d4eb2fU));
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(NUM_EPI_THREADS) : "memory"); }
+template <int NTHR> __device__ __forceinline__ void epi_bar_n() { asm volatile("bar.sync 1, %0;\n" ::"n"(NTHR) : "memory"); }
 
 // ---- cluster helpers (2-CTA LayerNorm epilogues)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -138,26 +138,33 @@ constexpr int SLAB_BYTES = BM * 64;              // staging slab: 128 rows x 64 
 __host__ __device__ constexpr bool epi_has_input(int epi) { return epi == EPI_GELU_BWD || epi == EPI_DROPRES_LN || epi == EPI_LNBWD_DROP; }
 __host__ __device__ constexpr int epi_stages(int epi) { return epi_has_input(epi) ? 3 : 4; }
 
-template <int NST>
+// NG = column groups of the epilogue (4 warps each): 2 with 8 epilogue warps, 4 with 16
+template <int NST, int NG = 2, bool HAS_IN = (NST == 3)>
 struct SmemT {
     static constexpr uint32_t stages = 0;
-    static constexpr int n_out = NST == 3 ? 2 : 1;                     // output slabs per column half (double-buffered when there is room)
+    static constexpr int n_out = (NST == 3 && NG == 2) ? 2 : 1;        // output slabs per column group (double-buffered when there is room)
+    static constexpr int n_in = HAS_IN ? 4 / NG : 0;                   // input slabs per column group: 2 (two groups) or 1 (four groups)
     static constexpr uint32_t ostage = NST * STAGE_BYTES;
-    static constexpr uint32_t istage = ostage + 2 * n_out * SLAB_BYTES;      // input slabs, two per column half (NST == 3 only)
-    static constexpr uint32_t bars = istage + (NST == 3 ? 4 * SLAB_BYTES : 0);      // mbarriers + tmem slot (256 bytes)
+    static constexpr uint32_t istage = ostage + NG * n_out * SLAB_BYTES;     // input slabs (epilogues with a per-row operand only)
+    static constexpr uint32_t bars = istage + NG * n_in * SLAB_BYTES;  // mbarriers + tmem slot (256 bytes)
     static constexpr uint32_t cs = bars + 256;                        // column-sum scratch: 3 x 256 floats
     static constexpr uint32_t xchg = cs + 3 * BN * 4;                 // [2 parities][4 slots][128 rows] float2
     static constexpr uint32_t vec = xchg + 2 * 4 * BM * 8;            // per-tile column vectors: [2 tiles][bias | ln_w | ln_b][256]
     static constexpr uint32_t total = vec + 2 * 3 * BN * 4;
 };
 
-template <int AMN, int BMN, int EPI, int NCTA>
-__global__ void __launch_bounds__(NUM_THREADS, 1)      // 10 warps: one scheduler holds 3 of them => 168 registers per thread
+// NEW = epilogue warps: 8 (10 warps per CTA: one scheduler holds 3 of them => 168 registers per thread) or 16 (18 warps, 112
+// registers: for the ALU-heavy epilogues that fit, 4 warps per scheduler keep the issue slots busy where 2 could not)
+template <int AMN, int BMN, int EPI, int NCTA, int NEW = NUM_EPI_WARPS>
+__global__ void __launch_bounds__(64 + NEW * 32, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
                const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmI0, const __grid_constant__ CUtensorMap tmI1,
                const GemmParams p) {
-    constexpr int NSTAGE = epi_stages(EPI);
-    using Smem = SmemT<NSTAGE>;
+    constexpr int NET = NEW * 32, NTHR = 64 + NET, NG = NEW / 4;      // epilogue threads, CTA threads, column groups
+    static_assert(NEW == 8 || (NEW == 16 && NCTA == 1 && (!epi_has_input(EPI) || EPI == EPI_GELU_BWD)), "16 epilogue warps: bias / GELU epilogues only");
+    constexpr int NSTAGE = NEW == 16 ? 3 : epi_stages(EPI);
+    using Smem = SmemT<NSTAGE, NG, epi_has_input(EPI)>;
+    auto epi_bar = [] { epi_bar_n<NET>(); };
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,17 +191,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], NUM_EPI_THREADS);
-            mbar_init(&xbar[i], NCTA * NUM_EPI_THREADS);
+            mbar_init(&tempty[i], NET);
+            mbar_init(&xbar[i], NCTA * NET);
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&inbar[i], 1);
             mbar_init(&sfull[i], 1);
-            mbar_init(&sempty[i], 1 + NUM_EPI_THREADS);
+            mbar_init(&sempty[i], 1 + NET);
         }
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < 3 * BN; i += NUM_THREADS) s_cs[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * BN; i += NTHR) s_cs[i] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
                      : "memory");
@@ -319,11 +326,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // weight / bias) are fetched BEFORE the wait for the accumulator and staged in shared memory (broadcast reads);
         // per-row operands (residual, z, dx_add) are register-prefetched one 32-column chunk ahead.
         const int ew = warp - 2;
-        const int quad = warp & 3, half = ew >> 2;
-        const int et = ew * 32 + lane;                    // 0..255
+        const int quad = warp & 3, half = ew >> 2;        // `half` = column group of this warp: 0..NG-1
+        const int et = ew * 32 + lane;                    // 0..NET-1
         const int r = quad * 32 + lane;                   // accumulator row of this thread inside the tile
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        constexpr int HC = BN / 2;                        // columns per epilogue thread
+        constexpr int HC = BN / NG;                       // columns per epilogue thread
         constexpr int NCH = HC / 32;                      // 32-column chunks per thread
         constexpr bool HAS_VEC = EPI == EPI_BIAS || EPI == EPI_BIAS_GELU || EPI == EPI_DROPRES_LN || EPI == EPI_LNBWD_DROP;
         uint32_t key = 0, fkey = 0;
@@ -367,18 +374,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         // input slabs: the leader of a column half issues TMA loads (two buffers, one mbarrier each); every thread waits
         // for the slab and reads its own 64-byte row segment (swizzled: conflict-free).  Counters are uniform per half.
-        unsigned char* islab = smem + Smem::istage + half * 2 * SLAB_BYTES;
-        uint64_t* ibar = inbar + half * 2;
+        constexpr int NIB = Smem::n_in > 0 ? Smem::n_in : 1;              // input buffers per column group
+        unsigned char* islab = smem + Smem::istage + half * NIB * SLAB_BYTES;
+        uint64_t* ibar = inbar + half * NIB;
         uint32_t in_issued = 0, in_read = 0;              // in_issued is only meaningful in the leader
         auto in_issue = [&](const CUtensorMap* tm, int col, int row0) {
-            const int b = in_issued & 1;
+            const int b = in_issued % NIB;
             mbar_arrive_expect_tx(&ibar[b], SLAB_BYTES);
             tma_load_2d(islab + b * SLAB_BYTES, tm, col, row0, &ibar[b]);
             ++in_issued;
         };
         auto in_take = [&](uint4 (&d)[4]) {
-            const int b = in_read & 1;
-            mbar_wait_g(&ibar[b], (in_read >> 1) & 1);
+            const int b = in_read % NIB;
+            mbar_wait_g(&ibar[b], (in_read / NIB) & 1);
             const unsigned char* rowp = islab + b * SLAB_BYTES + r * 64;
             const int sw = (r >> 1) & 3;
 #pragma unroll
@@ -400,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int cb = half * HC;                     // first column of this thread inside the tile
             float* sv = s_vec + (it & 1) * (3 * BN);      // column vectors of this tile: [0] bias, [1] ln_w, [2] ln_b
             float pv0 = 0.f, pv1 = 0.f, pv2 = 0.f;
-            if (HAS_VEC && n0 + et < p.N) {
+            if (HAS_VEC && et < BN && n0 + et < p.N) {
                 if (EPI != EPI_LNBWD_DROP) pv0 = __bfloat162float(p.bias[n0 + et]);
                 if (EPI == EPI_LNBWD_DROP || (EPI == EPI_DROPRES_LN && p.ln_w)) pv1 = __ldg(p.ln_w + n0 + et);
                 if (EPI == EPI_DROPRES_LN && p.ln_w) pv2 = __ldg(p.ln_b + n0 + et);
@@ -410,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int IN_W = EPI == EPI_GELU_BWD ? 32 : 16;
             if (epi_has_input(EPI) && slab_leader) {
                 in_issue(&tmI0, n0 + cb, row0);
-                in_issue(&tmI0, n0 + cb + IN_W, row0);
+                if (NIB > 1) in_issue(&tmI0, n0 + cb + IN_W, row0);
             }
             float mu = 0.f, rs = 0.f;
             if (EPI == EPI_LNBWD_DROP && row_ok) { mu = p.mean[row]; rs = p.rstd[row]; }
@@ -418,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait_g(&tfull[buf], use & 1);
             tc_fence_after();
             if (HAS_VEC) {
-                sv[et] = pv0; sv[BN + et] = pv1; sv[2 * BN + et] = pv2;
+                if (et < BN) { sv[et] = pv0; sv[BN + et] = pv1; sv[2 * BN + et] = pv2; }
                 epi_bar();
             }
 
@@ -475,7 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     out_acquire();
                     in_take(zq);
                     half_bar();                                       // everybody has read the slab: refill it
-                    if (slab_leader && ci + 2 < N_IN) in_issue(&tmI0, n0 + c0 + 64, row0);
+                    if (slab_leader && ci + NIB < N_IN) in_issue(&tmI0, n0 + c0 + NIB * 32, row0);
                     uint32_t v[32];
                     tc_ld32(acc_addr + c0, v);
                     float cs[32];
@@ -501,8 +509,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     atomicAdd(&s_cs[c0 + lane], tot);
                 }
                 epi_bar();
-                if (n0 + et < p.N && s_cs[et] != 0.f) atomicAdd(p.colsum0 + n0 + et, s_cs[et]);
-                s_cs[et] = 0.f;
+                if (et < BN) {
+                    if (n0 + et < p.N && s_cs[et] != 0.f) atomicAdd(p.colsum0 + n0 + et, s_cs[et]);
+                    s_cs[et] = 0.f;
+                }
                 epi_bar();
             } else if constexpr (EPI == EPI_DROPRES_LN) {
                 const int xpar = it & 1;
@@ -798,7 +808,7 @@ int* sched_slot() {
     return base[dev] + 2 * (next[dev]++ % SLOTS);
 }
 
-template <int AMN, int BMN, int EPI, int NCTA>
+template <int AMN, int BMN, int EPI, int NCTA, int NEW = NUM_EPI_WARPS>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st, const CUtensorMap* tmO0 = nullptr,
            const CUtensorMap* tmO1 = nullptr, const CUtensorMap* tmI0 = nullptr, const CUtensorMap* tmI1 = nullptr) {
     p.tiles_m = (p.M + BM - 1) / BM;
@@ -809,13 +819,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaSt
     p.kchunks_per_split = (p.kchunks + p.ksplit - 1) / p.ksplit;
     p.ksplit = (p.kchunks + p.kchunks_per_split - 1) / p.kchunks_per_split;
     if (p.ksplit > 1) p.use_atomics = 1;
-    auto kern = gemm_tc_kernel<AMN, BMN, EPI, NCTA>;
-    const int smem_bytes = (int)SmemT<epi_stages(EPI)>::total + 1024;
+    auto kern = gemm_tc_kernel<AMN, BMN, EPI, NCTA, NEW>;
+    const int smem_bytes = (int)SmemT<(NEW == 16 ? 3 : epi_stages(EPI)), NEW / 4, epi_has_input(EPI)>::total + 1024;
     MMDTI_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const int sms = num_sms();
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(64 + NEW * 32);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     if (NCTA == 1) {
@@ -875,6 +885,8 @@ extern "C" int mmdti_gemm_bias(const void* X, int64_t ldx, const void* W, int64_
     if (int rc = make_out_map(&tmY, Y, M, N, ldy, false)) return rc;
     if (bias) {
         MMDTI_REQUIRE(mmdti_aligned(bias, 16), "gemm_bias: bias must be 16-byte aligned");
+        static const bool epi16 = getenv("MMDTI_GEMM_BIAS16") && atoi(getenv("MMDTI_GEMM_BIAS16")) != 0;
+        if (epi16) return launch<0, 0, EPI_BIAS, 1, 16>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmY);
         return launch<0, 0, EPI_BIAS, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmY);
     }
     return launch<0, 0, EPI_STORE, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmY);
@@ -897,6 +909,9 @@ extern "C" int mmdti_gemm_bias_gelu(const void* X, int64_t ldx, const void* W, i
     CUtensorMap tmZ, tmU;
     if (int rc = make_out_map(&tmZ, Z, M, N, ldz, false)) return rc;
     if (int rc = make_out_map(&tmU, U, M, N, ldu, false)) return rc;
+    // the GELU epilogue is ALU-bound (2 MUFU + ~20 FMA per element): 16 epilogue warps (MMDTI_GEMM_EPI16=0: 8)
+    static const bool epi16 = !(getenv("MMDTI_GEMM_EPI16") && atoi(getenv("MMDTI_GEMM_EPI16")) == 0);
+    if (epi16) return launch<0, 0, EPI_BIAS_GELU, 1, 16>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmZ, &tmU);
     return launch<0, 0, EPI_BIAS_GELU, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmZ, &tmU);
 }
 
@@ -961,6 +976,8 @@ extern "C" int mmdti_gemm_dgrad_gelu(const void* dY, int64_t lddy, const void* W
     CUtensorMap tmDZ, tmZ;
     if (int rc = make_out_map(&tmDZ, dZ, M, K, lddz, false)) return rc;
     if (int rc = make_out_map(&tmZ, Z, M, K, ldz, false)) return rc;
+    static const bool epi16 = !(getenv("MMDTI_GEMM_EPI16") && atoi(getenv("MMDTI_GEMM_EPI16")) == 0);
+    if (epi16) return launch<0, 1, EPI_GELU_BWD, 1, 16>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmDZ, nullptr, &tmZ);
     return launch<0, 1, EPI_GELU_BWD, 1>(tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmDZ, nullptr, &tmZ);
 }
 
