@@ -22,3 +22,15 @@ extern "C" int mmdti_set_seed_offset(const uint64_t* device_counter) {
     g_seed_off = reinterpret_cast<const unsigned long long*>(device_counter);
     return MMDTI_OK;
 }
+
+int* mmdti_sched_slot() {
+    constexpr int SLOTS = 16384;
+    static int* base[MMDTI_MAX_DEVICES] = {};
+    static unsigned next[MMDTI_MAX_DEVICES] = {};
+    const int dev = mmdti_device_slot();
+    if (!base[dev]) {
+        if (cudaMalloc(&base[dev], SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+        if (cudaMemset(base[dev], 0, SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
+    }
+    return base[dev] + 2 * (next[dev]++ % SLOTS);
+}

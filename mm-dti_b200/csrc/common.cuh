@@ -46,6 +46,12 @@ static inline int mmdti_device_slot() {
     return dev >= 0 && dev < MMDTI_MAX_DEVICES ? dev : 0;
 }
 
+// Scheduler counters of the persistent kernels with dynamic work distribution (gemm_tc.cu, pair_attn.cu backward): a
+// zero-initialised ring of {next item, CTAs done} pairs in device memory, one pair per launch.  A kernel re-arms its pair when
+// its last CTA retires, so a CUDA-graph replay (which re-runs the same launch with the same pair) finds it zeroed; the ring is
+// long enough that a pair is never shared by two launches in flight.  NULL on allocation failure.
+int* mmdti_sched_slot();
+
 // ---------------------------------------------------------------- type helpers
 typedef __nv_bfloat16 bf16;
 

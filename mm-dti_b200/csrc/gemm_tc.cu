@@ -796,17 +796,7 @@ int make_out_map(CUtensorMap* map, const void* base, long long rows, long long c
 // Scheduler counters: a zero-initialised ring of {next item, CTAs done} pairs in device memory, one pair per launch.  The
 // kernel re-arms its pair when its last CTA retires, so a CUDA-graph replay (which re-runs the same launch with the same
 // pair) finds it zeroed; the ring is long enough that a pair is never shared by two launches in flight.
-int* sched_slot() {
-    constexpr int SLOTS = 16384;
-    static int* base[MMDTI_MAX_DEVICES] = {};
-    static unsigned next[MMDTI_MAX_DEVICES] = {};
-    const int dev = mmdti_device_slot();
-    if (!base[dev]) {
-        if (cudaMalloc(&base[dev], SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
-        if (cudaMemset(base[dev], 0, SLOTS * 2 * sizeof(int)) != cudaSuccess) return nullptr;
-    }
-    return base[dev] + 2 * (next[dev]++ % SLOTS);
-}
+int* sched_slot() { return mmdti_sched_slot(); }
 
 template <int AMN, int BMN, int EPI, int NCTA, int NEW = NUM_EPI_WARPS>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st, const CUtensorMap* tmO0 = nullptr,

@@ -63,6 +63,8 @@ struct BwdParams {
     unsigned long long seed;
     const unsigned long long* seed_off;
     int crb, nchunks;
+    int* sched;       // {next pool tile, CTAs done}: dynamic tile scheduler of the backward (NULL: static contiguous ranges)
+    int pool;         // tiles handed out dynamically (the LAST `pool` tiles); the others are split into contiguous ranges
 };
 
 // two adjacent pair elements (col even) of a slab row -> floats
@@ -633,14 +635,11 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
 
     const int ntiles = p.B * p.H;
     const int t0 = (int)((long long)ntiles * blockIdx.x / gridDim.x), t1 = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
-    const int w0 = t0 * p.nchunks, w1 = t1 * p.nchunks;
-    const FastDiv div_h((uint32_t)p.H), div_c((uint32_t)p.nchunks);
+    const FastDiv div_h((uint32_t)p.H);
     const size_t tile_elems = (size_t)L * G::STRIDE;
     const bool has_dpo = p.dpout != nullptr;
 
-    auto prefetch = [&](int w, int s) {
-        const int tile = (int)div_c.div((uint32_t)w);
-        const int chunk = w - tile * p.nchunks;
+    auto prefetch = [&](int tile, int chunk, int s) {
         const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
         if (tid == 0) {
@@ -675,23 +674,53 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
     const unsigned long long eff_seed = do_drop ? rng_effective_seed(p.seed, p.seed_off) : 0ull;      // once per kernel
     float dk_acc[MAXKB16][4], dv_acc[MAXKB16][4];
 
-    if (w0 < w1) prefetch(w0, 0);
-    int it = 0;
-    for (int w = w0; w < w1; ++w, ++it) {
+    // Work distribution.  A tile = one (molecule, head) with all its row chunks (dK / dV accumulate across the chunks).
+    // p.sched == NULL: every CTA walks a contiguous range of tiles (consecutive heads of a molecule share the cache lines of
+    // their q / k / v rows).  Otherwise only the first ntiles - p.pool tiles are split that way and the last p.pool tiles are
+    // handed out DYNAMICALLY from a global counter once a CTA has finished its range, so CTAs that share their SM with a kernel
+    // of another stream -- the NCCL all-reduce of the gradient buckets, the weight-gradient GEMMs of the side stream -- shed
+    // work instead of holding the whole kernel back.  Tile ids travel two ahead through s_tile[] (thread 0 fetches the id of
+    // the tile after next while the current tile computes), so the atomic's latency is never exposed.
+    __shared__ int s_tile[2];
+    const bool dyn = p.sched != nullptr;
+    const int nstat_all = ntiles - p.pool;
+    const int st0 = (int)((long long)nstat_all * blockIdx.x / gridDim.x), st1 = (int)((long long)nstat_all * (blockIdx.x + 1) / gridDim.x);
+    int n_fetched = 0;                                   // thread 0: ids taken so far
+    auto next_id = [&]() -> int {                        // thread 0 only
+        const int k = n_fetched++;
+        return st0 + k < st1 ? st0 + k : nstat_all + atomicAdd(p.sched, 1);
+    };
+    int tile = t0, chunk = 0, kt = 0, fetched = 0;
+    if (dyn) {
+        if (tid == 0) {
+            s_tile[0] = next_id();
+            s_tile[1] = next_id();
+        }
+        __syncthreads();
+        tile = s_tile[0];
+    }
+    const int tile_end = dyn ? ntiles : t1;
+    if (tile < tile_end) prefetch(tile, 0, 0);
+    for (int it = 0; tile < tile_end; ++it) {
         const int s = it & 1;
-        const int tile = (int)div_c.div((uint32_t)w);
-        const int chunk = w - tile * p.nchunks;
         const int b = (int)div_h.div((uint32_t)tile), h = tile - b * p.H;
         const int row0 = chunk * NR, nrows = min(L - row0, NR);
         const int nrb_chunk = (nrows + 15) >> 4;
 
         cp_async_wait<0>();
         mbar_wait(&full_bar[s], (it >> 1) & 1);
-        __syncthreads();        // item w resident; item w-1 (incl. its phase 2 readers) finished everywhere
-        if (w + 1 < w1) {
-            if (tid == 0) bulk_wait_read<0>();
-            prefetch(w + 1, s ^ 1);
+        __syncthreads();        // item resident; the previous item (incl. its phase 2 readers) finished everywhere
+        int ntile = tile, nchunk = chunk + 1;
+        if (nchunk == p.nchunks) {
+            nchunk = 0;
+            ntile = dyn ? s_tile[(kt + 1) & 1] : tile + 1;
         }
+        if (ntile < tile_end) {
+            if (tid == 0) bulk_wait_read<0>();
+            prefetch(ntile, nchunk, s ^ 1);
+        }
+        const bool fetch_now = dyn && chunk == 0 && tid == 0;
+        if (fetch_now) fetched = next_id();                  // id of tile kt + 2; stored at the end of this item
 
         if (chunk == 0) {
 #pragma unroll
@@ -1193,8 +1222,20 @@ __global__ void __launch_bounds__(256, CS ? 2 : 1) pair_attn_bwd_kernel(const Bw
                 }
             }
         }
+        // slot kt & 1 held this tile's id, which everybody read before the barrier at the top of this item
+        if (fetch_now) s_tile[kt & 1] = fetched;
+        if (nchunk == 0) ++kt;
+        tile = ntile;
+        chunk = nchunk;
     }
-    if (tid == 0) bulk_wait_all<0>();
+    if (tid == 0) {
+        bulk_wait_all<0>();
+        if (dyn) {
+            // the last CTA to finish re-arms the counters for the next launch that uses this pair (CUDA-graph replays)
+            __threadfence();
+            if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ debug: keep mask (dense (B,H,L,L))
@@ -1309,6 +1350,16 @@ int launch_bwd(BwdParams p, cudaStream_t st) {
     if (p.nchunks > 1)
         while (p.crb > 2 && smem_of(p.crb) > 113 * 1024) --p.crb;
     if (const char* e = getenv("MMDTI_K2_BWD_CRB")) p.crb = std::max(1, std::min(p.crb, atoi(e)));      // tuning knob
+    // dynamic tile scheduler (see the kernel): MMDTI_K2_BWD_DYN = fraction of the tiles in the dynamic pool, 0 .. 1.  Default 0
+    // (static contiguous ranges: fastest when nothing else runs on the SMs).  Measured at N = 4 under the overlapped NCCL
+    // all-reduce: 0.3 brings the launch from 203 to 141 us, but the step stays at 9.6 ms (the all-reduce, not K2, is what the
+    // backward waits for), so it stays off.
+    {
+        const char* e = getenv("MMDTI_K2_BWD_DYN");
+        const double frac = e ? std::min(1.0, std::max(0.0, atof(e))) : 0.0;
+        p.pool = (int)(frac * (double)p.B * (double)p.H);
+        p.sched = p.pool > 0 ? mmdti_sched_slot() : nullptr;
+    }
     const int nkb16 = (p.L + 15) / 16;
     if constexpr (!F32 && NKB >= 25) {
         // column-split phase 1 (see the kernel): 8 warps, 32-row chunks, two CTAs per SM

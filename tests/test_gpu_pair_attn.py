@@ -209,3 +209,36 @@ def test_column_split_matches_row_split(L, pdt, monkeypatch):
         assert (dp0 - dp1).abs().max() <= 2 ** -7 * dp0.abs().max()
         assert (dq0 - dq1).abs().max() <= 2 ** -6 * dq0.abs().max()
         assert (dp0 - dp1).abs().mean() <= 1e-4 * dp0.abs().mean() and (dq0 - dq1).abs().mean() <= 2e-3 * dq0.abs().mean()
+
+
+@pytest.mark.parametrize("B,L", [(12, 66), (3, 258), (1, 20)])
+def test_bwd_dynamic_tile_scheduler_is_bit_identical(B, L, monkeypatch):
+    """MMDTI_K2_BWD_DYN hands the last fraction of the (molecule, head) tiles out from a global counter instead of splitting
+    all of them into contiguous ranges (the data-parallel bench turns it on).  Which CTA runs a tile does not enter its math:
+    every output must be bit-identical for any pool fraction, launch after launch (the counter re-arms itself)."""
+    from mmdti_b200 import ops
+    from mmdti_b200._lib import DTYPE_CODE, call, f32, i32, i64, stream_ptr, u64
+    H, D, p, seed = 64, 512, 0.1, 99
+    Lp = ops.pair_ld(L)
+    g = torch.Generator(device="cuda").manual_seed(L + B)
+    qkv = (torch.randn(B * L, 3 * D, device="cuda", generator=g) * 0.5).bfloat16()
+    pair = torch.randn(B, H, L, Lp, device="cuda", generator=g).bfloat16()
+    pair[..., L:] = float("-inf")
+    d_o = (torch.randn(B * L, D, device="cuda", generator=g) * 0.1).bfloat16()
+    dpo = (torch.randn(B, H, L, Lp, device="cuda", generator=g) * 0.01).bfloat16()
+    dpo[..., L:] = 0
+    code = DTYPE_CODE[torch.bfloat16]
+    pout, o = torch.empty_like(pair), torch.empty((B * L, D), device="cuda", dtype=torch.bfloat16)
+    call("mmdti_pair_attn_fwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pair, pout, o, i64(D), i32(B), i32(H), i32(L),
+         f32(8 ** -0.5), f32(p), u64(seed), i32(code), i32(code), stream_ptr())
+    res = []
+    for frac in ("0", "0.3", "1", "0.3"):
+        monkeypatch.setenv("MMDTI_K2_BWD_DYN", frac)
+        dpi, dqkv = torch.full_like(pair, 7.0), torch.full_like(qkv, 7.0)
+        call("mmdti_pair_attn_bwd", qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], i64(3 * D), pout, o, d_o, i64(D), dpo, dpi,
+             dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], i64(3 * D), i32(B), i32(H), i32(L), f32(8 ** -0.5), f32(p), u64(seed),
+             i32(code), i32(code), i32(code), stream_ptr())
+        torch.cuda.synchronize()
+        res.append((dpi[..., :L].clone(), dqkv.clone()))
+    for dpi, dqkv in res[1:]:
+        assert torch.equal(dpi, res[0][0]) and torch.equal(dqkv, res[0][1])
