@@ -414,7 +414,7 @@ def run_ours(args, rank, local_rank, world):
             ids_h = smiles_ids(1234 + rank)
             extra_params += list(bert.parameters())
         if FUSION:
-            from mmdti_b200.models.cross_modal import CrossAttentionModel, crossmodal_config, fuse_and_pool
+            from mmdti_b200.models.cross_modal import CrossAttentionModel, crossmodal_config
             cross = CrossAttentionModel(crossmodal_config(), num_layers=1).to(dev).train()
             extra_params += list(cross.parameters())
         dp_ctx = None

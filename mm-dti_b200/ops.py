@@ -433,8 +433,10 @@ class TokenEmbeddingFn(torch.autograd.Function):
 class EncoderLayerFn(torch.autograd.Function):
     """One pre-LN Uni-Core TransformerEncoderLayer with return_attn=True (SURVEY.md Appendix A;
     call site models/transformers.py:136-139) as a single autograd node with a hand-written
-    backward: LayerNorm / dropout+residual / GELU / bias-gradient reductions are mmdti kernels,
-    the four dense projections are library GEMMs (cuBLASLt), K2 is the pair-biased attention.
+    backward.  bf16 mode: the four dense projections, forward / dgrad / wgrad, are the tcgen05 GEMMs of csrc/gemm_tc.cu whose
+    epilogues carry LayerNorm, dropout + residual, GELU and the bias / LayerNorm column sums (ops_gemm; `MMDTI_FUSED` selects
+    a subset); fp32 validation mode: fp32 library GEMMs around the stand-alone elementwise kernels.  K2 is the pair-biased
+    attention.
     x (B,L,D) f32 residual stream; pair_in padded (B,H,L,Lp)."""
 
     @staticmethod

@@ -102,7 +102,9 @@ def flat_dropout(x, p, training):
 
 class CrossLayerFn(torch.autograd.Function):
     """layer(s1, s2, mask2) of BertCrossAttentionLayer: q from s1 (B, L1, D), keys / values from s2 (B, L2, D), post-LN.
-    Returns the layer output (B, L1, D) in the activation dtype."""
+    Returns the layer output (B, L1, D): in the activation dtype, or -- cfg[6] -- as a fresh fp32 tensor (what the reference's
+    LayerNorm yields under autocast; its caller writes into it in place).  s2 may be s1 (self-attention: the RoBERTa layers
+    of models/chemberta.py)."""
 
     @staticmethod
     def forward(ctx, s1, s2, mask2, wq, bq, wk, bk, wv, bv, wo, bo, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b, cfg):
