@@ -224,3 +224,20 @@ def test_chemberta_encoder_dispatch_and_checkpoint_loading(tmp_path):
         warnings.simplefilter("always")
         stock = ChembertaEncoder(big)
     assert type(stock.bert).__module__.startswith("transformers") and any("stock HF" in str(x.message) for x in w)
+
+
+def test_cross_modal_dropin_has_the_reference_state_dict_and_config():
+    """models/mm_model.py:361-406: the drop-in fusion block exposes exactly the parameter names and shapes of the reference's
+    CrossAttentionModel, and crossmodal_config() the reference's values (needs a copy of the reference tree)."""
+    import pytest
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no copy of the reference tree on this machine")
+    mm = ref_loader.load()["mm_model"]
+    from mmdti_b200.models.cross_modal import CrossAttentionModel, crossmodal_config
+    ref_cfg, cfg = mm.crossmodal_config(), crossmodal_config()
+    for k, v in vars(cfg).items():
+        assert getattr(ref_cfg, k) == v, k
+    want = {k: tuple(v.shape) for k, v in mm.CrossAttentionModel(ref_cfg, num_layers=2).state_dict().items()}
+    got = {k: tuple(v.shape) for k, v in CrossAttentionModel(cfg, num_layers=2).state_dict().items()}
+    assert got == want
