@@ -618,6 +618,7 @@ int ca_check(const void* q, const void* k, const void* v, const uint8_t* kmask, 
                       "cross_attn: bf16 operands need 16-byte aligned rows");
     } else {
         MMDTI_REQUIRE(hd > 0 && hd <= 256, "cross_attn: head_dim out of range");
+        MMDTI_REQUIRE(Lq <= 1536, "cross_attn: the f32 validation path stages 2 * Lq floats per warp in 48 KB of shared memory (Lq = %d)", Lq);
     }
     return MMDTI_OK;
 }
